@@ -1,0 +1,468 @@
+// GGUF block packers / unpackers for sm_100a.  Compiled with --fmad=false: every product
+// and sum below is a separately rounded fp32 op, in llama.cpp's source order, so the packed
+// bytes are bit-identical to the strict-IEEE oracle (oracle/ggml_quants.c).
+//
+// Replaces: the `llama-quantize` child process of the reference,
+//   ref/src/quantool/methods/llama_cpp/llama_cpp.py:165-178 (`GGUF._quantize_gguf`)
+// i.e. llama.cpp ggml-quants.c quantize_row_{q8_0,q4_0,q4_1,q5_0,q5_1,q4_K,q5_K,q6_K}_ref
+// and dequantize_row_* (§D.1-§D.5).
+//
+// Data layout in HBM: src is the tensor as a flat row-major array (rows are a multiple of the
+// block size, so blocks never straddle rows and the whole tensor is one array of blocks);
+// dst is the array of packed blocks, back to back, no padding (GGUF tensor data layout).
+//
+// Simple types (32-element blocks) are HBM-bound streaming kernels:
+//   4 lanes per block, one 128-bit load per lane (8 fp16/bf16 elements), 4 blocks in flight
+//   per thread, cross-lane reduction by shuffles, packed bytes staged in shared memory and
+//   written back with coalesced 128-bit stores.
+// K-quants (256-element super-blocks) run a 19-21 candidate scale search per sub-block with
+//   strictly ordered fp32 sums: ~500 ALU ops per element, so they are fp32-ALU-bound, not
+//   HBM-bound; one thread owns one sub-block, input/output staged through shared memory.
+#include "gguf_kquant.cuh"
+
+namespace qt {
+namespace gguf {
+
+enum : int {
+    T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14
+};
+
+__host__ __device__ constexpr int block_elems(int t) {
+    return (t == T_Q4_K || t == T_Q5_K || t == T_Q6_K) ? 256
+         : (t == T_Q4_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_Q8_0) ? 32 : -1;
+}
+__host__ __device__ constexpr int block_bytes(int t) {
+    return t == T_Q4_0 ? 18 : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q8_0 ? 34
+         : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210 : -1;
+}
+
+QT_D void sts16(uint8_t* p, uint32_t v) { *reinterpret_cast<unsigned short*>(p) = (unsigned short)v; }
+
+// spread the 4 nibbles of a 16-bit value into the low nibbles of 4 bytes
+QT_D uint32_t spread4(uint32_t v) {
+    return (v & 0xFu) | ((v & 0xF0u) << 4) | ((v & 0xF00u) << 8) | ((v & 0xF000u) << 12);
+}
+
+// copy `bytes` from shared staging to global with 128-bit stores (+ byte tail on the last CTA)
+QT_D void copy_out(uint8_t* __restrict__ gdst, const uint8_t* sout, int bytes) {
+    const int nvec = bytes >> 4;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+        stg_stream(gdst + 16 * i, *reinterpret_cast<const uint4*>(sout + 16 * i));
+    for (int i = (nvec << 4) + threadIdx.x; i < bytes; i += blockDim.x) gdst[i] = sout[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// 32-element block types.  256 threads = 64 blocks per pass, U passes per CTA iteration.
+// ---------------------------------------------------------------------------------------
+constexpr int kSimpleU = 4;
+constexpr int kSimpleBlocksPerCta = 64 * kSimpleU;  // 256 blocks: 256*BB is a multiple of 16
+
+template <int TYPE>
+QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
+    // lane q (0..3) of the block holds elements 8q..8q+7 in v
+    if (TYPE == T_Q8_0) {
+        float amax = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        const float d = amax / 127;
+        const float id = d ? 1.0f / d : 0.0f;
+        uint32_t w[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int qi = (int)roundf(v[i] * id);
+            w[i >> 2] |= (uint32_t)(qi & 0xff) << (8 * (i & 3));
+        }
+        if (q == 0) sts16(o, __half_as_ushort(__float2half_rn(d)));
+        uint8_t* qs = o + 2 + 8 * q;
+        sts16(qs, w[0] & 0xffff); sts16(qs + 2, w[0] >> 16);
+        sts16(qs + 4, w[1] & 0xffff); sts16(qs + 6, w[1] >> 16);
+        return;
+    }
+    constexpr bool kSym = (TYPE == T_Q4_0 || TYPE == T_Q5_0);
+    constexpr bool k5 = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
+    constexpr int kHdr = kSym ? 2 : 4;
+    uint32_t nib = 0;   // 8 low nibbles
+    uint32_t hb = 0;    // 8 high bits (5-bit types)
+    if (kSym) {
+        // first element with the largest |v| wins (strict < in a forward scan)
+        float amax = 0.0f, mx = 0.0f;
+        int idx = 8 * q;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float a = fabsf(v[i]);
+            if (amax < a) { amax = a; mx = v[i]; idx = 8 * q + i; }
+        }
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1) {
+            const float oa = __shfl_xor_sync(0xffffffffu, amax, off);
+            const float om = __shfl_xor_sync(0xffffffffu, mx, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+            if (oa > amax || (oa == amax && oi < idx)) { amax = oa; mx = om; idx = oi; }
+        }
+        const float d = mx / (k5 ? -16 : -8);
+        const float id = d ? 1.0f / d : 0.0f;
+        if (q == 0) sts16(o, __half_as_ushort(__float2half_rn(d)));
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float x0 = v[i] * id;
+            int xi = (int)(signed char)(int)(x0 + (k5 ? 16.5f : 8.5f));
+            xi = xi < (k5 ? 31 : 15) ? xi : (k5 ? 31 : 15);
+            nib |= (uint32_t)(xi & 0xF) << (4 * i);
+            hb |= (uint32_t)((xi >> 4) & 1) << i;
+        }
+    } else {
+        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { mn = fminf(mn, v[i]); mx = fmaxf(mx, v[i]); }
+#pragma unroll
+        for (int off = 1; off <= 2; off <<= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        }
+        const float d = (mx - mn) / (k5 ? 31 : 15);
+        const float id = d ? 1.0f / d : 0.0f;
+        if (q == 0) {
+            sts16(o, __half_as_ushort(__float2half_rn(d)));
+            sts16(o + 2, __half_as_ushort(__float2half_rn(mn)));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float x0 = (v[i] - mn) * id;
+            int xi;
+            if (k5) {
+                xi = (int)(unsigned char)(int)(x0 + 0.5f);
+            } else {
+                xi = (int)(signed char)(int)(x0 + 0.5f);
+                xi = xi < 15 ? xi : 15;
+            }
+            nib |= (uint32_t)(xi & 0xF) << (4 * i);
+            hb |= (uint32_t)((xi >> 4) & 1) << i;
+        }
+    }
+    // byte j (j<16) = elem j (low nibble) | elem j+16 (high nibble): lanes 0,1 own j = 8q+i
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, nib, 2);
+    if (k5) {
+        uint32_t qh = hb << (8 * q);   // bit (8q+i): lanes 0,1 -> elems 0..15, lanes 2,3 -> elems 16..31
+        qh |= __shfl_xor_sync(0xffffffffu, qh, 1);
+        qh |= __shfl_xor_sync(0xffffffffu, qh, 2);
+        if (q == 0) { sts16(o + kHdr, qh & 0xffff); sts16(o + kHdr + 2, qh >> 16); }
+    }
+    if (q < 2) {
+        const uint32_t w0 = spread4(nib & 0xffff) | (spread4(other & 0xffff) << 4);
+        const uint32_t w1 = spread4(nib >> 16) | (spread4(other >> 16) << 4);
+        uint8_t* qs = o + kHdr + (k5 ? 4 : 0) + 8 * q;
+        sts16(qs, w0 & 0xffff); sts16(qs + 2, w0 >> 16);
+        sts16(qs + 4, w1 & 0xffff); sts16(qs + 6, w1 >> 16);
+    }
+}
+
+template <int TYPE, int DT, bool VIA_F16>
+__global__ void __launch_bounds__(256) pack_simple_kernel(const void* __restrict__ src,
+                                                          uint8_t* __restrict__ dst, int64_t nblocks) {
+    constexpr int BB = block_bytes(TYPE);
+    __shared__ __align__(16) uint8_t sout[kSimpleBlocksPerCta * BB];
+    const int tid = threadIdx.x, q = tid & 3, bl = tid >> 2;
+    for (int64_t base = (int64_t)blockIdx.x * kSimpleBlocksPerCta; base < nblocks;
+         base += (int64_t)gridDim.x * kSimpleBlocksPerCta) {
+        float v[kSimpleU][8];
+#pragma unroll
+        for (int u = 0; u < kSimpleU; u++) {
+            const int64_t blk = base + u * 64 + bl;
+            if (blk < nblocks) {
+                load8<DT>(src, blk * 4 + q, v[u]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[u][i] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSimpleU; u++) {
+            if (VIA_F16 && DT != QT_F16) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[u][i] = round_via_f16(v[u][i]);
+            }
+            pack_simple_block<TYPE>(v[u], q, sout + (u * 64 + bl) * BB);
+        }
+        __syncthreads();
+        const int64_t left = nblocks - base;
+        const int nvalid = left < kSimpleBlocksPerCta ? (int)left : kSimpleBlocksPerCta;
+        copy_out(dst + base * BB, sout, nvalid * BB);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K-quants
+// ---------------------------------------------------------------------------------------
+// stage NELEM consecutive elements (from super-block `sb0`) into s.x rows of ROW elements
+template <int DT, bool VIA_F16, int ROW, int PAD, int NELEM>
+QT_D void stage_in(const void* __restrict__ src, int64_t elem0, int64_t nvalid_elems, float (*sx)[PAD]) {
+    for (int c = threadIdx.x; c < NELEM / 8; c += blockDim.x) {
+        float v[8];
+        if ((int64_t)c * 8 < nvalid_elems) {
+            load8<DT>(src, elem0 / 8 + c, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = 0.f;
+        }
+        const int e = c * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float f = v[i];
+            if (VIA_F16 && DT != QT_F16) f = round_via_f16(f);
+            sx[(e + i) / ROW][(e + i) % ROW] = f;
+        }
+    }
+}
+
+constexpr int kK45Nsb = 32;  // 256 threads, 32 super-blocks (8192 elements) per CTA iteration
+constexpr int kK6Nsb = 16;   // 256 threads, 16 super-blocks (4096 elements)
+
+template <int TYPE, int DT, bool VIA_F16>
+__global__ void __launch_bounds__(256) pack_k45_kernel(const void* __restrict__ src, uint8_t* __restrict__ dst,
+                                                       int64_t nsuper) {
+    constexpr int BB = block_bytes(TYPE);
+    using S = kq::K45Shared<kK45Nsb, BB>;
+    __shared__ S s;
+    const int t = threadIdx.x;
+    constexpr int nmax = TYPE == T_Q4_K ? 15 : 31;
+    for (int64_t base = (int64_t)blockIdx.x * kK45Nsb; base < nsuper; base += (int64_t)gridDim.x * kK45Nsb) {
+        const int64_t left = nsuper - base;
+        const int nvalid = left < kK45Nsb ? (int)left : kK45Nsb;
+        stage_in<DT, VIA_F16, 32, 33, kK45Nsb * 256>(src, base * 256, (int64_t)nvalid * 256, s.u.x);
+        __syncthreads();
+        kq::K45Thread th;
+        if (TYPE == T_Q4_K) kq::k45_phase_a(t, s, th, 15, -1.f, 0.1f, 20);
+        else                kq::k45_phase_a(t, s, th, 31, -0.5f, 0.1f, 15);
+        __syncthreads();
+        kq::k45_phase_b<S, BB>(t, s, th, nmax);
+        __syncthreads();
+        if (TYPE == T_Q4_K) kq::q4k_phase_c(t, s); else kq::q5k_phase_c(t, s);
+        __syncthreads();
+        copy_out(dst + base * BB, s.u.o.out, nvalid * BB);
+        __syncthreads();
+    }
+}
+
+template <int DT, bool VIA_F16>
+__global__ void __launch_bounds__(256) pack_q6k_kernel(const void* __restrict__ src, uint8_t* __restrict__ dst,
+                                                       int64_t nsuper) {
+    using S = kq::K6Shared<kK6Nsb>;
+    __shared__ S s;
+    const int t = threadIdx.x;
+    for (int64_t base = (int64_t)blockIdx.x * kK6Nsb; base < nsuper; base += (int64_t)gridDim.x * kK6Nsb) {
+        const int64_t left = nsuper - base;
+        const int nvalid = left < kK6Nsb ? (int)left : kK6Nsb;
+        stage_in<DT, VIA_F16, 16, 17, kK6Nsb * 256>(src, base * 256, (int64_t)nvalid * 256, s.x);
+        __syncthreads();
+        kq::K6Thread th;
+        kq::q6k_phase_a(t, s, th);
+        __syncthreads();
+        kq::q6k_phase_b(t, s, th);
+        __syncthreads();
+        kq::q6k_phase_c(t, s);
+        __syncthreads();
+        copy_out(dst + base * 210, s.out, nvalid * 210);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// dequantize: one thread per 16 (simple) / 32 (K) output elements; packed blocks are read
+// byte-wise through the read-only path (they are 2-byte aligned at best), outputs are
+// written as 128-bit stores.  Expressions follow llama.cpp dequantize_row_* / gguf-py.
+// ---------------------------------------------------------------------------------------
+QT_D float ld_f16(const uint8_t* p) {
+    return __half2float(__ushort_as_half((unsigned short)(p[0] | (p[1] << 8))));
+}
+QT_D void st_f4(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(256) dequant_simple_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                             int64_t nblocks) {
+    constexpr int BB = block_bytes(TYPE);
+    // two threads per block: half h covers output elements 16h..16h+15
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t blk = gid >> 1;
+    const int h = (int)(gid & 1);
+    if (blk >= nblocks) return;
+    const uint8_t* b = src + blk * BB;
+    float* y = dst + blk * 32 + 16 * h;
+    float out[16];
+    if (TYPE == T_Q8_0) {
+        const float d = ld_f16(b);
+#pragma unroll
+        for (int j = 0; j < 16; j++) out[j] = (float)(int)(signed char)b[2 + 16 * h + j] * d;
+    } else {
+        constexpr bool kSym = (TYPE == T_Q4_0 || TYPE == T_Q5_0);
+        constexpr bool k5 = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
+        constexpr int kHdr = kSym ? 2 : 4;
+        const float d = ld_f16(b);
+        const float m = kSym ? 0.f : ld_f16(b + 2);
+        uint32_t qh = 0;
+        if (k5) qh = b[kHdr] | (b[kHdr + 1] << 8) | (b[kHdr + 2] << 16) | ((uint32_t)b[kHdr + 3] << 24);
+        const uint8_t* qs = b + kHdr + (k5 ? 4 : 0);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            int x = h ? (qs[j] >> 4) : (qs[j] & 0xF);
+            if (k5) x |= (int)((qh >> (j + 16 * h)) & 1) << 4;
+            if (kSym) out[j] = (float)(x - (k5 ? 16 : 8)) * d;
+            else out[j] = (float)x * d + m;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) st_f4(y + j, out[j], out[j + 1], out[j + 2], out[j + 3]);
+}
+
+QT_D void scale_min_k4(int j, const uint8_t* q, int& d, int& m) {
+    if (j < 4) { d = q[j] & 63; m = q[j + 4] & 63; }
+    else { d = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4); m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(256) dequant_k_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                        int64_t nsuper) {
+    constexpr int BB = block_bytes(TYPE);
+    // 8 threads per super-block, thread j covers output elements 32j..32j+31
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t sb = gid >> 3;
+    const int j = (int)(gid & 7);
+    if (sb >= nsuper) return;
+    const uint8_t* b = src + sb * BB;
+    float* y = dst + sb * 256 + 32 * j;
+    float out[32];
+    if (TYPE == T_Q4_K || TYPE == T_Q5_K) {
+        const float d = ld_f16(b), mn = ld_f16(b + 2);
+        int sc, m;
+        scale_min_k4(j, b + 4, sc, m);
+        const float d1 = d * sc, m1 = mn * m;
+        const int c = j >> 1, hi = j & 1;
+        const uint8_t* q = b + (TYPE == T_Q4_K ? 16 : 48) + 32 * c;
+        const uint8_t* qh = b + 16;
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+            int x = hi ? (q[l] >> 4) : (q[l] & 0xF);
+            if (TYPE == T_Q5_K) x += ((qh[l] >> j) & 1) ? 16 : 0;
+            out[l] = d1 * x - m1;
+        }
+    } else {  // Q6_K: element e = 32j + l -> half n=e/128, quarter k=(e%128)/32
+        const float d = ld_f16(b + 208);
+        const int n = j >> 2, k = j & 3;
+        const uint8_t* ql = b + 64 * n;
+        const uint8_t* qh = b + 128 + 32 * n;
+        const int8_t* sc = reinterpret_cast<const int8_t*>(b + 192) + 8 * n;
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+            const int is = l / 16;
+            const int lo = (k & 1) ? ql[l + 32] : ql[l];
+            const int nibble = (k >= 2) ? (lo >> 4) : (lo & 0xF);
+            const int q = (int)(signed char)(nibble | (((qh[l] >> (2 * k)) & 3) << 4)) - 32;
+            out[l] = d * sc[is + 2 * k] * q;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 32; l += 4) st_f4(y + l, out[l], out[l + 1], out[l + 2], out[l + 3]);
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------
+static int grid_for(int64_t units_per_cta_iter_total, int ctas_per_sm) {
+    const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+    return (int)(units_per_cta_iter_total < cap ? (units_per_cta_iter_total > 0 ? units_per_cta_iter_total : 1) : cap);
+}
+
+template <int TYPE, int DT, bool VIA>
+static void launch_pack(const void* src, uint8_t* dst, int64_t nblk, cudaStream_t st) {
+    if constexpr (block_elems(TYPE) == 32) {
+        const int64_t iters = (nblk + kSimpleBlocksPerCta - 1) / kSimpleBlocksPerCta;
+        pack_simple_kernel<TYPE, DT, VIA><<<grid_for(iters, 8), 256, 0, st>>>(src, dst, nblk);
+    } else if constexpr (TYPE == T_Q6_K) {
+        const int64_t iters = (nblk + kK6Nsb - 1) / kK6Nsb;
+        pack_q6k_kernel<DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
+    } else {
+        const int64_t iters = (nblk + kK45Nsb - 1) / kK45Nsb;
+        pack_k45_kernel<TYPE, DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
+    }
+}
+
+template <int TYPE>
+static int dispatch_dt(const void* src, int dt, int via, uint8_t* dst, int64_t nblk, cudaStream_t st) {
+    switch (dt) {
+        case QT_F32: via ? launch_pack<TYPE, QT_F32, true>(src, dst, nblk, st) : launch_pack<TYPE, QT_F32, false>(src, dst, nblk, st); break;
+        case QT_F16: launch_pack<TYPE, QT_F16, false>(src, dst, nblk, st); break;
+        case QT_BF16: via ? launch_pack<TYPE, QT_BF16, true>(src, dst, nblk, st) : launch_pack<TYPE, QT_BF16, false>(src, dst, nblk, st); break;
+        default: return QT_ERR_INVALID;
+    }
+    return check_launch("qt_gguf_quantize");
+}
+
+}  // namespace gguf
+}  // namespace qt
+
+using namespace qt::gguf;
+
+extern "C" {
+
+int qt_gguf_block_elems(int ggml_type) { return block_elems(ggml_type); }
+int qt_gguf_block_bytes(int ggml_type) { return block_bytes(ggml_type); }
+
+int qt_gguf_quantize(int ggml_type, const void* src, int src_dtype, int round_via_f16, int64_t nrows,
+                     int64_t ncols, void* dst, void* stream) {
+    const int be = block_elems(ggml_type);
+    if (be < 0) return QT_ERR_UNSUPPORTED;
+    if (nrows < 0 || ncols < 0 || ncols % be) return QT_ERR_INVALID;
+    if (nrows == 0 || ncols == 0) return QT_OK;
+    if (!src || !dst || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return QT_ERR_INVALID;
+    const int64_t nblk = nrows * (ncols / be);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* d = (uint8_t*)dst;
+    switch (ggml_type) {
+        case T_Q4_0: return dispatch_dt<T_Q4_0>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q4_1: return dispatch_dt<T_Q4_1>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q5_0: return dispatch_dt<T_Q5_0>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q5_1: return dispatch_dt<T_Q5_1>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q8_0: return dispatch_dt<T_Q8_0>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q4_K: return dispatch_dt<T_Q4_K>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q5_K: return dispatch_dt<T_Q5_K>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q6_K: return dispatch_dt<T_Q6_K>(src, src_dtype, round_via_f16, d, nblk, st);
+    }
+    return QT_ERR_UNSUPPORTED;
+}
+
+int qt_gguf_dequantize(int ggml_type, const void* src, int64_t nrows, int64_t ncols, float* dst, void* stream) {
+    const int be = block_elems(ggml_type);
+    if (be < 0) return QT_ERR_UNSUPPORTED;
+    if (nrows < 0 || ncols < 0 || ncols % be) return QT_ERR_INVALID;
+    if (nrows == 0 || ncols == 0) return QT_OK;
+    if (!src || !dst || ((uintptr_t)dst & 15)) return QT_ERR_INVALID;
+    const int64_t nblk = nrows * (ncols / be);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* s = (const uint8_t*)src;
+    if (be == 32) {
+        const int64_t nthreads = nblk * 2;
+        const unsigned grid = (unsigned)((nthreads + 255) / 256);
+        switch (ggml_type) {
+            case T_Q4_0: dequant_simple_kernel<T_Q4_0><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_Q4_1: dequant_simple_kernel<T_Q4_1><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_Q5_0: dequant_simple_kernel<T_Q5_0><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_Q5_1: dequant_simple_kernel<T_Q5_1><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_Q8_0: dequant_simple_kernel<T_Q8_0><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+        }
+    } else {
+        const int64_t nthreads = nblk * 8;
+        const unsigned grid = (unsigned)((nthreads + 255) / 256);
+        switch (ggml_type) {
+            case T_Q4_K: dequant_k_kernel<T_Q4_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_Q5_K: dequant_k_kernel<T_Q5_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_Q6_K: dequant_k_kernel<T_Q6_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+        }
+    }
+    return qt::check_launch("qt_gguf_dequantize");
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// K-quant (Q4_K / Q5_K / Q6_K) block math, written as phase functions that run once per
+// thread with every cross-thread exchange going through a plain "shared" struct.  On the
+// GPU the struct lives in shared memory and phases are separated by __syncthreads(); the
+// host test harness (tests/host_emul.cu) runs the same phase functions in a loop over
+// thread ids, so the arithmetic is checked on the CPU against the oracle before any GPU time.
+//
+// Replaces the per-row work of `llama-quantize` launched by the reference at
+// ref/src/quantool/methods/llama_cpp/llama_cpp.py:165-178; algorithm = llama.cpp
+// ggml-quants.c quantize_row_q4_K_ref / q5_K_ref / q6_K_ref as recorded in SURVEY.md §D.4-§D.5.
+// Arithmetic contract: strict fp32 in the source evaluation order, no FMA contraction
+// (this translation unit is compiled with --fmad=false), IEEE div/sqrt, fp16 = RNE.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace qt {
+namespace kq {
+
+QT_HD int nearest_int(float fval) {
+    // 12582912.f magic constant: round-half-even for |f| < 2^22
+    float val = fval + 12582912.f;
+#ifdef __CUDA_ARCH__
+    int i = __float_as_int(val);
+#else
+    int i;
+    memcpy(&i, &val, sizeof(int));
+#endif
+    return (i & 0x007fffff) - 0x00400000;
+}
+
+QT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------------------------------
+// make_qkx2_quants(n=32, nmax, x, weights=av_x+|x|, rmin, rdelta, nstep, use_mad=false)
+// Thread-private.  Instead of keeping L[]/Laux[] arrays it remembers the (iscale, min)
+// pair the adopted candidate was generated with; L is regenerated from that pair on demand
+// (identical fp32 expression, so identical integers).
+// ------------------------------------------------------------------------------------
+struct Qkx2Result {
+    float scale;      // returned scale
+    float the_min;    // *the_min = -min
+    float l_iscale;   // L[i] = clamp(nearest_int(l_iscale * (x[i] - l_min)), 0, nmax)
+    float l_min;
+    int all_zero;     // max == min path: L = 0
+};
+
+QT_HD void qkx2_search(const float (&x)[32], int nmax, float rmin, float rdelta, int nstep, Qkx2Result& r) {
+    float sum_x2 = 0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) sum_x2 += x[l] * x[l];
+    const float av_x = sqrtf(sum_x2 / 32);
+
+    float mn = x[0], mx = x[0];
+    float sum_w = av_x + fabsf(x[0]);
+    float sum_x = sum_w * x[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) {
+        if (x[i] < mn) mn = x[i];
+        if (x[i] > mx) mx = x[i];
+        const float w = av_x + fabsf(x[i]);
+        sum_w += w;
+        sum_x += w * x[i];
+    }
+    if (mn > 0) mn = 0;
+    if (mx == mn) {
+        r.scale = 0.f; r.the_min = -mn; r.l_iscale = 0.f; r.l_min = mn; r.all_zero = 1;
+        return;
+    }
+    float iscale = nmax / (mx - mn);
+    float scale = 1 / iscale;
+    float best_error = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
+        float diff = scale * l + mn - x[i];
+        diff = diff * diff;
+        const float w = av_x + fabsf(x[i]);
+        best_error += w * diff;
+    }
+    r.l_iscale = iscale; r.l_min = mn; r.all_zero = 0;
+    for (int is = 0; is <= nstep; ++is) {
+        iscale = (rmin + rdelta * is + nmax) / (mx - mn);
+        float lf[32];
+        float sum_l = 0, sum_l2 = 0, sum_xl = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
+            lf[i] = (float)l;
+            const float w = av_x + fabsf(x[i]);
+            const float wl = w * lf[i];
+            sum_l += wl;
+            sum_l2 += wl * lf[i];
+            sum_xl += wl * x[i];
+        }
+        const float D = sum_w * sum_l2 - sum_l * sum_l;
+        if (D > 0) {
+            float this_scale = (sum_w * sum_xl - sum_x * sum_l) / D;
+            float this_min = (sum_l2 * sum_x - sum_l * sum_xl) / D;
+            if (this_min > 0) {
+                this_min = 0;
+                this_scale = sum_xl / sum_l2;
+            }
+            float cur_error = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float diff = this_scale * lf[i] + this_min - x[i];
+                diff = diff * diff;
+                const float w = av_x + fabsf(x[i]);
+                cur_error += w * diff;
+            }
+            if (cur_error < best_error) {
+                r.l_iscale = iscale; r.l_min = mn;   // the pair Laux was generated with
+                best_error = cur_error;
+                scale = this_scale;
+                mn = this_min;                       // C: `min = this_min` feeds later candidates
+            }
+        }
+    }
+    r.scale = scale;
+    r.the_min = -mn;
+}
+
+// ------------------------------------------------------------------------------------
+// Q4_K / Q5_K: NSB super-blocks per CTA, 8 threads per super-block (one per 32-elem sub-block)
+// ------------------------------------------------------------------------------------
+template <int NSB, int OUT_BYTES>
+struct K45Shared {
+    // x is dead once phase A has copied it to registers, so L/out alias it (48 KB static limit)
+    union {
+        float x[NSB * 8][33];    // +1 pad: thread t walks row t -> conflict-free
+        struct {
+            alignas(16) uint8_t out[NSB * OUT_BYTES];
+            uint8_t L[NSB][256];
+        } o;
+    } u;
+    float sc[NSB * 8];
+    float mn[NSB * 8];
+    uint8_t ls[NSB * 8];
+    uint8_t lm[NSB * 8];
+};
+
+struct K45Thread {
+    float x[32];
+    Qkx2Result r;
+};
+
+template <class S>
+QT_HD void k45_phase_a(int t, S& s, K45Thread& th, int nmax, float rmin, float rdelta, int nstep) {
+#pragma unroll
+    for (int l = 0; l < 32; ++l) th.x[l] = s.u.x[t][l];
+    qkx2_search(th.x, nmax, rmin, rdelta, nstep, th.r);
+    s.sc[t] = th.r.scale;
+    s.mn[t] = th.r.the_min;
+}
+
+template <class S, int OUT_BYTES>
+QT_HD void k45_phase_b(int t, S& s, const K45Thread& th, int nmax) {
+    const int sb = t >> 3, j = t & 7;
+    float max_scale = 0, max_min = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float scale = s.sc[sb * 8 + k];
+        if (scale > max_scale) max_scale = scale;
+        const float m = s.mn[sb * 8 + k];
+        if (m > max_min) max_min = m;
+    }
+    const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
+    const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
+    uint8_t ls = (uint8_t)nearest_int(inv_scale * th.r.scale);
+    uint8_t lm = (uint8_t)nearest_int(inv_min * th.r.the_min);
+    ls = ls < 63 ? ls : 63;
+    lm = lm < 63 ? lm : 63;
+    s.ls[t] = ls;
+    s.lm[t] = lm;
+    const __half dh = __float2half_rn(max_scale / 63.f);
+    const __half mh = __float2half_rn(max_min / 63.f);
+    if (j == 0) {
+        uint8_t* o = s.u.o.out + sb * OUT_BYTES;
+        const unsigned short db = __half_as_ushort(dh), mb = __half_as_ushort(mh);
+        o[0] = (uint8_t)(db & 0xff); o[1] = (uint8_t)(db >> 8);
+        o[2] = (uint8_t)(mb & 0xff); o[3] = (uint8_t)(mb >> 8);
+    }
+    // get_scale_min_k4 returns exactly (ls, lm) after the 6-bit packing round trip
+    const float d = __half2float(dh) * ls;
+    uint8_t* L = &s.u.o.L[sb][32 * j];
+    if (d != 0.f) {
+        const float dm = __half2float(mh) * lm;
+#pragma unroll
+        for (int ii = 0; ii < 32; ++ii) L[ii] = (uint8_t)clampi(nearest_int((th.x[ii] + dm) / d), 0, nmax);
+    } else if (th.r.all_zero) {
+#pragma unroll
+        for (int ii = 0; ii < 32; ++ii) L[ii] = 0;
+    } else {
+#pragma unroll
+        for (int ii = 0; ii < 32; ++ii)
+            L[ii] = (uint8_t)clampi(nearest_int(th.r.l_iscale * (th.x[ii] - th.r.l_min)), 0, nmax);
+    }
+}
+
+// scales[12] packing, common to Q4_K and Q5_K (block offset 4)
+template <class S, int OUT_BYTES>
+QT_HD void k45_pack_scales(int t, S& s) {
+    const int sb = t >> 3, j = t & 7;
+    uint8_t* sc = s.u.o.out + sb * OUT_BYTES + 4;
+    const uint8_t ls = s.ls[t], lm = s.lm[t];
+    if (j < 4) {
+        const uint8_t ls4 = s.ls[t + 4], lm4 = s.lm[t + 4];
+        sc[j] = (uint8_t)(ls | ((ls4 >> 4) << 6));
+        sc[j + 4] = (uint8_t)(lm | ((lm4 >> 4) << 6));
+    } else {
+        sc[j + 4] = (uint8_t)((ls & 0xF) | ((lm & 0xF) << 4));
+    }
+}
+
+template <class S>
+QT_HD void q4k_phase_c(int t, S& s) {
+    k45_pack_scales<S, 144>(t, s);
+    const int sb = t >> 3, j = t & 7;
+    // qs byte b (0..127): chunk c=b/32, l=b%32 -> L[64c+l] | L[64c+32+l]<<4 ; thread j: bytes 16j..16j+15
+    uint8_t* q = s.u.o.out + sb * 144 + 16 + 16 * j;
+    const int c = j >> 1, l0 = (j & 1) * 16;
+    const uint8_t* L = s.u.o.L[sb];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = (uint8_t)(L[64 * c + l0 + i] | (L[64 * c + 32 + l0 + i] << 4));
+}
+
+template <class S>
+QT_HD void q5k_phase_c(int t, S& s) {
+    k45_pack_scales<S, 176>(t, s);
+    const int sb = t >> 3, j = t & 7;
+    const uint8_t* L = s.u.o.L[sb];
+    uint8_t* qh = s.u.o.out + sb * 176 + 16;
+    uint8_t* ql = s.u.o.out + sb * 176 + 48 + 16 * j;
+    const int c = j >> 1, l0 = (j & 1) * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int l1 = L[64 * c + l0 + i], l2 = L[64 * c + 32 + l0 + i];
+        ql[i] = (uint8_t)((l1 & 0xF) | ((l2 & 0xF) << 4));
+    }
+    // qh[jj] for jj = 4j..4j+3: bit 2c <- L[64c+jj] > 15, bit 2c+1 <- L[64c+32+jj] > 15
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int jj = 4 * j + k;
+        uint8_t h = 0;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            h |= (uint8_t)((L[64 * cc + jj] > 15 ? 1 : 0) << (2 * cc));
+            h |= (uint8_t)((L[64 * cc + 32 + jj] > 15 ? 1 : 0) << (2 * cc + 1));
+        }
+        qh[jj] = h;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Q6_K: 16 threads per super-block (one per 16-elem sub-block)
+// ------------------------------------------------------------------------------------
+template <int NSB>
+struct K6Shared {
+    float x[NSB * 16][17];
+    float sc[NSB * 16];
+    uint8_t L[NSB][256];
+    alignas(16) uint8_t out[NSB * 210];
+};
+
+struct K6Thread {
+    float x[16];
+    float scale;
+    float l_iscale;  // L[i] = 32 + clamp(nearest_int(l_iscale * x[i]), -32, 31)
+    int all_zero;
+};
+
+// make_qx_quants(n=16, nmax=32, rmse_type=1, qw=NULL)
+QT_HD void qx_search(K6Thread& th) {
+    const int nmax = 32;
+    float mx = 0, amax = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float ax = fabsf(th.x[i]);
+        if (ax > amax) { amax = ax; mx = th.x[i]; }
+    }
+    if (amax < 1e-15f) {
+        th.scale = 0.f; th.l_iscale = 0.f; th.all_zero = 1;
+        return;
+    }
+    th.all_zero = 0;
+    float iscale = -nmax / mx;
+    float sumlx = 0, suml2 = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int l = clampi(nearest_int(iscale * th.x[i]), -nmax, nmax - 1);
+        const float w = th.x[i] * th.x[i];
+        sumlx += w * th.x[i] * l;
+        suml2 += w * l * l;
+    }
+    float scale = suml2 ? sumlx / suml2 : 0.0f;
+    float best = scale * sumlx;
+    th.l_iscale = iscale;
+    for (int is = -9; is <= 9; ++is) {
+        if (is == 0) continue;
+        iscale = -(nmax + 0.1f * is) / mx;
+        sumlx = suml2 = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int l = clampi(nearest_int(iscale * th.x[i]), -nmax, nmax - 1);
+            const float w = th.x[i] * th.x[i];
+            sumlx += w * th.x[i] * l;
+            suml2 += w * l * l;
+        }
+        if (suml2 > 0 && sumlx * sumlx > best * suml2) {
+            th.l_iscale = iscale;
+            scale = sumlx / suml2;
+            best = scale * sumlx;
+        }
+    }
+    th.scale = scale;
+}
+
+template <class S>
+QT_HD void q6k_phase_a(int t, S& s, K6Thread& th) {
+#pragma unroll
+    for (int l = 0; l < 16; ++l) th.x[l] = s.x[t][l];
+    qx_search(th);
+    s.sc[t] = th.scale;
+}
+
+template <class S>
+QT_HD void q6k_phase_b(int t, S& s, const K6Thread& th) {
+    const int sb = t >> 4, j = t & 15;
+    float max_scale = 0, max_abs_scale = 0;
+#pragma unroll
+    for (int ib = 0; ib < 16; ++ib) {
+        const float scale = s.sc[sb * 16 + ib];
+        const float a = fabsf(scale);
+        if (a > max_abs_scale) { max_abs_scale = a; max_scale = scale; }
+    }
+    uint8_t* o = s.out + sb * 210;
+    uint8_t* L = &s.L[sb][16 * j];
+    if (max_abs_scale < 1e-15f) {
+        // memset(block, 0); d = fp16(0)
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) L[ii] = 0;
+        o[192 + j] = 0;
+        if (j == 0) { o[208] = 0; o[209] = 0; }
+        return;
+    }
+    const float iscale = -128.f / max_scale;
+    const __half dh = __float2half_rn(1 / iscale);
+    int q = nearest_int(iscale * th.scale);
+    q = q < 127 ? q : 127;
+    const int8_t q8 = (int8_t)q;
+    o[192 + j] = (uint8_t)q8;
+    if (j == 0) {
+        const unsigned short db = __half_as_ushort(dh);
+        o[208] = (uint8_t)(db & 0xff); o[209] = (uint8_t)(db >> 8);
+    }
+    const float d = __half2float(dh) * q8;
+    if (d != 0.f) {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) L[ii] = (uint8_t)(clampi(nearest_int(th.x[ii] / d), -32, 31) + 32);
+    } else if (th.all_zero) {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) L[ii] = 0;
+    } else {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii)
+            L[ii] = (uint8_t)(32 + clampi(nearest_int(th.l_iscale * th.x[ii]), -32, 31));
+    }
+}
+
+// returns 1 when the super-block is the all-zero special case (whole block memset to 0)
+template <class S>
+QT_HD void q6k_phase_c(int t, S& s) {
+    const int sb = t >> 4, j = t & 15;
+    const uint8_t* L = s.L[sb];
+    uint8_t* o = s.out + sb * 210;
+    // ql: 128 bytes; thread j writes bytes 8j..8j+7.  byte b: half h=b/64, r=b%64;
+    //   r<32 : L[128h + r] & 15 | (L[128h + r + 64] & 15) << 4
+    //   r>=32: L[128h + r] & 15 | (L[128h + r + 64] & 15) << 4    (r-32+32 = r; +96 = r+64)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int b = 8 * j + i, h = b >> 6, r = b & 63;
+        o[b] = (uint8_t)((L[128 * h + r] & 0xF) | ((L[128 * h + r + 64] & 0xF) << 4));
+    }
+    // qh: 64 bytes; thread j writes bytes 4j..4j+3.  byte b: h=b/32, l=b%32
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = 4 * j + i, h = b >> 5, l = b & 31;
+        const uint8_t* Lh = L + 128 * h;
+        o[128 + b] = (uint8_t)((Lh[l] >> 4) | ((Lh[l + 32] >> 4) << 2) | ((Lh[l + 64] >> 4) << 4) |
+                               ((Lh[l + 96] >> 4) << 6));
+    }
+}
+
+}  // namespace kq
+}  // namespace qt
