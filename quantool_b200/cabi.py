@@ -28,6 +28,21 @@ _SIGS = {
     "qt_gguf_block_bytes": [_i32],
     "qt_gguf_quantize": [_i32, _vp, _i32, _i32, _i64, _i64, _vp, _vp],
     "qt_gguf_dequantize": [_i32, _vp, _i64, _i64, _vp, _vp],
+    "qt_minmax_qparams": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "qt_quantize_codes": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "qt_pack_int32": [_vp, _i32, _i32, _i32, _vp, _vp],
+    "qt_unpack_int32": [_vp, _i32, _i32, _i32, _vp, _vp],
+    "qt_hessian_set_splits": [_i32],
+    "qt_hessian_accumulate": [_vp, _i64, _i32, _vp, _vp],
+    "qt_hessian_finalize": [_vp, _i32, _f32, _vp],
+    "qt_hessian_accumulate_reference": [_vp, _i64, _i32, _vp, _vp],
+    "qt_gptq_prepare_hessian": [_vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp],
+    "qt_gptq_hinv_factor": [_vp, _vp, _vp, _i32, _vp, _vp],
+    "qt_set_identity": [_vp, _i32, _vp],
+    "qt_sgemm": [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _vp],
+    "qt_gptq_permute_in": [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp],
+    "qt_gptq_permute_out": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }
 _RESTYPE = {"qt_last_error": ctypes.c_char_p}
 
@@ -118,3 +133,181 @@ def gguf_dequantize(y: torch.Tensor, qtype: str, ncols: int) -> torch.Tensor:
         _check(lib().qt_gguf_dequantize(GGML[qtype], _p(y), nrows, ncols, _p(out), _stream()),
                "qt_gguf_dequantize")
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# compressed-tensors primitives (observer, codes, int32 packing)
+# ---------------------------------------------------------------------------------------
+def minmax_qparams(w: torch.Tensor, group_size: int, num_bits: int, symmetric: bool):
+    """MinMax observer + calculate_qparams, evaluated in w.dtype.  Returns (scale, zp) fp32 [N, G];
+    zp holds integer values.  group_size <= 0 means one scale per row (CHANNEL)."""
+    _dev(w, "w")
+    N, K = w.shape
+    G = K // group_size if group_size > 0 else 1
+    scale = torch.empty((N, G), dtype=torch.float32, device=w.device)
+    zp = torch.empty((N, G), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _check(lib().qt_minmax_qparams(_p(w), _DT[w.dtype], N, K, max(group_size, 0), num_bits, int(symmetric),
+                                       _p(scale), _p(zp), _stream()), "qt_minmax_qparams")
+    return scale, zp
+
+
+def quantize_codes(w: torch.Tensor, scale: torch.Tensor, zp: Optional[torch.Tensor], g_idx: Optional[torch.Tensor],
+                   group_size: int, num_bits: int, want_codes: bool = True, want_dq: bool = False):
+    """CT `quantize` (-> int8 codes) and optionally `dequantize`, in w.dtype arithmetic.
+    scale must have w's dtype ([N, G]); zp fp32 integers [N, G] or None; g_idx int32 [K] or None."""
+    _dev(w, "w"); _dev(scale, "scale")
+    if scale.dtype != w.dtype:
+        raise QtError("scale must have the weight's dtype (the artifact stores weight_scale in model dtype)")
+    N, K = w.shape
+    G = scale.shape[1]
+    codes = torch.empty((N, K), dtype=torch.int8, device=w.device) if want_codes else None
+    dq = torch.empty_like(w) if want_dq else None
+    if zp is not None:
+        zp = _dev(zp.to(torch.float32), "zp")
+    if g_idx is not None:
+        g_idx = _dev(g_idx.to(torch.int32), "g_idx")
+    with torch.cuda.device(w.device):
+        _check(lib().qt_quantize_codes(_p(w), _p(scale), _p(zp), _p(g_idx), _DT[w.dtype], N, K, G,
+                                       max(group_size, 0), num_bits, _p(codes), _p(dq), _stream()),
+               "qt_quantize_codes")
+    return codes, dq
+
+
+def pack_int32(codes: torch.Tensor, num_bits: int) -> torch.Tensor:
+    _dev(codes, "codes")
+    assert codes.dtype == torch.int8
+    N, K = codes.shape
+    pf = 32 // num_bits
+    out = torch.empty((N, (K + pf - 1) // pf), dtype=torch.int32, device=codes.device)
+    with torch.cuda.device(codes.device):
+        _check(lib().qt_pack_int32(_p(codes), N, K, num_bits, _p(out), _stream()), "qt_pack_int32")
+    return out
+
+
+def unpack_int32(packed: torch.Tensor, num_bits: int, K: int) -> torch.Tensor:
+    _dev(packed, "packed")
+    N = packed.shape[0]
+    out = torch.empty((N, K), dtype=torch.int8, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _check(lib().qt_unpack_int32(_p(packed), N, K, num_bits, _p(out), _stream()), "qt_unpack_int32")
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# GPTQ
+# ---------------------------------------------------------------------------------------
+def hessian_accumulate(x: torch.Tensor, H: torch.Tensor) -> None:
+    """H (fp32 [K,K], raw sums, upper tiles) += x^T x.  x: [T, K] bf16."""
+    _dev(x, "x"); _dev(H, "H")
+    if x.dtype != torch.bfloat16:
+        raise QtError("hessian_accumulate takes bf16 activations")
+    T, K = x.shape
+    assert H.shape == (K, K) and H.dtype == torch.float32
+    with torch.cuda.device(x.device):
+        _check(lib().qt_hessian_accumulate(_p(x), T, K, _p(H), _stream()), "qt_hessian_accumulate")
+
+
+def hessian_accumulate_reference(x: torch.Tensor, H: torch.Tensor) -> None:
+    T, K = x.shape
+    with torch.cuda.device(x.device):
+        _check(lib().qt_hessian_accumulate_reference(_p(_dev(x, "x")), T, K, _p(_dev(H, "H")), _stream()),
+               "qt_hessian_accumulate_reference")
+
+
+def hessian_finalize(H: torch.Tensor, factor: float) -> None:
+    """Scale the accumulated upper triangle by `factor` (2 / n_samples) and mirror it."""
+    _dev(H, "H")
+    with torch.cuda.device(H.device):
+        _check(lib().qt_hessian_finalize(_p(H), H.shape[0], float(factor), _stream()), "qt_hessian_finalize")
+
+
+def gptq_prepare_hessian(H: torch.Tensor, perm: Optional[torch.Tensor], percdamp: float):
+    """Returns (Hf, dead): the damped Hessian, act_order-permuted and index-reversed (lower
+    triangle), and the dead-column mask of the ORIGINAL column order."""
+    _dev(H, "H")
+    K = H.shape[0]
+    Hf = torch.empty_like(H)
+    dead = torch.empty((K,), dtype=torch.uint8, device=H.device)
+    damp = torch.empty((1,), dtype=torch.float32, device=H.device)
+    if perm is not None:
+        perm = _dev(perm.to(torch.int32), "perm")
+    with torch.cuda.device(H.device):
+        _check(lib().qt_gptq_prepare_hessian(_p(H), _p(perm), K, float(percdamp), _p(Hf), _p(dead), _p(damp),
+                                             _stream()), "qt_gptq_prepare_hessian")
+    return Hf, dead
+
+
+def gptq_hinv_factor(Hf: torch.Tensor, scratch_x: Optional[torch.Tensor] = None,
+                     scratch_w: Optional[torch.Tensor] = None):
+    """In place: Hf (flipped damped H) -> U = cholesky(H^-1, upper).  Returns (U, info) where
+    info is a device int32 (0 = ok, else 1-based failing pivot; caller decides when to read it)."""
+    _dev(Hf, "Hf")
+    K = Hf.shape[0]
+    X = scratch_x if scratch_x is not None else torch.empty_like(Hf)
+    W = scratch_w if scratch_w is not None else torch.empty_like(Hf)
+    info = torch.zeros((1,), dtype=torch.int32, device=Hf.device)
+    with torch.cuda.device(Hf.device):
+        _check(lib().qt_gptq_hinv_factor(_p(Hf), _p(X), _p(W), K, _p(info), _stream()), "qt_gptq_hinv_factor")
+    return Hf, info
+
+
+def set_identity(U: torch.Tensor) -> None:
+    with torch.cuda.device(U.device):
+        _check(lib().qt_set_identity(_p(_dev(U, "U")), U.shape[0], _stream()), "qt_set_identity")
+
+
+def sgemm(A, B, C, alpha=1.0, beta=0.0, b_is_nk=False, lower_tiles_only=False, a_lower_tri=False,
+          b_lower_tri=False):
+    M, Kd = A.shape
+    N = C.shape[1]
+    with torch.cuda.device(A.device):
+        _check(lib().qt_sgemm(int(b_is_nk), _p(A), _p(B), _p(C), M, N, Kd, A.stride(0), B.stride(0), C.stride(0),
+                              float(alpha), float(beta), int(lower_tiles_only), int(a_lower_tri), int(b_lower_tri),
+                              _stream()), "qt_sgemm")
+    return C
+
+
+def gptq_permute_in(w: torch.Tensor, perm: Optional[torch.Tensor], dead: Optional[torch.Tensor]) -> torch.Tensor:
+    _dev(w, "w")
+    N, K = w.shape
+    out = torch.empty((N, K), dtype=torch.float32, device=w.device)
+    if perm is not None:
+        perm = _dev(perm.to(torch.int32), "perm")
+    with torch.cuda.device(w.device):
+        _check(lib().qt_gptq_permute_in(_p(w), _DT[w.dtype], _p(perm), _p(dead), _p(out), N, K, _stream()),
+               "qt_gptq_permute_in")
+    return out
+
+
+def gptq_permute_out(wp: torch.Tensor, inv_perm: Optional[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
+    _dev(wp, "wp")
+    N, K = wp.shape
+    out = torch.empty((N, K), dtype=dtype, device=wp.device)
+    if inv_perm is not None:
+        inv_perm = _dev(inv_perm.to(torch.int32), "inv_perm")
+    with torch.cuda.device(wp.device):
+        _check(lib().qt_gptq_permute_out(_p(wp), _p(inv_perm), _p(out), _DT[dtype], N, K, _stream()),
+               "qt_gptq_permute_out")
+    return out
+
+
+GPTQ_MODE_GROUP_REFIT, GPTQ_MODE_STATIC_GIDX, GPTQ_MODE_CHANNEL = 0, 1, 2
+
+
+def gptq_quantize_weight(wp: torch.Tensor, U: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor,
+                         g_idx: Optional[torch.Tensor], group_size: int, num_bits: int, symmetric: bool,
+                         mode: int, err_scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Blocked GPTQ column loop, in place on wp (fp32 [N,K], permuted order).  Returns per-row losses."""
+    _dev(wp, "wp"); _dev(U, "U"); _dev(scale, "scale"); _dev(zp, "zp")
+    N, K = wp.shape
+    G = scale.shape[1]
+    losses = torch.zeros((N,), dtype=torch.float32, device=wp.device)
+    err = err_scratch if err_scratch is not None else torch.empty((N, 128), dtype=torch.float32, device=wp.device)
+    if g_idx is not None:
+        g_idx = _dev(g_idx.to(torch.int32), "g_idx")
+    with torch.cuda.device(wp.device):
+        _check(lib().qt_gptq_quantize_weight(_p(wp), _p(U), _p(err), _p(scale), _p(zp), _p(g_idx), _p(losses),
+                                             N, K, G, max(group_size, 0), num_bits, int(symmetric), mode,
+                                             _stream()), "qt_gptq_quantize_weight")
+    return losses

@@ -24,6 +24,12 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 SOURCES = {
     "common.cu": [],
     "gguf.cu": ["--fmad=false"],
+    "quant.cu": [],
+    "linalg.cu": [],
+    "gptq.cu": [],
+    "hessian.cu": [],
+    "smooth.cu": [],
+    "awq.cu": [],
 }
 
 

@@ -1,0 +1,416 @@
+// GPTQ Hessian accumulation  H += X^T X  on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces UPSTREAM llmcompressor gptq_quantize.py `accumulate_hessian`,
+// the forward hook GPTQModifier installs on every Linear; reached from
+// ref/src/quantool/methods/llm_compressor/gptq/gptq.py:86 via llmcompressor.oneshot at
+// ref/src/quantool/methods/llm_compressor/base.py:159-161.  Upstream keeps a running mean
+// (H *= n/(n+b); H += (2/n) X^T X in fp32); here raw fp32 sums are accumulated over all
+// batches and qt_hessian_finalize applies the single factor 2/n_samples and mirrors the
+// upper triangle, which is the same matrix up to fp32 rounding.
+//
+// Shape of the work: X is [T, K] bf16 row-major (K contiguous).  Both MMA operands are tiles
+// of the SAME matrix, read "MN-major": a TMA box of 64 columns x 64 tokens lands in shared
+// memory as 64 token-rows of 128 bytes (SWIZZLE_128B), which is exactly the canonical
+// MN-major SW128 UMMA layout, so no transpose of X is ever materialised.
+//   D[128 x 256] (fp32, TMEM) += A[128 x 16]^T-view * B[256 x 16]^T-view per tcgen05.mma
+// Only tiles that touch the upper triangle are computed (SYRK); tokens are split S ways so
+// that tiles x S fills the 148 SMs evenly; partial tiles are added to H with vectorised
+// fp32 reductions (red.global.add.v4.f32) that resolve in L2.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over work units):
+//   warp 0    TMA producer      (one elected lane)
+//   warp 1    TMEM alloc + tcgen05.mma issuer (one elected lane)
+//   warps 2-5 epilogue: tcgen05.ld 32x32b -> registers -> red.global.add
+// Pipelines: 4-stage smem ring (full/empty mbarriers), 2 TMEM accumulators (512 columns).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace qt {
+namespace hess {
+
+constexpr int BM = 128;          // rows of the H tile  (columns m0.. of X)
+constexpr int BN = 256;          // cols of the H tile  (columns n0.. of X)
+constexpr int BKT = 64;          // tokens per pipeline stage
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int BOX_BYTES = 64 * 2 * BKT;               // 64 cols x BKT tokens of bf16 = 8 KB
+constexpr int A_BYTES = (BM / 64) * BOX_BYTES;        // 16 KB
+constexpr int B_BYTES = (BN / 64) * BOX_BYTES;        // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 192;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+QT_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+QT_D void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+QT_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+QT_D void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+QT_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+QT_D void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+QT_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+QT_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+QT_D void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+QT_D void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+QT_D void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+QT_D void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// MN-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4, [16,30) LBO>>4 = stride between 64-element MN atoms (one TMA box),
+//   [32,46) SBO>>4 = stride between 8-token groups (8 x 128 B), [46,48) version = 1,
+//   [61,64) layout = 2 (SWIZZLE_128B)
+QT_D uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both MN-major, N=256, M=128
+constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Sched {
+    int K, NI, NJ, ntiles, S, nkb;  // nkb = ceil(T / BKT)
+    int nunits;
+};
+
+// tile index -> (im, jn).  Column-block jn holds row-blocks 0..min(2jn+1, NI-1).
+QT_D void tile_coords(const Sched& s, int t, int& im, int& jn) {
+    int j = 0;
+    for (;;) {
+        int cnt = 2 * j + 2;
+        cnt = cnt < s.NI ? cnt : s.NI;
+        if (t < cnt) break;
+        t -= cnt;
+        ++j;
+    }
+    im = t;
+    jn = j;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+hessian_syrk_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ H, Sched s) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES]
+    uint64_t* empty = bars + STAGES;        // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;    // [2]
+    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < s.nunits; u += gridDim.x) {
+                const int split = u / s.ntiles, tile = u - split * s.ntiles;
+                int im, jn;
+                tile_coords(s, tile, im, jn);
+                const int kb0 = (int)((long long)s.nkb * split / s.S), kb1 = (int)((long long)s.nkb * (split + 1) / s.S);
+                for (int kb = kb0; kb < kb1; kb++, it++) {
+                    const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[stage], ph ^ 1);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+#pragma unroll
+                    for (int b = 0; b < BM / 64; b++) tma_load_2d(sa + b * BOX_BYTES, &tmap, &full[stage], im * BM + b * 64, kb * BKT);
+#pragma unroll
+                    for (int b = 0; b < BN / 64; b++) tma_load_2d(sb + b * BOX_BYTES, &tmap, &full[stage], jn * BN + b * 64, kb * BKT);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc();
+            uint32_t it = 0, li = 0;
+            for (int u = blockIdx.x; u < s.nunits; u += gridDim.x, li++) {
+                const int split = u / s.ntiles;
+                const int kb0 = (int)((long long)s.nkb * split / s.S), kb1 = (int)((long long)s.nkb * (split + 1) / s.S);
+                const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+                mbar_wait(&tempty[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; kb++, it++) {
+                    const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full[stage], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BKT / UMMA_K; k++) {
+                        const uint64_t ad = make_desc(sa + k * UMMA_K * 128, BOX_BYTES, 1024);
+                        const uint64_t bd = make_desc(sb + k * UMMA_K * 128, BOX_BYTES, 1024);
+                        tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[stage]);
+                }
+                tc_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> red.add into H =====
+        const int lg = warp & 3;  // TMEM lane group this warp may access
+        uint32_t li = 0;
+        for (int u = blockIdx.x; u < s.nunits; u += gridDim.x, li++) {
+            const int split = u / s.ntiles, tile = u - split * s.ntiles;
+            int im, jn;
+            tile_coords(s, tile, im, jn);
+            const int kb0 = (int)((long long)s.nkb * split / s.S), kb1 = (int)((long long)s.nkb * (split + 1) / s.S);
+            const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const int row = im * BM + lg * 32 + lane;
+            if (kb1 > kb0) {
+#pragma unroll 1
+                for (int cc = 0; cc < BN / 32; cc++) {
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + cc * 32, r);
+                    const int col0 = jn * BN + cc * 32;
+                    if (row < s.K) {
+                        float* hp = H + (long long)row * s.K + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < s.K && col0 + j + 3 >= row)   // keep the 4-group if it touches c >= r
+                                red_add_v4(hp + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// H <- factor * H on the upper triangle, mirrored to the lower triangle (32x32 smem transpose)
+__global__ void __launch_bounds__(256) finalize_kernel(float* __restrict__ H, int K, float factor) {
+    __shared__ float t[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        float v = 0.f;
+        if (i < K && j < K) {
+            if (bi == bj && j < i) {
+                v = 0.f;  // filled from the mirror below
+            } else {
+                v = H[(long long)i * K + j] * factor;
+                H[(long long)i * K + j] = v;
+            }
+        }
+        t[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        // write transposed tile: element (j, i) <- t[i][j]
+        const int jj = bj * 32 + r, ii = bi * 32 + tx;
+        if (jj < K && ii < K) {
+            if (bi == bj) {
+                if (ii < jj) H[(long long)jj * K + ii] = t[tx][r];
+            } else {
+                H[(long long)jj * K + ii] = t[tx][r];
+            }
+        }
+    }
+}
+
+// plain fp32 SIMT reference (no tensor cores): used by tests and smoke to cross-check the
+// tcgen05 path at sizes where the CPU oracle is too slow.  One thread per upper-triangle entry.
+__global__ void __launch_bounds__(256) syrk_reference_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ H,
+                                                             long long T, int K) {
+    const int j = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int i = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (i >= K || j >= K || j < i) return;
+    float acc = 0.f;
+    for (long long t = 0; t < T; t++)
+        acc = fmaf(__bfloat162float(X[t * K + i]), __bfloat162float(X[t * K + j]), acc);
+    H[(long long)i * K + j] += acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int g_force_splits = 0;
+
+}  // namespace hess
+}  // namespace qt
+
+using namespace qt;
+using namespace qt::hess;
+
+extern "C" {
+
+// debug/tuning knob: force the token split count (0 = heuristic)
+int qt_hessian_set_splits(int s) { g_force_splits = s; return QT_OK; }
+
+// H[K,K] (fp32, zero-initialised by the caller before the first batch) += X^T X over the upper
+// triangle tiles.  X: [T, K] bf16 row-major.  K % 8 == 0.
+int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* stream) {
+    if (!X || !H || T < 0 || K <= 0 || (K & 7)) return QT_ERR_INVALID;
+    if (T == 0) return QT_OK;
+    if (((uintptr_t)X & 15) || ((uintptr_t)H & 15)) return QT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point", cudaErrorUnknown); return QT_ERR_CUDA; }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)T};
+    const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)BKT};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(X), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue); return QT_ERR_CUDA; }
+
+    Sched s;
+    s.K = K;
+    s.NI = (K + BM - 1) / BM;
+    s.NJ = (K + BN - 1) / BN;
+    s.ntiles = 0;
+    for (int j = 0; j < s.NJ; j++) { int c = 2 * j + 2; s.ntiles += c < s.NI ? c : s.NI; }
+    s.nkb = (int)((T + BKT - 1) / BKT);
+    int dev = 0, nsm = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    // token splits: enough units to balance the SMs (waste <= ~3%), at least ~16 k-blocks per unit
+    int S = 1;
+    if (g_force_splits > 0) {
+        S = g_force_splits;
+    } else {
+        const int smax = s.nkb / 16 > 1 ? s.nkb / 16 : 1;
+        double best = 1e30;
+        for (int c = 1; c <= smax && c <= 256; c++) {
+            const long long units = (long long)s.ntiles * c;
+            const long long waves = (units + nsm - 1) / nsm;
+            const double eff_time = (double)waves * ((double)s.nkb / c + 6.0);  // +6 k-blocks of per-unit overhead
+            if (eff_time < best * 0.995) { best = eff_time; S = c; }
+        }
+    }
+    if (S > s.nkb) S = s.nkb;
+    s.S = S;
+    s.nunits = s.ntiles * S;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(hessian_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { set_last_error("hessian smem attr", e); return QT_ERR_CUDA; }
+        attr_set = true;
+    }
+    const int grid = s.nunits < nsm ? s.nunits : nsm;
+    hessian_syrk_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmap, H, s);
+    return check_launch("hessian_syrk");
+}
+
+int qt_hessian_finalize(float* H, int K, float factor, void* stream) {
+    if (!H || K <= 0) return QT_ERR_INVALID;
+    const int nb = (K + 31) / 32;
+    dim3 grid(nb, nb);
+    finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(H, K, factor);
+    return check_launch("hessian_finalize");
+}
+
+// fp32 SIMT cross-check (test infrastructure on the device; never on the product path)
+int qt_hessian_accumulate_reference(const void* X, int64_t T, int K, float* H, void* stream) {
+    if (!X || !H || T < 0 || K <= 0) return QT_ERR_INVALID;
+    dim3 grid((K + 15) / 16, (K + 15) / 16);
+    syrk_reference_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, H, T, K);
+    return check_launch("syrk_reference");
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// fp32 SIMT GEMM used by the Cholesky chain and the GPTQ lazy-batch update, where the
+// reference keeps everything in fp32 (GPTQ_PRECISION = torch.float32) and
+// north_star asks that the trailing updates stay in fp32.
+//
+//   C[M,N] = alpha * A[M,Kd] * op(B) + beta * C        (row-major, leading dims lda/ldb/ldc)
+//   B_NK = false : B is [Kd, N] (n contiguous)          "NN"
+//   B_NK = true  : B is [N, Kd] (k contiguous)          "NT"  (C += A * B^T)
+//
+// 128x128x16 CTA tile, 256 threads, 8x8 register micro-tile (two 4-wide halves per
+// dimension so every shared-memory read is a conflict-free LDS.128), global->register
+// prefetch of the next k-slab overlapped with the FMAs of the current one, two shared
+// buffers, one __syncthreads per slab.  Triangular structure is skipped at tile granularity.
+#pragma once
+#include "common.cuh"
+
+namespace qt {
+
+struct GemmArgs {
+    const float* A;
+    const float* B;
+    float* C;
+    int M, N, Kd;
+    int lda, ldb, ldc;
+    float alpha, beta;
+    long long strideA, strideB, strideC;  // batch strides (elements); batch = gridDim.z
+    int lower_tiles_only;  // 1: skip tiles entirely above the diagonal (SYRK into a lower triangle)
+    int a_lower_tri;       // 1: A[m][k] == 0 for k > m  -> k range ends at the tile's last row
+    int b_lower_tri;       // 1: B[k][n] == 0 for k < n  -> k range starts at the tile's first col
+};
+
+constexpr int GBM = 128, GBN = 128, GBK = 16;
+constexpr int GLD = GBM + 4;  // smem leading dim (keeps float4 alignment)
+
+template <bool B_NK>
+__global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[2][GBK][GLD];
+    __shared__ __align__(16) float Bs[2][GBK][GLD];
+
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    if (g.lower_tiles_only && n0 > m0 + GBM - 1) return;
+    const float* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
+    const float* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
+    float* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
+
+    int k_begin = 0, k_end = g.Kd;
+    if (g.a_lower_tri) { const int e = m0 + GBM; k_end = e < k_end ? e : k_end; }
+    if (g.b_lower_tri) { k_begin = (n0 / GBK) * GBK; }
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+
+    // global->smem mapping for a k-contiguous operand tile (128 rows x 16 k): 512 float4,
+    // thread t handles rows r = t/4 and r+64, k-quad kq = t%4
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    // mapping for an n-contiguous B slab (16 k x 128 n): 512 float4, thread t handles
+    // k = t/32 and k+8, n-quad = (t%32)*4
+    const int bk = tid >> 5, bn = (tid & 31) * 4;
+
+    float4 ra[2], rb[2];
+    auto load_slab = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = m0 + lr + 64 * h, k = k0 + lk;
+            ra[h] = (m < g.M && k < k_end) ? *reinterpret_cast<const float4*>(A + (long long)m * g.lda + k)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (B_NK) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int n = n0 + lr + 64 * h, k = k0 + lk;
+                rb[h] = (n < g.N && k < k_end) ? *reinterpret_cast<const float4*>(B + (long long)n * g.ldb + k)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int k = k0 + bk + 8 * h, n = n0 + bn;
+                rb[h] = (k < k_end && n < g.N) ? *reinterpret_cast<const float4*>(B + (long long)k * g.ldb + n)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    auto store_slab = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = lr + 64 * h;
+            As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y;
+            As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+        }
+        if (B_NK) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = lr + 64 * h;
+                Bs[buf][lk + 0][r] = rb[h].x; Bs[buf][lk + 1][r] = rb[h].y;
+                Bs[buf][lk + 2][r] = rb[h].z; Bs[buf][lk + 3][r] = rb[h].w;
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+                *reinterpret_cast<float4*>(&Bs[buf][bk + 8 * h][bn]) = rb[h];
+        }
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+    const int nslab = (k_end - k_begin + GBK - 1) / GBK;
+    if (nslab > 0) {
+        load_slab(k_begin);
+        store_slab(0);
+        __syncthreads();
+        for (int s = 0; s < nslab; s++) {
+            const int buf = s & 1;
+            if (s + 1 < nslab) load_slab(k_begin + (s + 1) * GBK);
+#pragma unroll
+            for (int k = 0; k < GBK; k++) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            if (s + 1 < nslab) {
+                store_slab(buf ^ 1);
+                __syncthreads();
+            }
+        }
+    }
+
+    // epilogue: rows {ty*4+i, 64+ty*4+i}, cols {tx*4.., 64+tx*4..}
+#pragma unroll
+    for (int ih = 0; ih < 2; ih++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int m = m0 + 64 * ih + ty * 4 + i;
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int jh = 0; jh < 2; jh++) {
+                const int n = n0 + 64 * jh + tx * 4;
+                if (n >= g.N) continue;  // N % 4 == 0 is enforced by the host wrapper
+                float* cp = C + (long long)m * g.ldc + n;
+                float4 o;
+                const float* v = &acc[4 * ih + i][4 * jh];
+                if (g.beta != 0.f) {
+                    const float4 c = *reinterpret_cast<const float4*>(cp);
+                    o.x = g.alpha * v[0] + g.beta * c.x; o.y = g.alpha * v[1] + g.beta * c.y;
+                    o.z = g.alpha * v[2] + g.beta * c.z; o.w = g.alpha * v[3] + g.beta * c.w;
+                } else {
+                    o.x = g.alpha * v[0]; o.y = g.alpha * v[1]; o.z = g.alpha * v[2]; o.w = g.alpha * v[3];
+                }
+                *reinterpret_cast<float4*>(cp) = o;
+            }
+        }
+}
+
+// returns QT_OK / QT_ERR_INVALID (alignment contract: dims and leading dims multiples of 4,
+// pointers 16-byte aligned).  Empty problems are a no-op.
+inline int sgemm(bool b_nk, const GemmArgs& g, int batch, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return QT_OK;
+    if ((g.N & 3) || (g.Kd & 3) || (g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return QT_ERR_INVALID;
+    if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || ((uintptr_t)g.C & 15)) return QT_ERR_INVALID;
+    if ((g.strideA & 3) || (g.strideB & 3) || (g.strideC & 3)) return QT_ERR_INVALID;
+    dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, batch);
+    if (b_nk) sgemm_kernel<true><<<grid, 256, 0, st>>>(g);
+    else      sgemm_kernel<false><<<grid, 256, 0, st>>>(g);
+    return check_launch("sgemm");
+}
+
+}  // namespace qt

@@ -1,0 +1,208 @@
+"""GPU parity: GPTQ kernels (tcgen05 Hessian, fp32 Cholesky chain, blocked column loop, codes)
+through the C-ABI against the CPU oracle (oracle/gptq.py, built on installed compressed-tensors)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _acts(T, K, seed=7, outliers=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((T, K), generator=g)
+    if outliers:
+        idx = torch.randperm(K, generator=g)[: max(1, K // 200)]
+        x[:, idx] *= 20.0
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("T,K", [(512, 256), (1000, 576), (4096, 1024), (3000, 2048)])
+def test_hessian_tcgen05_vs_fp64(T, K):
+    """H within 1e-3 relative (north_star) of the fp64 value and of the oracle's running mean."""
+    from quantool_b200 import cabi
+    from oracle import gptq as og
+    x = _acts(T, K)
+    n_samples = 8
+    H = torch.zeros((K, K), dtype=torch.float32, device="cuda")
+    xc = x.cuda()
+    half = (T // 2 // 8) * 8
+    cabi.hessian_accumulate(xc[:half].contiguous(), H)      # two batches: accumulation path
+    cabi.hessian_accumulate(xc[half:].contiguous(), H)
+    cabi.hessian_finalize(H, 2.0 / n_samples)
+    ref = (2.0 / n_samples) * (x.double().t() @ x.double())
+    got = H.cpu().double()
+    rel = torch.linalg.norm(got - ref) / torch.linalg.norm(ref)
+    assert rel < 1e-5, rel
+    assert torch.equal(H, H.t())
+    # oracle (SURVEY §A.1 running mean, fp32)
+    Ho, n = og.make_empty_hessian(K), 0
+    for xb in x.reshape(n_samples, T // n_samples, K) if T % n_samples == 0 else [x]:
+        Ho, n = og.accumulate_hessian(xb.unsqueeze(0) if T % n_samples == 0 else xb, Ho, n)
+    if T % n_samples != 0:
+        Ho = Ho * (1.0 / n_samples)   # one 2-D batch counted as 1 sample -> rescale to n_samples
+    rel_o = torch.linalg.norm(got - Ho.double()) / torch.linalg.norm(Ho.double())
+    assert rel_o < 1e-3, rel_o
+
+
+def test_hessian_vs_device_reference_full_width():
+    """K = 4096 (Llama-3-8B hidden) against the fp32 SIMT kernel on the same device."""
+    from quantool_b200 import cabi
+    T, K = 2048, 4096
+    x = _acts(T, K).cuda()
+    H = torch.zeros((K, K), dtype=torch.float32, device="cuda")
+    R = torch.zeros_like(H)
+    cabi.hessian_accumulate(x, H)
+    cabi.hessian_accumulate_reference(x, R)
+    cabi.hessian_finalize(H, 1.0)
+    cabi.hessian_finalize(R, 1.0)
+    rel = (torch.linalg.norm(H - R) / torch.linalg.norm(R)).item()
+    assert rel < 1e-5, rel
+
+
+@pytest.mark.parametrize("M,N,Kd,nk", [(300, 256, 128, False), (257, 384, 200, True), (128, 128, 64, False)])
+def test_sgemm(M, N, Kd, nk):
+    from quantool_b200 import cabi
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn((M, Kd), device="cuda", generator=g)
+    B = torch.randn((N, Kd) if nk else (Kd, N), device="cuda", generator=g)
+    C = torch.randn((M, N), device="cuda", generator=g)
+    ref = -1.0 * (A.double() @ (B.double().t() if nk else B.double())) + C.double()
+    cabi.sgemm(A, B, C, alpha=-1.0, beta=1.0, b_is_nk=nk)
+    assert (C.double() - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("K", [128, 384, 576, 1024, 2048])
+@pytest.mark.parametrize("act", [False, True])
+def test_hinv_factor_vs_fp64(K, act):
+    from quantool_b200 import cabi
+    T = 4 * K
+    x = _acts(T, K, seed=K)
+    H = ((2.0 / 16) * (x.double().t() @ x.double()))
+    Hc = H.float().cuda()
+    perm = torch.argsort(torch.diagonal(Hc), descending=True, stable=True).to(torch.int32) if act else None
+    Hf, dead = cabi.gptq_prepare_hessian(Hc, perm, 0.01)
+    U, info = cabi.gptq_hinv_factor(Hf)
+    assert int(info.item()) == 0
+    Hd = H.clone()
+    if act:
+        p = perm.cpu().long()
+        Hd = Hd[p][:, p]
+    Hd += 0.01 * torch.mean(torch.diag(Hd)) * torch.eye(K, dtype=torch.float64)
+    ref = torch.linalg.cholesky(torch.cholesky_inverse(torch.linalg.cholesky(Hd)), upper=True)
+    got = U.cpu().double()
+    assert torch.equal(torch.tril(got, -1), torch.zeros_like(got))
+    rel = torch.linalg.norm(got - ref) / torch.linalg.norm(ref)
+    assert rel < 2e-4, rel
+
+
+def test_hinv_not_pd_reports_info():
+    from quantool_b200 import cabi
+    K = 256
+    H = -torch.eye(K, device="cuda")
+    Hf, _ = cabi.gptq_prepare_hessian(H, None, 0.0)
+    _, info = cabi.gptq_hinv_factor(Hf)
+    assert int(info.item()) != 0
+
+
+CASES = [
+    ("W4A16", None, 96, 512),
+    ("W4A16", "group", 96, 512),
+    ("W4A16", "weight", 64, 384),
+    ("W4A16_ASYM", "group", 80, 256),
+    ("W8A16", None, 72, 320),
+    ("W8A8", None, 64, 576),
+]
+
+
+@pytest.mark.parametrize("level,actorder,N,K", CASES)
+def test_gptq_quantize_vs_oracle(level, actorder, N, K):
+    """north_star bar: artifact integer codes agree on >= 99.9 % of entries, ||WX - QX|| within 1 %."""
+    from quantool_b200.engine import gptq as eg, schemes
+    from oracle import gptq as og
+    from compressed_tensors.quantization import ActivationOrdering
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    T = 8 * K
+    x = _acts(T, K, seed=K + 1)
+    # oracle
+    oargs = og.scheme_weight_args(level)
+    if actorder is not None:
+        oargs.actorder = ActivationOrdering.GROUP if actorder == "group" else ActivationOrdering.WEIGHT
+    Ho, n = og.make_empty_hessian(K), 0
+    for xb in x.reshape(8, T // 8, K):
+        Ho, n = og.accumulate_hessian(xb.unsqueeze(0), Ho, n)
+    loss_o, Wq_o, s_o, z_o, gi_o = og.quantize_weight(W, Ho, oargs)
+    # CUDA path
+    args = schemes.resolve(level, actorder)
+    acc = eg.HessianAccumulator(K, "cuda")
+    for xb in x.reshape(8, T // 8, K):
+        acc.add(xb.unsqueeze(0).cuda())
+    H = acc.finalize()
+    relH = (torch.linalg.norm(H.cpu() - Ho) / torch.linalg.norm(Ho)).item()
+    assert relH < 1e-3, relH
+    res = eg.quantize_linear(W.cuda(), H, args)
+    assert int(res.info.item()) == 0
+    # artifact codes (what save_compressed stores)
+    if args.num_bits == 4:
+        codes_o, packed_o, pzp_o = og.compress_packed(Wq_o, s_o, z_o if not args.symmetric else None, gi_o, oargs)
+        art, codes = eg.compress_linear(res.weight, res.scale, res.zero_point, res.g_idx, args)
+    else:
+        codes_o = og.compress_int8(Wq_o, s_o, None, oargs)
+        art, codes = eg.compress_linear(res.weight, res.scale, res.zero_point, res.g_idx, args, fmt="int-quantized")
+    agree = (codes.cpu() == codes_o).float().mean().item()
+    assert agree >= 0.999, f"code agreement {agree:.5f}"
+    if gi_o is not None:
+        assert torch.equal(res.g_idx.cpu().to(torch.int64), gi_o.to(torch.int64))
+    e_o = og.layer_error(W, Wq_o, x.float())
+    e_c = og.layer_error(W, res.weight.cpu(), x.float())
+    assert abs(e_c - e_o) <= 0.01 * e_o, (e_c, e_o)
+    # and GPTQ must beat plain round-to-nearest on its own objective
+    Wr, _, _ = og.rtn_quantize(W, og.scheme_weight_args(level))
+    assert e_c < og.layer_error(W, Wr, x.float())
+    loss_c = res.losses.sum().item()
+    assert abs(loss_c - loss_o) <= 0.02 * abs(loss_o) + 1e-12, (loss_c, loss_o)
+
+
+@pytest.mark.parametrize("level", ["W4A16", "W4A16_ASYM", "W8A16"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_compress_codes_bit_exact_vs_compressed_tensors(level, dtype):
+    """Row a6: codes/packing from a saved (model dtype) weight + scale are integer work: bit-exact."""
+    from quantool_b200 import cabi
+    from quantool_b200.engine import gptq as eg, schemes
+    from oracle import gptq as og
+    N, K = 70, 768
+    g = torch.Generator().manual_seed(5)
+    W = (torch.randn((N, K), generator=g) * 0.05).to(dtype)
+    oargs = og.scheme_weight_args(level)
+    args = schemes.resolve(level)
+    Wq_o, s_o, z_o = og.rtn_quantize(W, oargs)
+    # observer parity (evaluated in the weight's dtype)
+    s_c, z_c = cabi.minmax_qparams(W.cuda(), args.group_size or 0, args.num_bits, args.symmetric)
+    assert torch.equal(s_c.cpu().to(dtype), s_o)
+    assert torch.equal(z_c.cpu().to(torch.int8), z_o.to(torch.int8))
+    gi = None
+    if args.strategy == "group":
+        gi = (torch.arange(K) // args.group_size)[torch.randperm(K, generator=g)].to(torch.int32)
+    if args.num_bits == 4:
+        codes_o, packed_o, pzp_o = og.compress_packed(W, s_o, z_o if not args.symmetric else None, gi, oargs)
+        art, codes = eg.compress_linear(W.cuda(), s_o.cuda(), z_o.to(torch.int8).cuda(),
+                                        gi.cuda() if gi is not None else None, args)
+        assert torch.equal(codes.cpu(), codes_o)
+        assert torch.equal(art["weight_packed"].cpu(), packed_o)
+        if pzp_o is not None:
+            assert torch.equal(art["weight_zero_point"].cpu(), pzp_o)
+        back = cabi.unpack_int32(art["weight_packed"], 4, K)
+        assert torch.equal(back, codes)
+    else:
+        codes_o = og.compress_int8(W, s_o, None, oargs)
+        art, codes = eg.compress_linear(W.cuda(), s_o.cuda(), z_o.to(torch.int8).cuda(), None, args,
+                                        fmt="int-quantized")
+        assert torch.equal(codes.cpu(), codes_o)
+
+
+def test_pack_kat():
+    """SURVEY §8c KAT: pack_to_int32([-8,-7,0,7,1,2,3,4, 5,6,7,-1,-2,-3,-4,-5], 4)."""
+    from quantool_b200 import cabi
+    v = torch.tensor([[-8, -7, 0, 7, 1, 2, 3, 4, 5, 6, 7, -1, -2, -3, -4, -5]], dtype=torch.int8).cuda()
+    p = cabi.pack_int32(v, 4).cpu().numpy().astype(np.uint32)
+    assert p.tolist() == [[0xCBA9F810, 0x34567FED]]
