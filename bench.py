@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the quantization hot path (BASELINE.json metric:
+"GPTQ/AWQ s per 8B model at 1/2/4/8 B200; GGUF pack GB/s vs HBM peak").
+
+One "step" = one complete GPTQ W4A16 g128 act_order pass over a random-init Llama-3-8B-shaped
+model (32 decoder layers x 7 Linears, 4 distinct Hessians per layer) with 128 x 2048-token
+synthetic calibration activations:
+    value  : seconds per model, activations and weights already resident in HBM
+             (Hessian SYRK -> NCCL all-reduce -> inverse-Hessian factor -> column loop -> codes/pack)
+    e2e    : seconds per model through the plugin-level entry (`quantize_model_gptq`): HOST
+             (pinned) weights and token ids in, HOST packed tensors out; includes every H2D/D2H
+             copy and the decoder-layer forwards that produce the activations.
+Multi-GPU (torchrun): calibration samples and output rows are sharded, H is all-reduced; total
+work is fixed => "strong" scaling.  Timing: CUDA events, barrier + synchronize on both sides, max
+over ranks.  `--impl reference` times the CPU oracle port on a bounded sample (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3-8b")
+    ap.add_argument("--layers", type=int, default=0, help="debug: limit decoder layers (0 = all)")
+    ap.add_argument("--samples", type=int, default=128)
+    ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--level", default="W4A16")
+    ap.add_argument("--actorder", default="group")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gguf", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_acts(T, K, device, seed):
+    """N(0,1) bf16 with 0.5 % outlier channels x20 (SURVEY §8d synthetic inputs)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn((T, K), generator=g, device=device, dtype=torch.bfloat16)
+    idx = torch.randperm(K, generator=g, device=device)[: max(1, K // 200)]
+    x[:, idx] *= 20.0
+    return x
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(shape, level, actorder, n_samples, seq, threads=None):
+    """Times the CPU oracle (torch CPU fp32, all host threads) on a bounded sample of the same
+    workload and extrapolates to the whole model by the work ratios stated in `sample`."""
+    from oracle import gptq as og
+    from compressed_tensors.quantization import ActivationOrdering
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    K, N = shape.hidden_size, shape.kv_dim          # k_proj: the smallest Linear of the layer
+    g = torch.Generator().manual_seed(0)
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    nb = 2
+    x = torch.randn((nb, seq, K), generator=g).to(torch.bfloat16)
+    args = og.scheme_weight_args(level)
+    if actorder:
+        args.actorder = ActivationOrdering.GROUP if actorder == "group" else ActivationOrdering.WEIGHT
+    H, n = og.make_empty_hessian(K), 0
+    t0 = time.perf_counter()
+    for b in range(nb):
+        H, n = og.accumulate_hessian(x[b:b + 1], H, n)
+    t_h = time.perf_counter() - t0                   # nb samples of K-wide Hessian
+    t0 = time.perf_counter()
+    og.quantize_weight(W, H, args)
+    t_q = time.perf_counter() - t0
+    # extrapolation by FLOP ratios: Hessian ~ samples * K^2 ; quantize_weight ~ (2/3... chain) K^3 + N K^2
+    L = shape.num_hidden_layers
+    dims = shape.input_dims()
+    hess_units = sum((n_samples / nb) * (k / K) ** 2 for k in dims.values()) * L
+    q_work = lambda n_, k_: (4.0 / 3.0) * k_ ** 3 + n_ * k_ ** 2
+    quant_units = sum(q_work(n_, k_) for (n_, k_) in shape.linear_shapes().values()) / q_work(N, K) * L
+    total = t_h * hess_units + t_q * quant_units
+    sample = (f"oracle port (torch CPU fp32): Hessian of {nb}x{seq} tokens at K={K} ({t_h:.2f}s) + quantize_weight of "
+              f"k_proj [{N},{K}] ({t_q:.2f}s); extrapolated to {L} layers x 7 Linears x {n_samples} samples by "
+              f"FLOP ratios (samples*K^2 ; 4/3 K^3 + N K^2) - an extrapolation, not a full CPU run")
+    return {"value": total, "unit": "s", "cores": threads, "kind": "port", "sample": sample,
+            "sample_seconds": t_h + t_q}
+
+
+def gguf_probe(device):
+    """GGUF pack GB/s vs HBM peak (second half of BASELINE's metric): one Llama-3-8B down_proj-sized
+    fp16 tensor per type, algorithmic bytes = fp16 in + packed out."""
+    from quantool_b200 import cabi
+    out = {}
+    n, k = 4096 * 4, 14336
+    x = (torch.randn((n, k), device=device) * 0.02).half()
+    for t in ("Q8_0", "Q4_0", "Q5_0", "Q4_K", "Q6_K"):
+        be, bb = cabi.gguf_block_elems(t), cabi.gguf_block_bytes(t)
+        y = torch.empty((n, k // be * bb), dtype=torch.uint8, device=device)
+        for _ in range(3):
+            cabi.gguf_quantize(x, t, out=y)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); cabi.gguf_quantize(x, t, out=y); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[len(ts) // 2]
+        byts = x.numel() * 2 + y.numel()
+        out[t] = {"ms": round(ms, 4), "GBps": round(byts / ms / 1e6, 1), "bytes_per_elem": round(byts / x.numel(), 4)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    from quantool_b200.engine import llama
+    shape = llama.SHAPES[a.model]
+    if a.layers:
+        shape = llama.LlamaShape(**{**shape.__dict__, "num_hidden_layers": a.layers})
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"gptq {a.level} g128 actorder={a.actorder} on random-init {a.model} "
+                f"({shape.num_hidden_layers} layers), {a.samples}x{a.seq}-token synthetic calibration")
+    config = {"workload": workload, "level": a.level, "actorder": a.actorder, "calibration": f"{a.samples}x{a.seq}",
+              "layers": shape.num_hidden_layers, "parallelism": f"samples+rows sharded x{world}, H all-reduce",
+              "l2": "inputs larger than L2 (13.5 GB activations + 0.44 GB weights per layer per step)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = []
+        cb = None
+        for _ in range(max(1, a.warmup and 1)):
+            cpu_reference_sample(shape, a.level, a.actorder, a.samples, a.seq)
+        for _ in range(max(1, a.steps)):
+            cb = cpu_reference_sample(shape, a.level, a.actorder, a.samples, a.seq)
+            steps.append(cb)
+        val = sum(s["value"] for s in steps) / len(steps)
+        cb["value"] = val
+        line = {"impl": "reference", "metric": "gptq_seconds_per_8b_model", "value": val, "unit": "s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * sum(s["sample_seconds"] for s in steps) / len(steps),
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from quantool_b200 import cabi
+    from quantool_b200.engine import pipeline, schemes
+    from quantool_b200.engine.gptq import compress_linear
+    d = pipeline.Dist()
+    args = schemes.resolve(a.level, a.actorder if a.actorder != "none" else None)
+
+    per = pipeline.row_split(a.samples, d.world)
+    n_local = per[d.rank]
+    T_local = n_local * a.seq
+    dims = shape.input_dims()
+    acts = {n: synth_acts(T_local, k, dev, 7 + i + 100 * d.rank) for i, (n, k) in enumerate(dims.items())}
+    L = shape.num_hidden_layers
+    weights = [llama.random_layer_weights(shape, l, dev) for l in range(L)]
+    lq = pipeline.GPTQLayerQuantizer(args, dist=d)
+    Kmax = max(dims.values())
+    hess_events = []
+
+    def hot_step(record=False):
+        for l in range(L):
+            hess = {}
+            for n, x in acts.items():
+                acc = pipeline.HessianAccumulator(x.shape[-1], dev)
+                if record and x.shape[-1] == Kmax:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); acc.add(x, n_local); e1.record()
+                    hess_events.append((e0, e1))
+                else:
+                    acc.add(x, n_local)
+                d.all_reduce_sum(acc.H)
+                hess[n] = acc.finalize(a.samples)
+            res = lq.quantize_layer(weights[l], hess)
+            for lin, r in res.items():
+                compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args)
+
+    def barrier():
+        if d.on:
+            d.dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        hot_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        hot_step(record=True)
+    e1.record()
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    d.all_reduce_max(ms_total)
+    launches = cabi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total.item() / a.steps
+    hess_ms = sum(x.elapsed_time(y) for x, y in hess_events) / max(1, len(hess_events))
+    del hess_events[:]
+
+    # roofline of the dominant single kernel: the tcgen05 Hessian SYRK at K = intermediate size
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" \
+        if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    NI, NJ = (Kmax + 127) // 128, (Kmax + 255) // 256
+    ntiles = sum(min(2 * j + 2, NI) for j in range(NJ))
+    exec_flops = 2.0 * T_local * ntiles * 128 * 256
+    ref_flops = 2.0 * T_local * Kmax * Kmax
+    roofline = {"kernel": "hessian_syrk_kernel", "bound": "tensor", "achieved": exec_flops / hess_ms / 1e9,
+                "peak": peak, "unit": "TFLOP/s", "frac": exec_flops / hess_ms / 1e9 / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": hess_ms, "shape": f"X[{T_local},{Kmax}] bf16 -> H[{Kmax},{Kmax}] fp32",
+                "algorithmic": "executed upper-triangle tile FLOPs 2*T*ntiles*128*256",
+                "reference_equivalent_tflops": ref_flops / hess_ms / 1e9}
+
+    # ---- e2e through the plugin-level entry with host buffers -------------------------------
+    e2e = None
+    if not a.no_e2e:
+        host_sd = {}
+        for l in range(L):
+            for k, v in weights[l].items():
+                host_sd[f"model.layers.{l}.{k}"] = v.cpu().pin_memory()
+        g = torch.Generator().manual_seed(1234)
+        emb = (torch.randn((shape.vocab_size, shape.hidden_size), device=dev) * 0.02).to(torch.bfloat16)
+        host_sd["model.embed_tokens.weight"] = emb.cpu().pin_memory()
+        del emb
+        token_ids = torch.randint(0, shape.vocab_size, (a.samples, a.seq), generator=g).pin_memory()
+        del weights, acts
+        lq.drop_scratch()
+        torch.cuda.empty_cache()
+        fmt = "pack-quantized"
+
+        def e2e_step():
+            return pipeline.quantize_model_gptq(shape, host_sd, token_ids, args, dev, fmt=fmt, dist=d)
+
+        e2e_step()   # warm-up (allocator, cuBLAS heuristics)
+        barrier()
+        t0 = time.perf_counter()
+        r = None
+        for _ in range(a.e2e_steps):
+            r = e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / a.e2e_steps], device=dev)
+        d.all_reduce_max(dt)
+        e2e = {"value": dt.item(), "unit": "s", "h2d_bytes_per_step": r.h2d_bytes, "d2h_bytes_per_step": r.d2h_bytes,
+               "steps": a.e2e_steps, "warmup": 1,
+               "path": "quantool_b200.engine.pipeline.quantize_model_gptq (what GPTQ.quantize() runs): pinned host "
+                       "weights + token ids -> layer forwards -> Hessians -> GPTQ -> packed host tensors"}
+
+    if rank != 0:
+        if d.on:
+            d.dist.destroy_process_group()
+        return
+    cb = None if a.no_cpu else cpu_reference_sample(shape, a.level, a.actorder, a.samples, a.seq)
+    gg = None if a.no_gguf else gguf_probe(dev)
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    if gg:
+        for t in gg.values():
+            t["frac_of_hbm_peak"] = round(t["GBps"] / hbm, 3)
+    line = {"metric": "gptq_seconds_per_8b_model", "value": ms_step / 1e3, "unit": "s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 activations -> f32 accumulate / f32 solve",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cb, "gguf_pack": gg}
+    print(json.dumps(line))
+    if d.on:
+        d.dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

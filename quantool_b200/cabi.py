@@ -24,6 +24,7 @@ _i64, _i32, _vp, _f32 = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_
 _SIGS = {
     "qt_abi_version": [],
     "qt_device_sm_count": [],
+    "qt_launch_count": [],
     "qt_gguf_block_elems": [_i32],
     "qt_gguf_block_bytes": [_i32],
     "qt_gguf_quantize": [_i32, _vp, _i32, _i32, _i64, _i64, _vp, _vp],
@@ -44,7 +45,7 @@ _SIGS = {
     "qt_gptq_permute_out": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }
-_RESTYPE = {"qt_last_error": ctypes.c_char_p}
+_RESTYPE = {"qt_last_error": ctypes.c_char_p, "qt_launch_count": ctypes.c_ulonglong}
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -69,6 +70,10 @@ def lib() -> ctypes.CDLL:
             fn.restype = _RESTYPE.get(name, ctypes.c_int)
         _lib = L
     return _lib
+
+
+def launch_count() -> int:
+    return int(lib().qt_launch_count())
 
 
 def exported_symbols():

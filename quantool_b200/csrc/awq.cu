@@ -1,0 +1,205 @@
+// AWQ scale-search kernels on sm_100a.
+//
+// Replaces UPSTREAM llmcompressor AWQModifier `_compute_best_scale`, `_pseudo_quantize_tensor`,
+// `_compute_loss` reached from
+// ref/src/quantool/methods/llm_compressor/awq/awq.py:81 via llmcompressor.oneshot at
+// ref/src/quantool/methods/llm_compressor/base.py:159-161.
+//
+//   awq_group_absmax / awq_wmean : w_mean = column mean of |W| normalised by its group's max
+//   awq_scale_qdq                : W' = pseudo_quant(W * s) / s in ONE pass over W per grid point
+//                                  (scale -> group min/max -> quantize -> dequantize -> unscale)
+//   sq_err_sum                   : sum((a - b)^2) of the parent outputs, fp32 squares, fp64 total
+//
+// torch evaluates these on the model-dtype weight: every elementwise op is "fp32 compute,
+// round to the tensor dtype".  DT reproduces that rounding after each op.  All HBM-bound.
+#include "common.cuh"
+
+namespace qt {
+namespace awq {
+
+template <int DT>
+QT_D float rnd(float v) {
+    if (DT == QT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    if (DT == QT_F16) return __half2float(__float2half_rn(v));
+    return v;
+}
+template <int DT>
+QT_D float ld(const void* p, long long i) {
+    if (DT == QT_F32) return reinterpret_cast<const float*>(p)[i];
+    if (DT == QT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+template <int DT>
+QT_D void st(void* p, long long i, float v) {
+    if (DT == QT_F32) reinterpret_cast<float*>(p)[i] = v;
+    else if (DT == QT_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// one warp per row, loop over groups: gamax[n][g] = max |W[n][g*gs .. (g+1)*gs)|
+template <int DT>
+__global__ void __launch_bounds__(256) group_absmax_kernel(const void* __restrict__ W, int N, int K, int gs,
+                                                           float* __restrict__ gamax) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const int G = K / gs;
+    for (int g = 0; g < G; g++) {
+        float m = 0.f;
+        for (int c = lane; c < gs; c += 32) m = fmaxf(m, fabsf(ld<DT>(W, (long long)row * K + (long long)g * gs + c)));
+        m = warp_max(m);
+        if (lane == 0) gamax[(long long)row * G + g] = m;
+    }
+}
+
+// colsum[c] += sum_n rnd(|W[n][c]| / rnd(gamax[n][c/gs] + 1e-6))
+template <int DT>
+__global__ void __launch_bounds__(256) wmean_kernel(const void* __restrict__ W, const float* __restrict__ gamax,
+                                                    int N, int K, int gs, float* __restrict__ colsum) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= K) return;
+    const int G = K / gs, g = c / gs;
+    float acc = 0.f;
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const float den = rnd<DT>(gamax[(long long)n * G + g] + rnd<DT>(1e-6f));
+        acc += rnd<DT>(fabsf(ld<DT>(W, (long long)n * K + c)) / den);
+    }
+    atomicAdd(colsum + c, acc);
+}
+
+// out[n][c] = rnd( pq( rnd(W[n][c] * s[c]) ) / s[c] )   (pq = _pseudo_quantize_tensor per group)
+template <int DT>
+__global__ void __launch_bounds__(256) scale_qdq_kernel(const void* __restrict__ W, const float* __restrict__ s,
+                                                        int N, int K, int gs, int num_bits, int symmetric,
+                                                        void* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const int G = K / gs;
+    for (int g = 0; g < G; g++) {
+        const long long base = (long long)row * K + (long long)g * gs;
+        const float* sg = s + (long long)g * gs;
+        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+        for (int c = lane; c < gs; c += 32) {
+            const float v = rnd<DT>(ld<DT>(W, base + c) * sg[c]);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (symmetric) {
+            const float max_int = (float)((1 << (num_bits - 1)) - 1), min_int = -(float)(1 << (num_bits - 1));
+            const float max_val = fmaxf(fmaxf(fabsf(mn), fabsf(mx)), rnd<DT>(1e-5f));
+            const float sc = rnd<DT>(max_val / max_int);
+            for (int c = lane; c < gs; c += 32) {
+                const float v = rnd<DT>(ld<DT>(W, base + c) * sg[c]);
+                float q = rintf(rnd<DT>(v / sc));
+                q = fminf(fmaxf(q, min_int), max_int);
+                const float dq = rnd<DT>(q * sc);
+                st<DT>(out, base + c, dq / sg[c]);
+            }
+        } else {
+            const float max_int = (float)((1 << num_bits) - 1);
+            const float sc = rnd<DT>(fmaxf(rnd<DT>(mx - mn), rnd<DT>(1e-5f)) / max_int);
+            float z = -rintf(rnd<DT>(mn / sc));
+            z = fminf(fmaxf(z, 0.f), max_int);
+            for (int c = lane; c < gs; c += 32) {
+                const float v = rnd<DT>(ld<DT>(W, base + c) * sg[c]);
+                float q = rnd<DT>(rintf(rnd<DT>(v / sc)) + z);
+                q = fminf(fmaxf(q, 0.f), max_int);
+                const float dq = rnd<DT>(rnd<DT>(q - z) * sc);
+                st<DT>(out, base + c, dq / sg[c]);
+            }
+        }
+    }
+}
+
+// sum over i of rnd(a[i] - b[i])^2 ; fp32 per-thread partials, fp64 block total -> atomicAdd(double)
+template <int DT>
+__global__ void __launch_bounds__(256) sq_err_kernel(const void* __restrict__ a, const void* __restrict__ b,
+                                                     long long n, double* __restrict__ out) {
+    __shared__ double red[8];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float d = rnd<DT>(ld<DT>(a, i) - ld<DT>(b, i));
+        acc = fmaf(d, d, acc);
+    }
+    double v = (double)acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        atomicAdd(out, t);
+    }
+}
+
+}  // namespace awq
+}  // namespace qt
+
+using namespace qt;
+using namespace qt::awq;
+
+extern "C" {
+
+// colsum [K] fp32 += column sums of the group-normalised |W| [N, K]; gamax_scratch is [N, K/gs] fp32.
+// group_size <= 0 means one group per row.  The caller divides by the total row count.
+int qt_awq_wmean_accumulate(const void* W, int dtype, int N, int K, int group_size, float* gamax_scratch,
+                            float* colsum, void* stream) {
+    if (!W || !gamax_scratch || !colsum || N <= 0 || K <= 0) return QT_ERR_INVALID;
+    const int gs = group_size > 0 ? group_size : K;
+    if (K % gs) return QT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (K + 255) / 256;
+    int gy = kNumSMs * 8 / gx + 1;
+    if (gy > N) gy = N;
+#define QT_RUN(DT)                                                                          \
+    group_absmax_kernel<DT><<<(N + 7) / 8, 256, 0, st>>>(W, N, K, gs, gamax_scratch);        \
+    wmean_kernel<DT><<<dim3(gx, gy), 256, 0, st>>>(W, gamax_scratch, N, K, gs, colsum);
+    switch (dtype) {
+        case QT_F32: QT_RUN(QT_F32) break;
+        case QT_F16: QT_RUN(QT_F16) break;
+        case QT_BF16: QT_RUN(QT_BF16) break;
+        default: return QT_ERR_INVALID;
+    }
+#undef QT_RUN
+    int rc = check_launch("awq_wmean");
+    return rc ? rc : check_launch("awq_wmean");
+}
+
+int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int group_size, int num_bits,
+                     int symmetric, void* out, void* stream) {
+    if (!W || !s || !out || N <= 0 || K <= 0 || num_bits < 2 || num_bits > 8) return QT_ERR_INVALID;
+    const int gs = group_size > 0 ? group_size : K;
+    if (K % gs) return QT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (N + 7) / 8;
+    switch (dtype) {
+        case QT_F32: scale_qdq_kernel<QT_F32><<<grid, 256, 0, st>>>(W, s, N, K, gs, num_bits, symmetric, out); break;
+        case QT_F16: scale_qdq_kernel<QT_F16><<<grid, 256, 0, st>>>(W, s, N, K, gs, num_bits, symmetric, out); break;
+        case QT_BF16: scale_qdq_kernel<QT_BF16><<<grid, 256, 0, st>>>(W, s, N, K, gs, num_bits, symmetric, out); break;
+        default: return QT_ERR_INVALID;
+    }
+    return check_launch("awq_scale_qdq");
+}
+
+// *out (device double, zeroed by the caller) += sum (a - b)^2 over n elements
+int qt_sq_err_sum(const void* a, const void* b, int dtype, int64_t n, double* out, void* stream) {
+    if (!a || !b || !out || n < 0) return QT_ERR_INVALID;
+    if (n == 0) return QT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    switch (dtype) {
+        case QT_F32: sq_err_kernel<QT_F32><<<(unsigned)blocks, 256, 0, st>>>(a, b, n, out); break;
+        case QT_F16: sq_err_kernel<QT_F16><<<(unsigned)blocks, 256, 0, st>>>(a, b, n, out); break;
+        case QT_BF16: sq_err_kernel<QT_BF16><<<(unsigned)blocks, 256, 0, st>>>(a, b, n, out); break;
+        default: return QT_ERR_INVALID;
+    }
+    return check_launch("sq_err_sum");
+}
+
+}  // extern "C"

@@ -22,6 +22,7 @@ namespace qt {
 
 void set_last_error(const char* what, cudaError_t e);
 int check_launch(const char* what);
+unsigned long long launch_count();
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

@@ -1,0 +1,193 @@
+"""Llama-family decoder plumbing for the sequential calibration driver.
+
+What upstream's SequentialPipeline gets from `transformers` (SURVEY.md §3.1 "HOT LOOP 1/2"):
+run one decoder layer at a time over the calibration batches, exposing the inputs of every
+Linear.  This is plumbing around the quantization kernels - plain torch ops (cuBLAS GEMMs,
+SDPA) on the device - written functionally so a layer's weights can be swapped for their
+quantized versions between the two passes.
+
+Weights follow the HF checkpoint naming (`model.layers.{i}.self_attn.q_proj.weight`, ...).
+"""
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+LINEARS = ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
+           "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj")
+# which captured activation feeds which Linear (4 distinct inputs per layer)
+INPUT_OF = {"self_attn.q_proj": "attn_in", "self_attn.k_proj": "attn_in", "self_attn.v_proj": "attn_in",
+            "self_attn.o_proj": "o_in", "mlp.gate_proj": "mlp_in", "mlp.up_proj": "mlp_in",
+            "mlp.down_proj": "down_in"}
+
+
+@dataclass
+class LlamaShape:
+    hidden_size: int
+    intermediate_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    vocab_size: int
+    head_dim: Optional[int] = None
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    tie_word_embeddings: bool = False
+    max_position_embeddings: int = 8192
+
+    def __post_init__(self):
+        if self.head_dim is None:
+            self.head_dim = self.hidden_size // self.num_attention_heads
+
+    @property
+    def kv_dim(self):
+        return self.num_key_value_heads * self.head_dim
+
+    @property
+    def q_dim(self):
+        return self.num_attention_heads * self.head_dim
+
+    def linear_shapes(self) -> Dict[str, tuple]:
+        h, i = self.hidden_size, self.intermediate_size
+        return {"self_attn.q_proj": (self.q_dim, h), "self_attn.k_proj": (self.kv_dim, h),
+                "self_attn.v_proj": (self.kv_dim, h), "self_attn.o_proj": (h, self.q_dim),
+                "mlp.gate_proj": (i, h), "mlp.up_proj": (i, h), "mlp.down_proj": (h, i)}
+
+    def input_dims(self) -> Dict[str, int]:
+        return {"attn_in": self.hidden_size, "o_in": self.q_dim, "mlp_in": self.hidden_size,
+                "down_in": self.intermediate_size}
+
+    def to_hf_config(self) -> dict:
+        return {"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": self.hidden_size,
+                "intermediate_size": self.intermediate_size, "num_hidden_layers": self.num_hidden_layers,
+                "num_attention_heads": self.num_attention_heads, "num_key_value_heads": self.num_key_value_heads,
+                "head_dim": self.head_dim, "vocab_size": self.vocab_size, "rms_norm_eps": self.rms_norm_eps,
+                "rope_theta": self.rope_theta, "tie_word_embeddings": self.tie_word_embeddings,
+                "max_position_embeddings": self.max_position_embeddings, "hidden_act": "silu",
+                "torch_dtype": "bfloat16", "attention_bias": False, "mlp_bias": False}
+
+    @staticmethod
+    def from_hf_config(cfg: dict) -> "LlamaShape":
+        rope = cfg.get("rope_theta")
+        if rope is None and isinstance(cfg.get("rope_parameters"), dict):
+            rope = cfg["rope_parameters"].get("rope_theta")
+        return LlamaShape(hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                          num_hidden_layers=cfg["num_hidden_layers"],
+                          num_attention_heads=cfg["num_attention_heads"],
+                          num_key_value_heads=cfg.get("num_key_value_heads", cfg["num_attention_heads"]),
+                          vocab_size=cfg["vocab_size"], head_dim=cfg.get("head_dim"),
+                          rms_norm_eps=cfg.get("rms_norm_eps", 1e-5), rope_theta=rope or 10000.0,
+                          tie_word_embeddings=cfg.get("tie_word_embeddings", False),
+                          max_position_embeddings=cfg.get("max_position_embeddings", 8192))
+
+
+# the shapes BASELINE.json names (SURVEY.md §8 header)
+SHAPES = {
+    "smollm2-135m": LlamaShape(576, 1536, 30, 9, 3, 49152, rope_theta=100000.0, tie_word_embeddings=True),
+    "llama-3.2-1b": LlamaShape(2048, 8192, 16, 32, 8, 128256, head_dim=64, tie_word_embeddings=True),
+    "llama-3-8b": LlamaShape(4096, 14336, 32, 32, 8, 128256),
+    "llama-3-70b": LlamaShape(8192, 28672, 80, 64, 8, 128256),
+}
+
+
+def random_layer_weights(shape: LlamaShape, layer: int, device, dtype=torch.bfloat16, seed: int = 0,
+                         pin: bool = False) -> Dict[str, torch.Tensor]:
+    """Random-init weights of one decoder layer (normal(0, 0.02) like HF `initializer_range`)."""
+    g = torch.Generator(device=device).manual_seed(seed * 100003 + layer)
+    out = {}
+    for name, (n, k) in shape.linear_shapes().items():
+        w = (torch.randn((n, k), generator=g, device=device, dtype=torch.float32) * 0.02).to(dtype)
+        out[f"{name}.weight"] = w
+    out["input_layernorm.weight"] = torch.ones(shape.hidden_size, device=device, dtype=dtype)
+    out["post_attention_layernorm.weight"] = torch.ones(shape.hidden_size, device=device, dtype=dtype)
+    if pin and str(device) == "cpu":
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+def random_state_dict(shape: LlamaShape, dtype=torch.bfloat16, seed: int = 0, device="cpu") -> Dict[str, torch.Tensor]:
+    """Whole-model random init in HF key names (host tensors by default)."""
+    sd = {}
+    g = torch.Generator(device=device).manual_seed(seed * 100003 + 99991)
+    sd["model.embed_tokens.weight"] = (torch.randn((shape.vocab_size, shape.hidden_size), generator=g,
+                                                   device=device) * 0.02).to(dtype)
+    for l in range(shape.num_hidden_layers):
+        for k, v in random_layer_weights(shape, l, device, dtype, seed).items():
+            sd[f"model.layers.{l}.{k}"] = v
+    sd["model.norm.weight"] = torch.ones(shape.hidden_size, device=device, dtype=dtype)
+    if not shape.tie_word_embeddings:
+        sd["lm_head.weight"] = (torch.randn((shape.vocab_size, shape.hidden_size), generator=g,
+                                            device=device) * 0.02).to(dtype)
+    return sd
+
+
+def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    xf = x.float()
+    xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return (w * xf.to(x.dtype))
+
+
+def rope_tables(shape: LlamaShape, seq: int, device, dtype):
+    inv = 1.0 / (shape.rope_theta ** (torch.arange(0, shape.head_dim, 2, device=device, dtype=torch.float32)
+                                     / shape.head_dim))
+    t = torch.arange(seq, device=device, dtype=torch.float32)
+    f = torch.outer(t, inv)
+    emb = torch.cat((f, f), dim=-1)
+    return emb.cos().to(dtype), emb.sin().to(dtype)
+
+
+def _rot_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def layer_forward(shape: LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor, cos, sin,
+                  capture: Optional[Dict[str, torch.Tensor]] = None, row0: int = 0) -> torch.Tensor:
+    """h: [B, S, hidden].  If `capture` is given, the inputs of the Linears are written into
+    capture[name][row0 : row0 + B*S] (preallocated [T, K] buffers)."""
+    B, S, _ = h.shape
+    nh, nkv, hd = shape.num_attention_heads, shape.num_key_value_heads, shape.head_dim
+
+    def cap(name, t):
+        if capture is not None:
+            capture[name][row0: row0 + B * S].copy_(t.reshape(B * S, -1))
+
+    x = rms_norm(h, w["input_layernorm.weight"], shape.rms_norm_eps)
+    cap("attn_in", x)
+    q = F.linear(x, w["self_attn.q_proj.weight"]).view(B, S, nh, hd).transpose(1, 2)
+    k = F.linear(x, w["self_attn.k_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
+    v = F.linear(x, w["self_attn.v_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
+    c, s = cos[None, None], sin[None, None]
+    q = q * c + _rot_half(q) * s
+    k = k * c + _rot_half(k) * s
+    a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=(nkv != nh))
+    a = a.transpose(1, 2).reshape(B, S, nh * hd)
+    cap("o_in", a)
+    h = h + F.linear(a, w["self_attn.o_proj.weight"])
+    x = rms_norm(h, w["post_attention_layernorm.weight"], shape.rms_norm_eps)
+    cap("mlp_in", x)
+    d = F.silu(F.linear(x, w["mlp.gate_proj.weight"])) * F.linear(x, w["mlp.up_proj.weight"])
+    cap("down_in", d)
+    return h + F.linear(d, w["mlp.down_proj.weight"])
+
+
+def attention_forward(shape: LlamaShape, w: Dict[str, torch.Tensor], x: torch.Tensor, cos, sin) -> torch.Tensor:
+    """self_attn(x) on normed input x [B,S,hidden] -> [B,S,hidden] (AWQ parent module of q/k/v)."""
+    B, S, _ = x.shape
+    nh, nkv, hd = shape.num_attention_heads, shape.num_key_value_heads, shape.head_dim
+    q = F.linear(x, w["self_attn.q_proj.weight"]).view(B, S, nh, hd).transpose(1, 2)
+    k = F.linear(x, w["self_attn.k_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
+    v = F.linear(x, w["self_attn.v_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
+    c, s = cos[None, None], sin[None, None]
+    q = q * c + _rot_half(q) * s
+    k = k * c + _rot_half(k) * s
+    a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=(nkv != nh))
+    a = a.transpose(1, 2).reshape(B, S, nh * hd)
+    return F.linear(a, w["self_attn.o_proj.weight"])
+
+
+def mlp_forward(w: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    return F.linear(F.silu(F.linear(x, w["mlp.gate_proj.weight"])) * F.linear(x, w["mlp.up_proj.weight"]),
+                    w["mlp.down_proj.weight"])

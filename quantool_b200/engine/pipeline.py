@@ -1,0 +1,331 @@
+"""Sequential calibration driver: layer-by-layer GPTQ / SmoothQuant+GPTQ / AWQ over a Llama model.
+
+B200-native stand-in for what `llmcompressor.oneshot` does underneath the reference's call at
+ref/src/quantool/methods/llm_compressor/base.py:159-161: for each decoder
+layer, run the calibration batches through it, accumulate per-Linear statistics, quantize the
+layer's Linears, then re-run the batches through the quantized layer to feed the next one.
+
+Single node, one process per GPU:
+  * calibration samples are split across ranks; each unique Hessian is summed with ONE NCCL
+    all-reduce over NVLink before the 2/n scaling;
+  * the inverse-Hessian factor of each distinct input is computed on one rank (distinct
+    inputs go to different ranks) and broadcast;
+  * output rows of every Linear are split across ranks for the column loop (rows are
+    independent given U), and the fake-quantized rows / scales are all-gathered.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import cabi
+from . import llama
+from .gptq import HessianAccumulator
+from .schemes import WeightArgs
+
+
+class Dist:
+    """Thin view of torch.distributed (NCCL on GPUs, gloo in CPU tests); world_size 1 = no-op."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.rank = dist.get_rank() if self.on else 0
+        self.world = dist.get_world_size() if self.on else 1
+
+    def all_reduce_sum(self, t):
+        if self.on:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t
+
+    def all_reduce_max(self, t):
+        if self.on:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t
+
+    def all_reduce_min(self, t):
+        if self.on:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return t
+
+    def broadcast(self, t, src):
+        if self.on:
+            self.dist.broadcast(t, src=src)
+        return t
+
+    def all_gather_rows(self, local: torch.Tensor, sizes: List[int]) -> torch.Tensor:
+        """Concatenate per-rank row blocks (sizes may be ragged) along dim 0."""
+        if not self.on:
+            return local
+        mx = max(sizes)
+        pad = local
+        if local.shape[0] < mx:
+            pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            pad[: local.shape[0]] = local
+        outs = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(outs, pad.contiguous())
+        return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
+
+
+def row_split(n: int, world: int, align: int = 1) -> List[int]:
+    """Split n rows over `world` ranks in `align`-row units, remainder to the first ranks."""
+    units = (n + align - 1) // align
+    base, rem = divmod(units, world)
+    sizes = []
+    left = n
+    for r in range(world):
+        s = min(left, (base + (1 if r < rem else 0)) * align)
+        sizes.append(s)
+        left -= s
+    return sizes
+
+
+@dataclass
+class InputContext:
+    """Everything that depends only on one distinct Linear input (shared by q/k/v, gate/up)."""
+    K: int
+    perm: Optional[torch.Tensor]
+    inv_perm: Optional[torch.Tensor]
+    U: torch.Tensor
+    dead: torch.Tensor
+    info: torch.Tensor
+
+
+@dataclass
+class LinearResult:
+    weight: torch.Tensor
+    scale: torch.Tensor
+    zero_point: torch.Tensor
+    g_idx: Optional[torch.Tensor]
+    loss: torch.Tensor
+
+
+class GPTQLayerQuantizer:
+    def __init__(self, args: WeightArgs, blocksize: int = 128, percdamp: float = 0.01, dist: Optional[Dist] = None):
+        if blocksize != 128:
+            raise ValueError("the sm_100a GPTQ kernel is specialised for block_size=128 (upstream default)")
+        self.args = args
+        self.percdamp = percdamp
+        self.dist = dist or Dist()
+        self._scratch: Dict[tuple, torch.Tensor] = {}
+        self.launches = 0   # C-ABI calls issued (each is >= 1 kernel launch)
+
+    def _buf(self, tag: str, shape, dtype, device):
+        key = (tag, tuple(shape), dtype, str(device))
+        t = self._scratch.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self._scratch[key] = t
+        return t
+
+    def drop_scratch(self):
+        self._scratch.clear()
+
+    # ---- per distinct input -------------------------------------------------------------
+    def prepare_input(self, H: torch.Tensor, owner: int = 0) -> InputContext:
+        """H: finalized (scaled, symmetric) fp32 [K,K], identical on every rank."""
+        K = H.shape[0]
+        dev = H.device
+        d = self.dist
+        perm = inv_perm = None
+        if self.args.actorder in ("group", "weight"):
+            perm = torch.argsort(torch.diagonal(H), descending=True, stable=True).to(torch.int32)
+            inv_perm = torch.argsort(perm).to(torch.int32)
+        U = self._buf("U", (K, K), torch.float32, dev)
+        info = torch.zeros((1,), dtype=torch.int32, device=dev)
+        dead = torch.empty((K,), dtype=torch.uint8, device=dev)
+        if (not d.on) or d.rank == owner % d.world:
+            damp = self._buf("damp", (1,), torch.float32, dev)
+            perm_p = perm
+            cabi._check(cabi.lib().qt_gptq_prepare_hessian(cabi._p(H), cabi._p(perm_p), K, float(self.percdamp),
+                                                           cabi._p(U), cabi._p(dead), cabi._p(damp),
+                                                           cabi._stream()), "qt_gptq_prepare_hessian")
+            X = self._buf("X", (K, K), torch.float32, dev)
+            W = self._buf("W", (K, K), torch.float32, dev)
+            cabi._check(cabi.lib().qt_gptq_hinv_factor(cabi._p(U), cabi._p(X), cabi._p(W), K, cabi._p(info),
+                                                       cabi._stream()), "qt_gptq_hinv_factor")
+            self.launches += 2
+        if d.on:
+            d.broadcast(U, owner % d.world)
+            d.broadcast(info, owner % d.world)
+            d.broadcast(dead, owner % d.world)
+        return InputContext(K, perm, inv_perm, U, dead, info)
+
+    # ---- per Linear ---------------------------------------------------------------------
+    def quantize_linear(self, weight: torch.Tensor, ctx: InputContext) -> LinearResult:
+        a = self.args
+        d = self.dist
+        N, K = weight.shape
+        dev = weight.device
+        sizes = row_split(N, d.world, 16)
+        r0 = sum(sizes[: d.rank])
+        nloc = sizes[d.rank]
+        wl = weight[r0: r0 + nloc].contiguous()
+        g_idx_perm = None
+        gs = a.group_size or 0
+        if a.strategy == "channel":
+            mode = cabi.GPTQ_MODE_CHANNEL
+            G = 1
+        else:
+            if K % gs:
+                raise ValueError(f"tensor column shape must be divisble by the given group_size {gs} but got {K}")
+            G = K // gs
+            mode = cabi.GPTQ_MODE_STATIC_GIDX if a.actorder == "weight" else cabi.GPTQ_MODE_GROUP_REFIT
+            if a.actorder == "weight":
+                g_idx_perm = (torch.arange(K, device=dev, dtype=torch.int32) // gs)[ctx.perm.long()].contiguous()
+        if nloc > 0:
+            if mode == cabi.GPTQ_MODE_GROUP_REFIT:
+                scale = torch.empty((nloc, G), dtype=torch.float32, device=dev)
+                zp = torch.empty((nloc, G), dtype=torch.float32, device=dev)
+            else:
+                scale, zp = cabi.minmax_qparams(wl.float(), gs, a.num_bits, a.symmetric)
+                self.launches += 1
+            wp = cabi.gptq_permute_in(wl, ctx.perm, ctx.dead)
+            err = self._buf("err", (nloc, 128), torch.float32, dev)
+            losses = cabi.gptq_quantize_weight(wp, ctx.U, scale, zp, g_idx_perm, gs, a.num_bits, a.symmetric, mode,
+                                               err_scratch=err)
+            wq = cabi.gptq_permute_out(wp, ctx.inv_perm, weight.dtype)
+            self.launches += 2 + 2 * ((K + 127) // 128)
+            loss = losses.sum()
+        else:
+            scale = torch.empty((0, G), dtype=torch.float32, device=dev)
+            zp = torch.empty((0, G), dtype=torch.float32, device=dev)
+            wq = torch.empty((0, K), dtype=weight.dtype, device=dev)
+            loss = torch.zeros((), dtype=torch.float32, device=dev)
+        scale_m = scale.to(weight.dtype)
+        zp8 = zp.to(torch.int8)
+        if d.on:
+            wq = d.all_gather_rows(wq, sizes)
+            scale_m = d.all_gather_rows(scale_m, sizes)
+            zp8 = d.all_gather_rows(zp8, sizes)
+            loss = d.all_reduce_sum(loss.reshape(1)).reshape(())
+        g_idx = None
+        if a.strategy == "group" and a.actorder == "group":
+            g_idx = (torch.arange(K, device=dev, dtype=torch.int32) // gs)[ctx.inv_perm.long()].contiguous()
+        return LinearResult(wq, scale_m, zp8, g_idx, loss)
+
+    # ---- one decoder layer from ready-made activations ----------------------------------
+    def quantize_layer(self, weights: Dict[str, torch.Tensor], hessians: Dict[str, torch.Tensor],
+                       linears=llama.LINEARS, input_of=llama.INPUT_OF) -> Dict[str, LinearResult]:
+        """hessians: finalized H per distinct input name.  Returns per-Linear results; the
+        identity fallback of upstream (LinAlgError -> Hinv = I) is applied per input."""
+        names = sorted(hessians, key=lambda n: -hessians[n].shape[0])
+        out: Dict[str, LinearResult] = {}
+        # One U buffer per K is reused, so finish all Linears of an input before the next input
+        for idx, inp in enumerate(names):
+            ctx = self.prepare_input(hessians[inp], owner=idx)
+            if int(ctx.info.item()) != 0:
+                cabi.set_identity(ctx.U)
+            for lin in linears:
+                if input_of[lin] == inp:
+                    out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx)
+        return out
+
+
+def accumulate_layer_hessians(inputs: Dict[str, torch.Tensor], n_samples_local: int, n_samples_total: int,
+                              dist: Optional[Dist] = None) -> Dict[str, torch.Tensor]:
+    """inputs: name -> [T_local, K] bf16 activations.  One tcgen05 SYRK launch per distinct
+    input, one all-reduce, one finalize."""
+    dist = dist or Dist()
+    out = {}
+    for name, x in inputs.items():
+        acc = HessianAccumulator(x.shape[-1], x.device)
+        acc.add(x, n_samples_local)
+        dist.all_reduce_sum(acc.H)
+        out[name] = acc.finalize(n_samples_total)
+    return out
+
+
+@dataclass
+class ModelQuantResult:
+    tensors: Dict[str, torch.Tensor] = field(default_factory=dict)   # host tensors, artifact key names
+    losses: Dict[str, float] = field(default_factory=dict)
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    launches: int = 0
+
+
+def _to_dev(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device, non_blocking=True)
+
+
+def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor], token_ids: torch.Tensor,
+                        args: WeightArgs, device, fmt: str = "pack-quantized", percdamp: float = 0.01,
+                        chunk_samples: int = 8, smooth_strength: Optional[float] = None,
+                        dist: Optional[Dist] = None, ignore=("lm_head",), progress=None) -> ModelQuantResult:
+    """Host weights + host token ids -> host artifact tensors.  Everything between the H2D copy
+    of a layer's weights and the D2H copy of its packed tensors stays on the device.
+    `smooth_strength` not None runs the SmoothQuant pass on each layer first (reference recipe
+    [SmoothQuantModifier, GPTQModifier], ref/.../smoothquant/smoothquant.py:77-84)."""
+    from .gptq import compress_linear
+    dist = dist or Dist()
+    res = ModelQuantResult()
+    dev = torch.device(device)
+    n_total, seq = token_ids.shape
+    # sample sharding
+    per = row_split(n_total, dist.world)
+    s0 = sum(per[: dist.rank])
+    ids = token_ids[s0: s0 + per[dist.rank]].to(dev)
+    res.h2d_bytes += ids.numel() * ids.element_size()
+    n_local = ids.shape[0]
+    emb = _to_dev(host_sd["model.embed_tokens.weight"], dev)
+    res.h2d_bytes += emb.numel() * emb.element_size()
+    h = torch.nn.functional.embedding(ids, emb)
+    del emb
+    cos, sin = llama.rope_tables(shape, seq, dev, h.dtype)
+    lq = GPTQLayerQuantizer(args, percdamp=percdamp, dist=dist)
+    dims = shape.input_dims()
+    for l in range(shape.num_hidden_layers):
+        pre = f"model.layers.{l}."
+        w = {}
+        for k, v in host_sd.items():
+            if k.startswith(pre):
+                w[k[len(pre):]] = _to_dev(v, dev)
+                res.h2d_bytes += v.numel() * v.element_size()
+        if smooth_strength is not None:
+            from .smoothquant import smooth_layer
+            smooth_layer(shape, w, h, cos, sin, smooth_strength, chunk_samples, dist)
+        # pass 1: statistics with the layer's original weights
+        accs = {n: HessianAccumulator(k, dev) for n, k in dims.items()}
+        cap = {n: torch.empty((chunk_samples * seq, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
+        for c0 in range(0, n_local, chunk_samples):
+            hb = h[c0: c0 + chunk_samples]
+            rows = hb.shape[0] * seq
+            llama.layer_forward(shape, w, hb, cos, sin, capture=cap, row0=0)
+            for n in dims:
+                accs[n].add(cap[n][:rows], hb.shape[0])
+                lq.launches += 1
+        del cap
+        hess = {}
+        for n in dims:
+            dist.all_reduce_sum(accs[n].H)
+            hess[n] = accs[n].finalize(n_total)
+            lq.launches += 1
+        results = lq.quantize_layer(w, hess)
+        del hess, accs
+        for lin, r in results.items():
+            w[f"{lin}.weight"] = r.weight
+            art, _codes = compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args, fmt=fmt)
+            lq.launches += 2
+            if dist.rank == 0:
+                for k, t in art.items():
+                    th = t.cpu() if t.is_cuda else t
+                    res.tensors[f"{pre}{lin}.{k}"] = th
+                    res.d2h_bytes += th.numel() * th.element_size()
+                res.losses[f"{pre}{lin}"] = float(r.loss.item())
+        if dist.rank == 0:
+            for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
+                res.tensors[pre + k] = w[k].cpu()
+        # pass 2: propagate through the quantized layer
+        for c0 in range(0, n_local, chunk_samples):
+            h[c0: c0 + chunk_samples] = llama.layer_forward(shape, w, h[c0: c0 + chunk_samples], cos, sin)
+        del w
+        if progress:
+            progress(l)
+    if dist.rank == 0:
+        for k in ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight"):
+            if k in host_sd:
+                res.tensors[k] = host_sd[k]
+    res.launches = lq.launches
+    return res
