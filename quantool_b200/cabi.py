@@ -43,6 +43,14 @@ _SIGS = {
     "qt_sgemm": [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _vp],
     "qt_gptq_permute_in": [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp],
     "qt_gptq_permute_out": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "qt_fill_f32": [_vp, _i32, _f32, _vp],
+    "qt_channel_minmax": [_vp, _i32, _i64, _i32, _vp, _vp, _vp],
+    "qt_channel_abs_sum": [_vp, _i32, _i64, _i32, _vp, _vp],
+    "qt_smooth_scales": [_vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _i32, _vp],
+    "qt_scale_matrix": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
+    "qt_awq_wmean_accumulate": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "qt_awq_scale_qdq": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
+    "qt_sq_err_sum": [_vp, _vp, _i32, _i64, _vp, _vp],
     "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }
 _RESTYPE = {"qt_last_error": ctypes.c_char_p, "qt_launch_count": ctypes.c_ulonglong}
@@ -316,3 +324,98 @@ def gptq_quantize_weight(wp: torch.Tensor, U: torch.Tensor, scale: torch.Tensor,
                                              N, K, G, max(group_size, 0), num_bits, int(symmetric), mode,
                                              _stream()), "qt_gptq_quantize_weight")
     return losses
+
+
+# ---------------------------------------------------------------------------------------
+# SmoothQuant / AWQ reductions and folds
+# ---------------------------------------------------------------------------------------
+FLT_MAX = 3.4028234663852886e38
+
+
+def new_minmax(K: int, device):
+    mn = torch.full((K,), FLT_MAX, dtype=torch.float32, device=device)
+    mx = torch.full((K,), -FLT_MAX, dtype=torch.float32, device=device)
+    return mn, mx
+
+
+def channel_minmax(x: torch.Tensor, mn: torch.Tensor, mx: torch.Tensor) -> None:
+    """Running per-channel min/max over the rows of x [T, K] into fp32 mn/mx [K]."""
+    _dev(x, "x")
+    x2 = x.reshape(-1, x.shape[-1])
+    T, K = x2.shape
+    with torch.cuda.device(x.device):
+        _check(lib().qt_channel_minmax(_p(x2), _DT[x2.dtype], T, K, _p(mn), _p(mx), _stream()), "qt_channel_minmax")
+
+
+def channel_abs_sum(x: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc [K] fp32 += sum over rows of |x|."""
+    _dev(x, "x")
+    x2 = x.reshape(-1, x.shape[-1])
+    T, K = x2.shape
+    with torch.cuda.device(x.device):
+        _check(lib().qt_channel_abs_sum(_p(x2), _DT[x2.dtype], T, K, _p(acc), _stream()), "qt_channel_abs_sum")
+
+
+def smooth_scales(amin, amax, wmin, wmax, alpha: float, compute_dtype: torch.dtype) -> torch.Tensor:
+    K = amin.shape[0]
+    out = torch.empty((K,), dtype=torch.float32, device=amin.device)
+    with torch.cuda.device(amin.device):
+        _check(lib().qt_smooth_scales(_p(amin), _p(amax), _p(wmin), _p(wmax), float(alpha), float(1 - alpha),
+                                      _DT[compute_dtype], _p(out), K, _stream()), "qt_smooth_scales")
+    return out
+
+
+def scale_matrix_(w: torch.Tensor, s: torch.Tensor, divide: bool = False, by_row: bool = False) -> None:
+    """In place, in w's dtype: w[n][c] *= s[c] (or /=; by_row: s[n]).  1-D w is treated as one row."""
+    _dev(w, "w"); _dev(s, "s")
+    assert s.dtype == torch.float32
+    N, K = (1, w.shape[0]) if w.dim() == 1 else w.shape
+    assert s.numel() == (N if by_row else K)
+    with torch.cuda.device(w.device):
+        for r0 in range(0, N, 65535):
+            n = min(65535, N - r0)
+            ptr = ctypes.c_void_p(w.data_ptr() + r0 * K * w.element_size())
+            sp = ctypes.c_void_p(s.data_ptr() + (r0 * 4 if by_row else 0))
+            _check(lib().qt_scale_matrix(ptr, _DT[w.dtype], n, K, sp, int(divide), int(by_row), _stream()),
+                   "qt_scale_matrix")
+
+
+def awq_wmean(weights, group_size: int) -> torch.Tensor:
+    """Column mean of the group-normalised |W| over the concatenated balance weights; result in
+    the weights' dtype (torch: bf16 ops, fp32-accumulated mean)."""
+    K = weights[0].shape[1]
+    dev = weights[0].device
+    acc = torch.zeros((K,), dtype=torch.float32, device=dev)
+    total = 0
+    gs = group_size if group_size and group_size > 0 else 0
+    with torch.cuda.device(dev):
+        for w in weights:
+            _dev(w, "w")
+            N = w.shape[0]
+            scratch = torch.empty((N, K // gs if gs else 1), dtype=torch.float32, device=dev)
+            _check(lib().qt_awq_wmean_accumulate(_p(w), _DT[w.dtype], N, K, gs, _p(scratch), _p(acc), _stream()),
+                   "qt_awq_wmean_accumulate")
+            total += N
+    return (acc / total).to(weights[0].dtype)
+
+
+def awq_scale_qdq(w: torch.Tensor, s: torch.Tensor, group_size: int, num_bits: int, symmetric: bool,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """W' = pseudo_quant(W * s) / s in one pass (AWQ grid-search candidate weight), w's dtype."""
+    _dev(w, "w"); _dev(s, "s")
+    assert s.dtype == torch.float32
+    N, K = w.shape
+    if out is None:
+        out = torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        _check(lib().qt_awq_scale_qdq(_p(w), _DT[w.dtype], N, K, _p(s), max(group_size or 0, 0), num_bits,
+                                      int(symmetric), _p(out), _stream()), "qt_awq_scale_qdq")
+    return out
+
+
+def sq_err_sum(a: torch.Tensor, b: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc (device float64 scalar) += sum((a - b)^2), difference rounded to the tensors' dtype."""
+    _dev(a, "a"); _dev(b, "b")
+    assert a.dtype == b.dtype and a.numel() == b.numel() and acc.dtype == torch.float64
+    with torch.cuda.device(a.device):
+        _check(lib().qt_sq_err_sum(_p(a), _p(b), _DT[a.dtype], a.numel(), _p(acc), _stream()), "qt_sq_err_sum")

@@ -91,18 +91,18 @@ __global__ void fill_kernel(float* p, int n, float v) {
 template <int CD>
 __global__ void smooth_scales_kernel(const float* __restrict__ amin, const float* __restrict__ amax,
                                      const float* __restrict__ wmin, const float* __restrict__ wmax, float alpha,
-                                     float* __restrict__ s_out, int K) {
+                                     float one_minus_alpha, float* __restrict__ s_out, int K) {
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= K) return;
     const float act = rnd<CD>(amax[c] - amin[c]);
     const float wabs = fmaxf(fabsf(wmin[c]), fabsf(wmax[c]));
     const float w = rnd<CD>(2.0f * wabs);
-    const float num = rnd<CD>((float)pow((double)act, (double)alpha));
-    const float den = rnd<CD>((float)pow((double)w, (double)(1.0f - alpha)));
+    // torch casts a python-scalar exponent to the tensor dtype: bf16 tensors see pow(x, bf16(alpha))
+    const float num = rnd<CD>((float)pow((double)act, (double)rnd<CD>(alpha)));
+    const float den = rnd<CD>((float)pow((double)w, (double)rnd<CD>(one_minus_alpha)));
     float s = rnd<CD>(num / den);
     s = (w > 0.f) ? s : act;
-    const float floor_ = rnd<CD>(1e-5f);
-    s = fmaxf(s, floor_);
+    s = fmaxf(s, 1e-5f);   // torch.maximum(scales, torch.Tensor([1e-5])): fp32 floor, result promoted to fp32
     s_out[c] = s;
 }
 
@@ -179,14 +179,14 @@ int qt_channel_abs_sum(const void* X, int dtype, int64_t T, int K, float* sum, v
 }
 
 int qt_smooth_scales(const float* amin, const float* amax, const float* wmin, const float* wmax, float alpha,
-                     int compute_dtype, float* s_out, int K, void* stream) {
+                     float one_minus_alpha, int compute_dtype, float* s_out, int K, void* stream) {
     if (!amin || !amax || !wmin || !wmax || !s_out || K <= 0) return QT_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const int g = (K + 255) / 256;
     switch (compute_dtype) {
-        case QT_F32: smooth_scales_kernel<QT_F32><<<g, 256, 0, st>>>(amin, amax, wmin, wmax, alpha, s_out, K); break;
-        case QT_F16: smooth_scales_kernel<QT_F16><<<g, 256, 0, st>>>(amin, amax, wmin, wmax, alpha, s_out, K); break;
-        case QT_BF16: smooth_scales_kernel<QT_BF16><<<g, 256, 0, st>>>(amin, amax, wmin, wmax, alpha, s_out, K); break;
+        case QT_F32: smooth_scales_kernel<QT_F32><<<g, 256, 0, st>>>(amin, amax, wmin, wmax, alpha, one_minus_alpha, s_out, K); break;
+        case QT_F16: smooth_scales_kernel<QT_F16><<<g, 256, 0, st>>>(amin, amax, wmin, wmax, alpha, one_minus_alpha, s_out, K); break;
+        case QT_BF16: smooth_scales_kernel<QT_BF16><<<g, 256, 0, st>>>(amin, amax, wmin, wmax, alpha, one_minus_alpha, s_out, K); break;
         default: return QT_ERR_INVALID;
     }
     return check_launch("smooth_scales");

@@ -1,0 +1,146 @@
+"""AWQ for one decoder layer: activation means, w_mean, n_grid scale search, smoothing, RTN qparams.
+
+Mirrors UPSTREAM llmcompressor AWQModifier, built by the reference at
+ref/src/quantool/methods/llm_compressor/awq/awq.py:81.  The per-candidate weight
+(scale -> quantize -> dequantize -> unscale) is ONE fused kernel pass (qt_awq_scale_qdq); the
+parent-module forwards are plain torch (cuBLAS / SDPA) and the reconstruction loss is reduced on
+the device (qt_sq_err_sum) - 20 losses come back to the host once per mapping.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import cabi
+from . import llama
+from .schemes import WeightArgs
+
+N_GRID = 20
+
+
+@dataclass
+class Mapping:
+    smooth: str              # weight key of the smooth layer
+    balance: List[str]       # Linear names
+    inp: str                 # captured input feeding the balance layers
+    parent: str              # "self_attn" | "mlp" | "linear"
+
+
+def llama_mappings(shape: llama.LlamaShape) -> List[Mapping]:
+    """Default Llama mappings: v_proj -> o_proj is skipped when the shapes differ (GQA)."""
+    m = [Mapping("input_layernorm", ["self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj"], "attn_in",
+                 "self_attn")]
+    if shape.kv_dim == shape.q_dim and shape.q_dim == shape.hidden_size:
+        m.append(Mapping("self_attn.v_proj", ["self_attn.o_proj"], "o_in", "linear"))
+    m.append(Mapping("post_attention_layernorm", ["mlp.gate_proj", "mlp.up_proj"], "mlp_in", "mlp"))
+    m.append(Mapping("mlp.up_proj", ["mlp.down_proj"], "down_in", "linear"))
+    return m
+
+
+def candidate_scales(x_mean: torch.Tensor, w_mean: torch.Tensor, ratio: float, duo_scaling: bool = True):
+    """[K]-vector bookkeeping of the grid search (negligible work; torch ops on the device)."""
+    if duo_scaling:
+        scales = (x_mean.pow(ratio) / (w_mean.pow(1 - ratio) + 1e-4)).clamp(min=1e-4)
+    else:
+        scales = x_mean.pow(ratio).clamp(min=1e-4).view(-1)
+    scales = scales / (scales.max() * scales.min()).sqrt()
+    scales[torch.isinf(scales)] = 1
+    scales[torch.isnan(scales)] = 1
+    return scales.to(torch.float32).contiguous()
+
+
+def _parent_forward(shape, kind: str, w: Dict[str, torch.Tensor], lin: Optional[str], x: torch.Tensor, cos, sin):
+    if kind == "self_attn":
+        return llama.attention_forward(shape, w, x, cos, sin)
+    if kind == "mlp":
+        return llama.mlp_forward(w, x)
+    return F.linear(x, w[f"{lin}.weight"])
+
+
+def search_mapping(shape, w: Dict[str, torch.Tensor], mp: Mapping, x_all: torch.Tensor, x_mean: torch.Tensor,
+                   args: WeightArgs, cos, sin, seq: int, chunk_samples: int, dist=None, n_grid: int = N_GRID,
+                   duo_scaling: bool = True):
+    """x_all: [n_local*seq, K] cached inputs of the parent.  Returns (best_scales, best_ratio, losses)."""
+    dev = x_all.device
+    gs = args.group_size if args.strategy == "group" else 0
+    bw = [w[f"{b}.weight"] for b in mp.balance]
+    w_mean = cabi.awq_wmean(bw, gs)
+    lin = mp.balance[0] if mp.parent == "linear" else None
+    n_local = x_all.shape[0] // seq
+    chunks = [(c0, min(c0 + chunk_samples, n_local)) for c0 in range(0, n_local, chunk_samples)]
+    xin = x_all.view(n_local, seq, -1)
+    ref_out = [_parent_forward(shape, mp.parent, w, lin, xin[a:b], cos, sin) for a, b in chunks]
+    numel = sum(o.numel() for o in ref_out)
+    losses_dev = torch.zeros((n_grid,), dtype=torch.float64, device=dev)
+    patched = dict(w)
+    bufs = [torch.empty_like(t) for t in bw]
+    cand = []
+    for gi in range(n_grid):
+        ratio = gi / n_grid
+        s = candidate_scales(x_mean, w_mean, ratio, duo_scaling)
+        cand.append(s)
+        for name, t, buf in zip(mp.balance, bw, bufs):
+            cabi.awq_scale_qdq(t, s, gs, args.num_bits, args.symmetric, out=buf)
+            patched[f"{name}.weight"] = buf
+        for (a, b), ro in zip(chunks, ref_out):
+            out = _parent_forward(shape, mp.parent, patched, lin, xin[a:b], cos, sin)
+            cabi.sq_err_sum(ro, out, losses_dev[gi:gi + 1])
+    tot = torch.tensor([float(numel)], dtype=torch.float64, device=dev)
+    if dist is not None and dist.on:
+        dist.all_reduce_sum(losses_dev)
+        dist.all_reduce_sum(tot)
+    losses = (losses_dev / tot).cpu().tolist()
+    best, best_err = -1, float("inf")
+    for gi, l in enumerate(losses):
+        if l < best_err:          # strict <: first minimum wins
+            best_err, best = l, gi
+    if best < 0:
+        raise RuntimeError("AWQ scale search produced no finite loss")
+    return cand[best], best / n_grid, losses
+
+
+def apply_mapping(w: Dict[str, torch.Tensor], mp: Mapping, s: torch.Tensor) -> None:
+    for b in mp.balance:
+        cabi.scale_matrix_(w[f"{b}.weight"], s)                       # W *= s[None, :]
+    sw = w[f"{mp.smooth}.weight"]
+    if sw.dim() == 1:
+        cabi.scale_matrix_(sw, s, divide=True)                        # norm weight /= s
+    else:
+        tail = sw[sw.shape[0] - s.numel():]
+        cabi.scale_matrix_(tail, s, divide=True, by_row=True)         # weight[-len(s):] /= s[:, None]
+
+
+def awq_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor, cos, sin, args: WeightArgs,
+              chunk_samples: int = 8, dist=None, n_grid: int = N_GRID, duo_scaling: bool = True):
+    """Calibrate + smooth one decoder layer in place.  Returns {smooth-name: (scales, ratio, losses)}."""
+    dev = h.device
+    n_local, seq, _ = h.shape
+    dims = shape.input_dims()
+    T = n_local * seq
+    cache = {n: torch.empty((T, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
+    for c0 in range(0, n_local, chunk_samples):
+        hb = h[c0: c0 + chunk_samples]
+        llama.layer_forward(shape, w, hb, cos, sin, capture=cache, row0=c0 * seq)
+    out = {}
+    for mp in llama_mappings(shape):
+        x_all = cache[mp.inp]
+        acc = torch.zeros((x_all.shape[1],), dtype=torch.float32, device=dev)
+        cabi.channel_abs_sum(x_all, acc)
+        cnt = torch.tensor([float(T)], dtype=torch.float32, device=dev)
+        if dist is not None and dist.on:
+            dist.all_reduce_sum(acc)
+            dist.all_reduce_sum(cnt)
+        x_mean = acc / cnt
+        s, ratio, losses = search_mapping(shape, w, mp, x_all, x_mean, args, cos, sin, seq, chunk_samples, dist,
+                                          n_grid, duo_scaling)
+        apply_mapping(w, mp, s)
+        out[mp.smooth] = (s, ratio, losses)
+    return out
+
+
+def rtn_qparams(weight: torch.Tensor, args: WeightArgs):
+    """Final weight qparams: minmax observer evaluated in the weight's dtype."""
+    gs = args.group_size if args.strategy == "group" else 0
+    scale, zp = cabi.minmax_qparams(weight.contiguous(), gs, args.num_bits, args.symmetric)
+    return scale.to(weight.dtype), zp.to(torch.int8)

@@ -250,6 +250,16 @@ def _to_dev(t: torch.Tensor, device) -> torch.Tensor:
     return t.to(device, non_blocking=True)
 
 
+def _layer_weights(host_sd, pre: str, dev, res) -> Dict[str, torch.Tensor]:
+    """Fresh device copies of one decoder layer's tensors (the layer is modified in place)."""
+    w = {}
+    for k, v in host_sd.items():
+        if k.startswith(pre):
+            w[k[len(pre):]] = v.clone() if v.device == dev else _to_dev(v, dev)
+            res.h2d_bytes += v.numel() * v.element_size()
+    return w
+
+
 def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor], token_ids: torch.Tensor,
                         args: WeightArgs, device, fmt: str = "pack-quantized", percdamp: float = 0.01,
                         chunk_samples: int = 8, smooth_strength: Optional[float] = None,
@@ -278,11 +288,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
     dims = shape.input_dims()
     for l in range(shape.num_hidden_layers):
         pre = f"model.layers.{l}."
-        w = {}
-        for k, v in host_sd.items():
-            if k.startswith(pre):
-                w[k[len(pre):]] = _to_dev(v, dev)
-                res.h2d_bytes += v.numel() * v.element_size()
+        w = _layer_weights(host_sd, pre, dev, res)
         if smooth_strength is not None:
             from .smoothquant import smooth_layer
             smooth_layer(shape, w, h, cos, sin, smooth_strength, chunk_samples, dist)
@@ -328,4 +334,59 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
             if k in host_sd:
                 res.tensors[k] = host_sd[k]
     res.launches = lq.launches
+    return res
+
+
+def quantize_model_awq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor], token_ids: torch.Tensor,
+                       args: WeightArgs, device, fmt: str = "pack-quantized", chunk_samples: int = 8,
+                       n_grid: int = 20, duo_scaling: bool = True, dist: Optional[Dist] = None,
+                       progress=None) -> ModelQuantResult:
+    """AWQ over the whole model: per layer calibrate -> 20-point scale search per mapping -> smooth ->
+    propagate through the smoothed (unquantized) layer; weights get round-to-nearest qparams and the
+    artifact codes at the end of each layer."""
+    from . import awq
+    from .gptq import compress_linear
+    dist = dist or Dist()
+    res = ModelQuantResult()
+    dev = torch.device(device)
+    n_total, seq = token_ids.shape
+    per = row_split(n_total, dist.world)
+    s0 = sum(per[: dist.rank])
+    ids = token_ids[s0: s0 + per[dist.rank]].to(dev)
+    res.h2d_bytes += ids.numel() * ids.element_size()
+    n_local = ids.shape[0]
+    emb = _to_dev(host_sd["model.embed_tokens.weight"], dev)
+    res.h2d_bytes += emb.numel() * emb.element_size()
+    h = torch.nn.functional.embedding(ids, emb)
+    del emb
+    cos, sin = llama.rope_tables(shape, seq, dev, h.dtype)
+    l0 = cabi.launch_count()
+    for l in range(shape.num_hidden_layers):
+        pre = f"model.layers.{l}."
+        w = _layer_weights(host_sd, pre, dev, res)
+        info = awq.awq_layer(shape, w, h, cos, sin, args, chunk_samples, dist, n_grid, duo_scaling)
+        for lin in llama.LINEARS:
+            wt = w[f"{lin}.weight"]
+            scale, zp = awq.rtn_qparams(wt, args)
+            art, _ = compress_linear(wt, scale, zp, None, args, fmt=fmt)
+            if dist.rank == 0:
+                for k, t in art.items():
+                    th = t.cpu() if t.is_cuda else t
+                    res.tensors[f"{pre}{lin}.{k}"] = th
+                    res.d2h_bytes += th.numel() * th.element_size()
+        if dist.rank == 0:
+            for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
+                res.tensors[pre + k] = w[k].cpu()
+            for name, (_s, ratio, losses) in info.items():
+                res.losses[f"{pre}{name}.awq_ratio"] = ratio
+        for c0 in range(0, n_local, chunk_samples):
+            h[c0: c0 + chunk_samples] = llama.layer_forward(shape, w, h[c0: c0 + chunk_samples], cos, sin)
+        del w
+        if progress:
+            progress(l)
+    if dist.rank == 0:
+        for k in ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight"):
+            if k in host_sd:
+                res.tensors[k] = host_sd[k]
+    res.launches = cabi.launch_count() - l0
     return res
