@@ -59,6 +59,80 @@ int qt_gguf_quantize(int ggml_type, const void* src, int src_dtype, int round_vi
                      int64_t ncols, void* dst, void* stream);
 int qt_gguf_dequantize(int ggml_type, const void* src, int64_t nrows, int64_t ncols, float* dst, void* stream);
 
+unsigned long long qt_launch_count(void);   /* kernel launches issued through this library since load */
+
+/* ---- compressed-tensors primitives -----------------------------------------------------------
+ * What the reference's artifacts are made of when llm-compressor plugins save with
+ * save_compressed=True (ref/src/quantool/methods/llm_compressor/base.py:188,230):
+ *   CT/quantization/utils/helpers.py:50-137      calculate_qparams (MinMax observer)
+ *   CT/quantization/lifecycle/forward.py:36-73   quantize -> int8 codes / dequantize
+ *   CT/compressors/pack_quantized/helpers.py:20-161  pack_to_int32 / unpack_from_int32
+ * Arithmetic is evaluated in `dtype` (bf16/fp16 tensors round after every op, as torch does). */
+/* W [N,K] of `dtype`; group_size 0 = one scale per row; scale, zp: fp32 [N, K/group_size] (zp integer-valued) */
+int qt_minmax_qparams(const void* W, int dtype, int N, int K, int group_size, int num_bits, int symmetric,
+                      float* scale, float* zp, void* stream);
+/* scale [N,G] of `dtype`; zp fp32 [N,G] or NULL; g_idx int32 [K] or NULL (column -> group);
+ * codes int8 [N,K] and/or dq_out [N,K] of `dtype` (either may be NULL, not both) */
+int qt_quantize_codes(const void* W, const void* scale, const float* zp, const int* g_idx, int dtype, int N, int K,
+                      int G, int group_size, int num_bits, int8_t* codes, void* dq_out, void* stream);
+int qt_pack_int32(const int8_t* codes, int N, int K, int num_bits, int32_t* packed, void* stream);
+int qt_unpack_int32(const int32_t* packed, int N, int K, int num_bits, int8_t* codes, void* stream);
+
+/* ---- GPTQ ---------------------------------------------------------------------------------------
+ * Replaces UPSTREAM llmcompressor modifiers/quantization/gptq/gptq_quantize.py (accumulate_hessian,
+ * quantize_weight), which the reference reaches by building GPTQModifier at
+ * ref/src/quantool/methods/llm_compressor/gptq/gptq.py:86 and running llmcompressor.oneshot at
+ * ref/src/quantool/methods/llm_compressor/base.py:159-161. */
+/* H fp32 [K,K] (raw sums, caller zeroes it first) += X^T X on upper-triangle tiles; X bf16 [T,K]; tcgen05 */
+int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* stream);
+/* H <- factor * H (factor = 2 / n_samples) on the upper triangle, mirrored to the lower */
+int qt_hessian_finalize(float* H, int K, float factor, void* stream);
+int qt_hessian_set_splits(int splits);   /* tuning: force the token split count (0 = heuristic) */
+/* fp32 SIMT cross-check of qt_hessian_accumulate (tests / smoke only) */
+int qt_hessian_accumulate_reference(const void* X, int64_t T, int K, float* H, void* stream);
+/* dead[i] = (H[i][i]==0); damp = percdamp*mean(diag); Hf = J P^T (H' + damp I) P J (lower triangle),
+ * perm int32 [K] or NULL, dead uint8 [K], damp_scratch fp32 [1] */
+int qt_gptq_prepare_hessian(const float* H, const int* perm, int K, float percdamp, float* Hf, uint8_t* dead,
+                            float* damp_scratch, void* stream);
+/* in place: A = Hf -> U = cholesky(H^-1, upper); X, W: [K,K] fp32 scratch; info: device int32,
+ * 0 = ok else 1-based failing pivot (upstream's LinAlgError path: caller sets U = I) */
+int qt_gptq_hinv_factor(float* A, float* X, float* W, int K, int* info, void* stream);
+int qt_set_identity(float* U, int K, void* stream);
+int qt_sgemm(int b_is_nk, const float* A, const float* B, float* C, int M, int N, int Kd, int lda, int ldb, int ldc,
+             float alpha, float beta, int lower_tiles_only, int a_lower_tri, int b_lower_tri, void* stream);
+/* Wp[n][j] = float(W[n][perm[j]]) with dead columns zeroed; out[n][c] = cast(Wp[n][inv_perm[c]]) */
+int qt_gptq_permute_in(const void* W, int dtype, const int* perm, const uint8_t* dead, float* Wp, int N, int K,
+                       void* stream);
+int qt_gptq_permute_out(const float* Wp, const int* inv_perm, void* out, int dtype, int N, int K, void* stream);
+/* blocked column loop (block 128).  mode 0: re-fit group qparams at group starts (group_size 32/64/128),
+ * 1: static scales looked up through g_idx (actorder=weight), 2: one scale per row.  W in/out. */
+int qt_gptq_quantize_weight(float* W, const float* U, float* err_scratch, float* scale, float* zp, const int* g_idx,
+                            float* losses, int N, int K, int G, int group_size, int num_bits, int symmetric, int mode,
+                            void* stream);
+
+/* ---- SmoothQuant / AWQ --------------------------------------------------------------------------
+ * Replaces UPSTREAM llmcompressor SmoothQuantModifier built at
+ * ref/src/quantool/methods/llm_compressor/smoothquant/smoothquant.py:77-84 and AWQModifier
+ *  built at ref/src/quantool/methods/llm_compressor/awq/awq.py:81. */
+int qt_fill_f32(float* p, int n, float v, void* stream);
+/* running per-channel min/max over rows of X [T,K]; mn/mx fp32 [K] initialised to +/-FLT_MAX */
+int qt_channel_minmax(const void* X, int dtype, int64_t T, int K, float* mn, float* mx, void* stream);
+/* sum[c] += sum_t |X[t][c]| */
+int qt_channel_abs_sum(const void* X, int dtype, int64_t T, int K, float* sum, void* stream);
+/* s = (amax-amin)^alpha / (2 max|w|)^(1-alpha), where(w>0, s, act), max(s, 1e-5); evaluated in compute_dtype */
+int qt_smooth_scales(const float* amin, const float* amax, const float* wmin, const float* wmax, float alpha,
+                     float one_minus_alpha, int compute_dtype, float* s_out, int K, void* stream);
+/* in place W[n][c] *= s[c] (divide: /=), or by_row: s[n] */
+int qt_scale_matrix(void* W, int dtype, int N, int K, const float* s, int divide, int by_row, void* stream);
+/* colsum[c] += sum_n |W[n][c]| / (group amax + 1e-6); gamax_scratch fp32 [N, K/group_size] */
+int qt_awq_wmean_accumulate(const void* W, int dtype, int N, int K, int group_size, float* gamax_scratch,
+                            float* colsum, void* stream);
+/* out = pseudo_quantize(W * s) / s in one pass (AWQ grid-search candidate) */
+int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int group_size, int num_bits,
+                     int symmetric, void* out, void* stream);
+/* *out (device double) += sum (a-b)^2 */
+int qt_sq_err_sum(const void* a, const void* b, int dtype, int64_t n, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,89 @@
+"""compressed-tensors artifact writer: model.safetensors + config.json["quantization_config"].
+
+What `last_model.save_pretrained(dest, save_compressed=True)` produces for the reference
+(ref/src/quantool/methods/llm_compressor/base.py:188; CT/compressors/model_compressors/model_compressor.py:177-213;
+SURVEY.md §8b "Artifact contract", §8f row 1).  The metadata block is generated with the installed
+compressed-tensors pydantic models so that key names / defaults are the real ones; tensors come
+from the CUDA kernels.  Also offers the AutoGPTQ / AutoAWQ `qweight/qzeros/scales/g_idx` view as a
+pure repack of the same codes (north_star naming; layouts per
+VLLM/model_executor/layers/quantization/utils/quant_utils.py:704-813).
+"""
+import json
+import os
+import shutil
+from typing import Dict, Optional
+
+import torch
+
+
+def quantization_config(level: str, actorder: Optional[str], fmt: str, ignore=("lm_head",)) -> dict:
+    from compressed_tensors import __version__ as ct_version
+    from compressed_tensors.quantization import QuantizationConfig, preset_name_to_scheme
+    scheme = preset_name_to_scheme(level, ["Linear"])
+    if actorder is not None and scheme.weights is not None:
+        scheme.weights.actorder = "static" if actorder == "weight" else actorder
+    qc = QuantizationConfig(config_groups={"group_0": scheme}, quant_method="compressed-tensors", format=fmt,
+                            quantization_status="compressed", ignore=list(ignore))
+    d = qc.model_dump(mode="json")
+    d["version"] = ct_version
+    return d
+
+
+def artifact_format(num_bits: int, level: str) -> str:
+    """pack-quantized for 4-bit weight-only schemes, int-quantized for int8 weights (rows a6/a7)."""
+    return "pack-quantized" if num_bits == 4 else "int-quantized"
+
+
+class QuantizedModel:
+    """Holder returned as `plugin.last_model`: host tensors in artifact key names + HF config."""
+
+    def __init__(self, hf_config: dict, tensors: Dict[str, torch.Tensor], qconfig: dict, source_dir: Optional[str] = None):
+        self.hf_config = dict(hf_config)
+        self.tensors = tensors
+        self.qconfig = qconfig
+        self.source_dir = source_dir
+
+    def save_pretrained(self, dest: str, save_compressed: bool = True, **_):
+        from safetensors.torch import save_file
+        os.makedirs(dest, exist_ok=True)
+        cfg = dict(self.hf_config)
+        cfg["quantization_config"] = self.qconfig
+        with open(os.path.join(dest, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.contiguous() for k, v in self.tensors.items()}, os.path.join(dest, "model.safetensors"),
+                  metadata={"format": "pt"})
+        if self.source_dir and os.path.isdir(self.source_dir):
+            for fn in os.listdir(self.source_dir):
+                if fn.startswith("tokenizer") or fn in ("special_tokens_map.json", "generation_config.json", "vocab.json",
+                                                        "merges.txt"):
+                    shutil.copy(os.path.join(self.source_dir, fn), dest)
+
+
+def autogptq_view(weight_packed: torch.Tensor, weight_scale: torch.Tensor, weight_zero_point: Optional[torch.Tensor],
+                  g_idx: Optional[torch.Tensor], num_bits: int, K: int, group_size: int) -> Dict[str, torch.Tensor]:
+    """AutoGPTQ layout: qweight [K/pf, N] packed along K, scales [G, N], qzeros [G, N/pf], g_idx [K].
+    Pure index shuffling of the compressed-tensors codes (device or host tensors)."""
+    from .. import cabi
+    N = weight_packed.shape[0]
+    pf = 32 // num_bits
+    dev = weight_packed.device
+    if dev.type == "cuda":
+        codes = cabi.unpack_int32(weight_packed.contiguous(), num_bits, K)
+    else:
+        shifts = torch.arange(pf, dtype=torch.int32) * num_bits
+        u = (weight_packed.unsqueeze(-1) >> shifts) & ((1 << num_bits) - 1)
+        codes = (u.reshape(N, -1)[:, :K] - (1 << (num_bits - 1))).to(torch.int8)
+    u = (codes.to(torch.int32) + (1 << (num_bits - 1))).t().contiguous()          # [K, N] unsigned
+    shifts = (torch.arange(pf, dtype=torch.int32, device=u.device) * num_bits).view(1, pf, 1)
+    qweight = (u.view(K // pf, pf, N) << shifts).sum(dim=1, dtype=torch.int32)
+    G = weight_scale.shape[1]
+    scales = weight_scale.t().contiguous()
+    if weight_zero_point is None:
+        zeros = torch.full((G, N), 1 << (num_bits - 1), dtype=torch.int32, device=u.device)
+    else:
+        zeros = (weight_zero_point.to(torch.int32) + (1 << (num_bits - 1))).t().contiguous()
+    shifts2 = (torch.arange(pf, dtype=torch.int32, device=u.device) * num_bits).view(1, 1, pf)
+    qzeros = (zeros.view(G, N // pf, pf) << shifts2).sum(dim=2, dtype=torch.int32)
+    if g_idx is None:
+        g_idx = (torch.arange(K, dtype=torch.int32, device=u.device) // (group_size or K))
+    return {"qweight": qweight, "qzeros": qzeros, "scales": scales, "g_idx": g_idx.to(torch.int32)}

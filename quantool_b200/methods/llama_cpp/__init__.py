@@ -1,0 +1,1 @@
+from . import llama_cpp  # noqa: F401  (registration side effect)

@@ -1,0 +1,1 @@
+from . import awq, gptq, smoothquant  # noqa: F401  (registration side effect)

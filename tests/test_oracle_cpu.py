@@ -1,0 +1,185 @@
+"""Pins the oracle (CPU restatement) to every external vector available for this path:
+the sha256 KATs of SURVEY.md §8c, gguf-py, compressed-tensors, the committed golden fixtures, an
+independent numpy restatement, and the host emulation of the CUDA K-quant kernels."""
+import ctypes
+import hashlib
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+KAT = {"Q8_0": ("d8b3256c9fd9ae4c", (8, 544)), "Q4_0": ("d153bbca62836335", (8, 288)),
+       "Q5_0": ("c9154c30f4008bbe", (8, 352)), "Q4_1": ("f1844724bdbc3ca3", (8, 320)),
+       "Q5_1": ("2cce57372f71162a", (8, 384))}
+
+
+def _edge(rng, nrows, ncols):
+    x = rng.standard_normal((nrows, ncols)).astype(np.float32)
+    x[0, :256] = 0.0
+    x[1, :32] = 1.5
+    x[2, :] *= 1e-3
+    x[3, 5] = 40.0
+    x[4, :256] = np.abs(x[4, :256])
+    x[5, :256] = 1e-20
+    x[6, 0] = -x[6, 1]
+    return x
+
+
+@pytest.mark.parametrize("qtype", sorted(KAT))
+def test_survey_kat_sha256(qtype):
+    from oracle import ggml_quants as oq
+    x = np.random.default_rng(0).standard_normal((8, 512)).astype(np.float32)
+    y = oq.quantize(x, qtype)
+    assert y.shape == KAT[qtype][1]
+    assert hashlib.sha256(y.tobytes()).hexdigest()[:16] == KAT[qtype][0]
+
+
+@pytest.mark.parametrize("qtype", sorted(KAT))
+def test_simple_types_equal_gguf_py(qtype):
+    from gguf import GGMLQuantizationType as T
+    from gguf import quants as gq
+    from oracle import ggml_quants as oq
+    x = _edge(np.random.default_rng(3), 9, 768)
+    assert np.array_equal(oq.quantize(x, qtype), gq.quantize(x, getattr(T, qtype)))
+
+
+def test_golden_fixtures():
+    from oracle import ggml_quants as oq
+    s = np.load(os.path.join(GOLD, "gguf_simple_types.npz"))
+    for q in ("Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1"):
+        assert np.array_equal(oq.quantize(s["x"], q), s[f"packed_{q}"]), q
+    k = np.load(os.path.join(GOLD, "gguf_k_quants.npz"))
+    for q in ("Q4_K", "Q5_K", "Q6_K"):
+        packed = oq.quantize(k["x"], q)
+        assert np.array_equal(packed, k[f"packed_{q}"]), q
+        assert np.array_equal(oq.dequantize(packed, q, 512).view(np.uint32), k[f"dequant_{q}"].view(np.uint32)), q
+
+
+@pytest.mark.parametrize("qtype", ["Q4_K", "Q5_K", "Q6_K"])
+def test_k_quants_two_independent_restatements_agree(qtype):
+    from gguf import GGMLQuantizationType as T
+    from gguf import quants as gq
+    from oracle import ggml_quants as oq, ggml_quants_np as onp
+    x = _edge(np.random.default_rng(5), 12, 1024)
+    a = oq.quantize(x, qtype)
+    assert np.array_equal(a, onp.QUANTIZE[qtype](x))
+    d = gq.dequantize(a, getattr(T, qtype)).astype(np.float32)
+    assert np.array_equal(d.view(np.uint32), oq.dequantize(a, qtype, 1024).view(np.uint32))
+    rmse = float(np.sqrt(np.mean((d[7:] - x[7:]) ** 2)))
+    assert rmse < {"Q4_K": 0.09, "Q5_K": 0.045, "Q6_K": 0.025}[qtype]
+
+
+@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q4_K", "Q5_K", "Q6_K"])
+def test_dequant_equals_gguf_py(qtype):
+    from gguf import GGMLQuantizationType as T
+    from gguf import quants as gq
+    from oracle import ggml_quants as oq
+    x = _edge(np.random.default_rng(8), 8, 512)
+    p = oq.quantize(x, qtype)
+    assert np.array_equal(oq.dequantize(p, qtype, 512).view(np.uint32),
+                          gq.dequantize(p, getattr(T, qtype)).astype(np.float32).view(np.uint32))
+
+
+def test_threads_do_not_change_bytes():
+    from oracle import ggml_quants as oq
+    x = np.random.default_rng(1).standard_normal((64, 512)).astype(np.float32)
+    oq.set_threads(1)
+    a = oq.quantize(x, "Q4_K")
+    oq.set_threads(0)
+    assert np.array_equal(a, oq.quantize(x, "Q4_K"))
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
+@pytest.mark.parametrize("qtype", ["Q4_K", "Q5_K", "Q6_K"])
+def test_cuda_kquant_device_math_on_host_equals_oracle(qtype):
+    """The __host__ __device__ phase functions the CUDA kernels run, executed on the CPU."""
+    from oracle import ggml_quants as oq
+    so = os.path.join(ROOT, "tests", "_build", "libhost_emul.so")
+    src = os.path.join(ROOT, "tests", "host_emul.cu")
+    hdr = os.path.join(ROOT, "quantool_b200", "csrc", "gguf_kquant.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Xcompiler",
+                               "-ffp-contract=off", "-Wno-deprecated-gpu-targets", "-I",
+                               os.path.join(ROOT, "quantool_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                               "-o", so, src])
+    L = ctypes.CDLL(so)
+    x = _edge(np.random.default_rng(2), 40, 1024)
+    ref = oq.quantize(x, qtype)
+    out = np.zeros_like(ref)
+    getattr(L, "emul_" + qtype.lower().replace("_k", "_K"))(ctypes.c_void_p(x.ctypes.data),
+                                                          ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(x.size // 256))
+    assert np.array_equal(out, ref)
+
+
+# ---- compressed-tensors / GPTQ oracle -----------------------------------------------------------
+def test_ct_kats_from_survey():
+    from compressed_tensors.compressors.pack_quantized.helpers import pack_to_int32
+    from compressed_tensors.quantization.utils import calculate_qparams
+    from oracle import gptq as og
+    v = torch.tensor([[-8, -7, 0, 7, 1, 2, 3, 4, 5, 6, 7, -1, -2, -3, -4, -5]], dtype=torch.int8)
+    assert pack_to_int32(v, 4).numpy().astype(np.uint32).tolist() == [[0xCBA9F810, 0x34567FED]]
+    mn, mx = torch.tensor([-1.0]), torch.tensor([0.5])
+    s, z = calculate_qparams(mn, mx, og.scheme_weight_args("W4A16"))
+    assert abs(s.item() - 1 / 7.5) < 1e-7 and z.item() == 0
+    s, z = calculate_qparams(mn, mx, og.scheme_weight_args("W4A16_ASYM"))
+    assert abs(s.item() - 0.1) < 1e-7 and z.item() == 2
+    s, z = calculate_qparams(mn, mx, og.scheme_weight_args("W8A16"))
+    assert abs(s.item() - 1 / 127.5) < 1e-8
+    assert torch.round(torch.tensor([0.5, 1.5, 2.5])).tolist() == [0.0, 2.0, 2.0]
+
+
+def test_ct_golden_fixture():
+    from oracle import gptq as og
+    g = np.load(os.path.join(GOLD, "ct_quantize.npz"))
+    W = torch.from_numpy(g["W_bf16_bits"]).view(torch.bfloat16)
+    for level in ("W4A16", "W4A16_ASYM", "W8A16"):
+        a = og.scheme_weight_args(level)
+        s, z = og.minmax_qparams(W, a)
+        assert np.array_equal(s.view(torch.int16).numpy(), g[f"{level}_scale_bits"])
+        assert np.array_equal(z.to(torch.int8).numpy(), g[f"{level}_zp"])
+        if a.num_bits == 4:
+            codes, packed, _ = og.compress_packed(W, s, z if not a.symmetric else None, None, a)
+            assert np.array_equal(packed.numpy(), g[f"{level}_packed"])
+        else:
+            codes = og.compress_int8(W, s, None, a)
+        assert np.array_equal(codes.numpy(), g[f"{level}_codes"])
+
+
+@pytest.mark.parametrize("level,actorder", [("W4A16", None), ("W4A16", "group"), ("W4A16", "weight"), ("W8A8", None)])
+def test_gptq_oracle_self_consistency(level, actorder):
+    """Unpinned driver: H equals the fp64 value, the inverse factor satisfies U^T U = (H+damp)^-1, and
+    GPTQ beats round-to-nearest on its own objective."""
+    from compressed_tensors.quantization import ActivationOrdering
+    from oracle import gptq as og
+    g = torch.Generator().manual_seed(0)
+    N, K, n, seq = 48, 256, 6, 300
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    X = torch.randn((n, seq, K), generator=g).to(torch.bfloat16)
+    X[..., 7] *= 10
+    H, cnt = og.make_empty_hessian(K), 0
+    for b in range(n):
+        H, cnt = og.accumulate_hessian(X[b:b + 1], H, cnt)
+    Xf = X.reshape(-1, K).double()
+    ref = (2.0 / n) * Xf.t() @ Xf
+    assert (torch.linalg.norm(H.double() - ref) / torch.linalg.norm(ref)).item() < 1e-5
+    a = og.scheme_weight_args(level)
+    if actorder:
+        a.actorder = ActivationOrdering.GROUP if actorder == "group" else ActivationOrdering.WEIGHT
+    loss, Wq, s, z, gi, Hinv, perm = og.quantize_weight(W, H, a, return_hinv=True)
+    Hd = H.double().clone()
+    if perm is not None:
+        Hd = Hd[perm][:, perm]
+    Hd += 0.01 * torch.mean(torch.diag(Hd)) * torch.eye(K, dtype=torch.float64)
+    err = torch.linalg.norm(Hinv.double().t() @ Hinv.double() @ Hd - torch.eye(K, dtype=torch.float64))
+    assert err.item() < 1e-2
+    Wr, _, _ = og.rtn_quantize(W, og.scheme_weight_args(level))
+    assert og.layer_error(W, Wq, X.reshape(-1, K).float()) < og.layer_error(W, Wr, X.reshape(-1, K).float())
+    assert (gi is not None) == (actorder == "group")
+    assert loss > 0

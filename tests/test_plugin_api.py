@@ -1,0 +1,159 @@
+"""Plugin / registry API: same names, attributes, argument routing and error behaviour as the
+reference (ref/src/quantool/core/{base,registry}.py, methods/*).  The GGUF flow
+test mirrors ref/tests/quantool/methods/test_llama_cpp.py."""
+from pathlib import Path
+from unittest.mock import patch
+
+import pytest
+import torch
+
+import quantool_b200.methods  # noqa: F401  (registers the plugins)
+from quantool_b200 import BaseQuantizer, QuantizerRegistry, TemplateQuantizationCard
+from quantool_b200.core.registry import Registry
+from quantool_b200.methods.llama_cpp.llama_cpp import GGUF, QuantType
+from quantool_b200.methods.llm_compressor.base import Modifier
+
+
+def test_four_methods_registered_with_reference_attributes():
+    assert set(QuantizerRegistry.list()) == {"gguf", "gptq", "awq", "smoothquant"}
+    gptq = QuantizerRegistry.create("gptq", model_id="org/model")
+    assert gptq.supported_levels == ["W4A16", "W8A8", "INT8", "W8A16", "W4A16_ASYM", "W4A8"]
+    assert QuantizerRegistry.create("awq", model_id="m").supported_levels == ["W4A16", "W4A16_ASYM", "W8A16"]
+    assert QuantizerRegistry.create("smoothquant", model_id="m").supported_levels == ["W8A8", "INT8", "W4A8"]
+    assert gptq.supports_multiple_levels is False and gptq.require_calibration() is True
+    with patch.object(GGUF, "_check_dependencies"):
+        g = QuantizerRegistry.create("gguf", model_id="m")
+    assert g.supports_multiple_levels is True and g.require_calibration() is False
+    assert [q.value for q in QuantType][-3:] == ["Q8_0", "f16", "f32"] and len(list(QuantType)) == 16
+    assert isinstance(gptq.template_card, TemplateQuantizationCard)
+
+
+def test_registry_errors():
+    r = Registry()
+
+    class NoName(BaseQuantizer):
+        def quantize(self, model, level, **kw):
+            return ""
+    with pytest.raises(ValueError):
+        r.register(NoName)
+
+    class A(BaseQuantizer):
+        name = "a"
+
+        def quantize(self, model, level, **kw):
+            super().quantize(model, level, **kw)
+            return "ok"
+    r.register(A)
+    with pytest.raises(KeyError):
+        r.register(A)
+    with pytest.raises(KeyError):
+        r.create("missing")
+    a = r.create("a", model_id="x")
+    assert a.model_id == "x" and r.list() == ["a"]
+    with pytest.raises(ValueError):
+        a.quantize("m", ["L1", "L2"])          # list level on a single-level method
+
+
+def test_kwargs_routing_like_the_reference(tmp_path):
+    q = QuantizerRegistry.create("gptq", model_id="org/model")
+    seen = {}
+
+    def fake_oneshot(**kw):
+        seen.update(kw)
+        return object()
+    ids = torch.zeros((2, 8), dtype=torch.long)
+    with patch.object(q, "_oneshot", side_effect=fake_oneshot):
+        out = q.quantize(model="some/path", level="W4A16", dataset=ids, num_calibration_samples=2, max_seq_length=8,
+                         output_dir=str(tmp_path / "o"), method_kwargs__dampening_frac=0.05,
+                         method_kwargs={"actorder": "group"}, targets="ignored-top-level", llama_cpp_path="ignored")
+    assert out == str((tmp_path / "o").resolve()) and q.last_output_dir == (tmp_path / "o").resolve()
+    assert seen["num_calibration_samples"] == 2 and seen["max_seq_length"] == 8 and seen["model"] == "some/path"
+    assert seen["save_compressed"] is True and seen["trust_remote_code_model"] is True
+    rec = seen["recipe"]
+    assert isinstance(rec, Modifier) and rec.kind == "gptq" and rec.scheme == "W4A16"
+    assert rec.dampening_frac == 0.05 and rec.actorder == "group"
+    assert rec.targets == "Linear" and rec.ignore == ["lm_head"]          # top-level `targets` is dropped
+
+
+def test_default_output_dir_and_errors(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    q = QuantizerRegistry.create("gptq", model_id="org/model")
+    with patch.object(q, "_oneshot", return_value=object()):
+        out = q.quantize(model="p", level="W8A8", dataset=torch.zeros((1, 4), dtype=torch.long))
+    assert out.endswith("output/gptq_org_model_W8A8")
+    with pytest.raises(ValueError, match="calibration data"):
+        q.quantize(model="p", level="W4A16")
+    with pytest.raises(ValueError, match="not a valid compressed-tensors preset scheme"):
+        q.quantize(model="p", level="W3A16", dataset=torch.zeros((1, 4), dtype=torch.long))
+    with pytest.raises(ValueError, match="does not support multiple"):
+        q.quantize(model="p", level=["W4A16", "W8A8"], dataset=torch.zeros((1, 4), dtype=torch.long))
+    with pytest.raises(RuntimeError):
+        q2 = QuantizerRegistry.create("awq", model_id="m")
+        q2.save_pretrained(str(tmp_path / "s"))         # nothing quantized yet
+
+
+def test_smoothquant_recipe_is_smoothing_then_gptq():
+    q = QuantizerRegistry.create("smoothquant", model_id="m")
+    rec, scheme = q._build_recipe(None, {"smoothing_strength": 0.8})
+    assert scheme == "W8A8" and [m.kind for m in rec] == ["smoothquant", "gptq"]
+    assert rec[0].smoothing_strength == 0.8 and rec[1].scheme == "W8A8"
+
+
+def test_gguf_multiple_levels_returns_list(tmp_path):
+    with patch.object(GGUF, "_check_dependencies"):
+        quantizer = QuantizerRegistry.create("gguf", model_id="test/model")
+    output_dir = tmp_path / "gguf"
+    levels = ["Q4_K_M", QuantType.Q3_K_S]
+    convert_calls, quantize_calls = [], []
+
+    def fake_convert(model_path, out_path, outtype):
+        convert_calls.append((model_path, out_path, outtype))
+        assert outtype == "f16"
+        return "base_f16.gguf"
+
+    def fake_quantize(base_file, out_path, quant_level):
+        quantize_calls.append((base_file, out_path, quant_level))
+        return str(Path(out_path) / f"model-{quant_level}.gguf")
+
+    with (patch.object(quantizer, "_ensure_output_directory", return_value=output_dir) as mock_ensure,
+          patch.object(quantizer, "_convert_hf", side_effect=fake_convert) as mock_convert,
+          patch.object(quantizer, "_quantize_gguf", side_effect=fake_quantize) as mock_quantize):
+        artifacts = quantizer.quantize(model="hf-repo/model", level=levels)
+    expected = [str(output_dir / "model-Q4_K_M.gguf"), str(output_dir / "model-Q3_K_S.gguf")]
+    assert artifacts == expected and quantizer.last_gguf == expected
+    assert mock_ensure.called
+    mock_convert.assert_called_once()
+    assert convert_calls == [("hf-repo/model", output_dir, "f16")]
+    assert mock_quantize.call_count == 2
+    assert quantize_calls == [("base_f16.gguf", output_dir, "Q4_K_M"), ("base_f16.gguf", output_dir, "Q3_K_S")]
+
+
+def test_gguf_q8_0_goes_through_the_f16_base_and_bad_level_defaults(tmp_path):
+    with patch.object(GGUF, "_check_dependencies"):
+        q = QuantizerRegistry.create("gguf", model_id="org/My-Model")
+    calls = []
+    with (patch.object(q, "_convert_hf", side_effect=lambda m, o, t: calls.append(("c", t)) or "b.gguf"),
+          patch.object(q, "_quantize_gguf", side_effect=lambda b, o, l: calls.append(("q", l)) or f"x-{l}.gguf")):
+        q.quantize(model="p", level="Q8_0", output_dir=str(tmp_path))
+        q.quantize(model="p", level="nonsense", output_dir=str(tmp_path))
+        q.quantize(model="p", level="f16", output_dir=str(tmp_path))
+    assert calls == [("c", "f16"), ("q", "Q8_0"), ("c", "f16"), ("q", "Q4_K_M"), ("c", "f16")]
+
+
+def test_gguf_tensor_type_table_smollm_and_llama():
+    """SmolLM2-135M (h=576) under Q4_K_M."""
+    from quantool_b200.engine.gguf_file import tensor_type, use_more_bits
+    more = [i for i in range(30) if use_more_bits(i, 30)]
+    assert more == [0, 1, 2, 5, 8, 11, 14, 17, 20, 23, 26, 27, 28, 29]
+    t = lambda n, s, f="Q4_K_M", L=30, out=False: tensor_type(n, s, f, L, out)
+    assert t("blk.3.attn_q.weight", (576, 576)) == "Q5_0"            # Q4_K falls back (576 % 256 != 0)
+    assert t("blk.0.attn_v.weight", (192, 576)) == "Q8_0"            # Q6_K falls back
+    assert t("blk.3.attn_v.weight", (192, 576)) == "Q5_0"
+    assert t("blk.0.ffn_down.weight", (576, 1536)) == "Q6_K"
+    assert t("blk.3.ffn_down.weight", (576, 1536)) == "Q4_K"
+    assert t("token_embd.weight", (49152, 576)) == "Q8_0"            # tied: acts as output, Q6_K -> Q8_0
+    assert t("blk.0.attn_norm.weight", (576,)) == "F32"
+    assert t("output.weight", (128256, 4096), L=32, out=True) == "Q6_K"
+    assert t("token_embd.weight", (128256, 4096), L=32, out=True) == "Q4_K"
+    assert t("blk.1.ffn_gate.weight", (14336, 4096), "Q8_0", 32, True) == "Q8_0"
+    assert t("output.weight", (128256, 4096), "Q8_0", 32, True) == "Q8_0"

@@ -1,0 +1,131 @@
+"""GPU end-to-end through the plugin API: model directory in, artifact out."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_model(tmp_path, layers=2, hidden=256, inter=512, heads=4, kv=2, vocab=512, tied=True):
+    from safetensors.torch import save_file
+    from quantool_b200.engine import llama
+    shape = llama.LlamaShape(hidden, inter, layers, heads, kv, vocab, rope_theta=10000.0, tie_word_embeddings=tied)
+    sd = llama.random_state_dict(shape, seed=3)
+    d = tmp_path / "tiny-llama"
+    d.mkdir()
+    save_file(sd, str(d / "model.safetensors"), metadata={"format": "pt"})
+    json.dump(shape.to_hf_config(), open(d / "config.json", "w"))
+    return shape, sd, str(d)
+
+
+@pytest.mark.parametrize("method,level,mk", [("gptq", "W4A16", {"actorder": "group"}), ("gptq", "W4A16_ASYM", {}),
+                                             ("smoothquant", "W8A8", {}), ("awq", "W4A16", {"n_grid": 4})])
+def test_llm_compressor_family_end_to_end(tmp_path, method, level, mk):
+    import quantool_b200.methods  # noqa: F401
+    from safetensors.torch import load_file
+    from quantool_b200 import QuantizerRegistry, cabi
+    shape, sd, path = _write_model(tmp_path)
+    g = torch.Generator().manual_seed(1234)
+    ids = torch.randint(0, shape.vocab_size, (12, 128), generator=g)
+    q = QuantizerRegistry.create(method, model_id="org/tiny-llama")
+    out = q.quantize(model=path, level=level, dataset=ids, num_calibration_samples=8, max_seq_length=96,
+                     output_dir=str(tmp_path / "out"), method_kwargs=mk)
+    assert os.path.isdir(out)
+    cfg = json.load(open(os.path.join(out, "config.json")))
+    qc = cfg["quantization_config"]
+    assert qc["quant_method"] == "compressed-tensors" and qc["quantization_status"] == "compressed"
+    assert qc["ignore"] == ["lm_head"] and qc["config_groups"]["group_0"]["targets"] == ["Linear"]
+    t = load_file(os.path.join(out, "model.safetensors"))
+    key = "model.layers.1.mlp.down_proj"
+    N, K = shape.hidden_size, shape.intermediate_size
+    if level.startswith("W4"):
+        assert qc["format"] == "pack-quantized"
+        assert t[key + ".weight_packed"].shape == (N, K // 8) and t[key + ".weight_packed"].dtype == torch.int32
+        assert t[key + ".weight_scale"].shape == (N, K // 128) and t[key + ".weight_scale"].dtype == torch.bfloat16
+        assert t[key + ".weight_shape"].tolist() == [N, K]
+        assert (key + ".weight_g_idx" in t) == (mk.get("actorder") == "group")
+        assert (key + ".weight_zero_point" in t) == (level == "W4A16_ASYM")
+        if level == "W4A16_ASYM":
+            assert t[key + ".weight_zero_point"].shape == (N // 8, K // 128)
+        # the artifact dequantizes back to something close to the original weight
+        codes = cabi.unpack_int32(t[key + ".weight_packed"].cuda(), 4, K).cpu().float()
+        sc = t[key + ".weight_scale"].float()
+        if key + ".weight_g_idx" in t:
+            gi = t[key + ".weight_g_idx"].long()
+            scale_full = sc[:, gi]
+        else:
+            scale_full = sc.repeat_interleave(128, dim=1)
+        if level == "W4A16_ASYM":
+            zp = cabi.unpack_int32(t[key + ".weight_zero_point"].t().contiguous().cuda(), 4, N).cpu().t().float()
+            codes = codes - zp.repeat_interleave(128, dim=1)
+        W = sd[key + ".weight"].float()
+        rel = (torch.linalg.norm(codes * scale_full - W) / torch.linalg.norm(W)).item()
+        assert rel < (0.25 if method != "awq" else 0.6), rel     # AWQ stores the smoothed weight (W*s)
+    else:
+        assert qc["format"] == "int-quantized"
+        assert t[key + ".weight"].dtype == torch.int8 and t[key + ".weight"].shape == (N, K)
+        assert t[key + ".weight_scale"].shape == (N, 1)
+    assert q.last_model is not None
+    q.save_pretrained(str(tmp_path / "saved"))
+    q.save_model_card(str(tmp_path / "saved"))
+    assert os.path.exists(tmp_path / "saved" / "model.safetensors") and os.path.exists(tmp_path / "saved" / "README.md")
+
+
+def test_gguf_plugin_end_to_end_bit_exact_vs_oracle(tmp_path):
+    """BASELINE config 1 in miniature: Q8_0 and Q4_K_M files; every packed tensor bit-exact vs the
+    C oracle run on the fp16-rounded weights, type table as llama-quantize would choose."""
+    import gguf
+    import quantool_b200.methods  # noqa: F401
+    from quantool_b200 import QuantizerRegistry
+    from quantool_b200.engine import gguf_file
+    from oracle import ggml_quants as oq
+    shape, sd, path = _write_model(tmp_path, layers=2, hidden=576, inter=1536, heads=9, kv=3, vocab=1024)
+    q = QuantizerRegistry.create("gguf", model_id="org/tiny-llama")
+    outs = q.quantize(model=path, level=["Q8_0", "Q4_K_M"], output_dir=str(tmp_path / "gg"))
+    assert [os.path.basename(o) for o in outs] == ["tiny-llama-Q8_0.gguf", "tiny-llama-Q4_K_M.gguf"]
+    assert os.path.exists(tmp_path / "gg" / "model.f16.gguf")
+    for out, ftype in zip(outs, ["Q8_0", "Q4_K_M"]):
+        r = gguf.GGUFReader(out)
+        names = {t.name: t for t in r.tensors}
+        assert "token_embd.weight" in names and "blk.1.ffn_down.weight" in names and "output.weight" not in names
+        seen_types = set()
+        for hf_name, w in sd.items():
+            gname = gguf_file.hf_to_gguf_name(hf_name, shape.num_hidden_layers)
+            t = names[gname]
+            if hf_name.endswith("q_proj.weight"):
+                w = gguf_file._permute_qk(w, shape.num_attention_heads)
+            elif hf_name.endswith("k_proj.weight"):
+                w = gguf_file._permute_qk(w, shape.num_key_value_heads)
+            want = gguf_file.tensor_type(gname, tuple(w.shape), ftype, shape.num_hidden_layers, False)
+            assert t.tensor_type.name == want, (gname, t.tensor_type.name, want)
+            seen_types.add(want)
+            if want in ("F32", "F16"):
+                continue
+            x = oq.round_f16(w.float().numpy())
+            ref = oq.quantize(x, want)
+            got = np.asarray(t.data).reshape(ref.shape)
+            assert np.array_equal(got, ref), (gname, want)
+        if ftype == "Q4_K_M":
+            assert {"Q5_0", "Q8_0", "Q4_K", "Q6_K", "F32"} <= seen_types
+    q.save_pretrained(str(tmp_path / "saved"))
+    assert sorted(os.listdir(tmp_path / "saved")) == ["tiny-llama-Q4_K_M.gguf", "tiny-llama-Q8_0.gguf"]
+    with pytest.raises(NotImplementedError):
+        q.quantize(model=path, level="Q3_K_S", output_dir=str(tmp_path / "gg2"))
+
+
+def test_autogptq_view_is_a_pure_repack():
+    from quantool_b200 import cabi
+    from quantool_b200.engine import artifacts
+    N, K = 64, 256
+    codes = torch.randint(-8, 8, (N, K), dtype=torch.int8, device="cuda")
+    packed = cabi.pack_int32(codes, 4)
+    scale = torch.rand((N, K // 128), device="cuda").to(torch.bfloat16)
+    v = artifacts.autogptq_view(packed, scale, None, None, 4, K, 128)
+    assert v["qweight"].shape == (K // 8, N) and v["scales"].shape == (K // 128, N) and v["qzeros"].shape == (K // 128, N // 8)
+    # unpack the AutoGPTQ layout on the host and compare codes
+    qw = v["qweight"].cpu()
+    u = torch.stack([(qw >> (4 * i)) & 0xF for i in range(8)], dim=1).reshape(K, N).t()
+    assert torch.equal((u - 8).to(torch.int8), codes.cpu())
