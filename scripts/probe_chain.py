@@ -1,0 +1,28 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from quantool_b200 import cabi
+def timeit(fn, n=3, warm=1):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize(); ts=[]
+    for _ in range(n):
+        a,b=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return min(ts)
+for K in (4096, 14336):
+    x = torch.randn((8192 if K==4096 else 16384, K), device="cuda", dtype=torch.bfloat16)
+    x[:, :20] *= 20
+    H = torch.zeros((K,K), device="cuda"); cabi.hessian_accumulate(x, H); cabi.hessian_finalize(H, 2/128); del x
+    perm = torch.argsort(torch.diagonal(H), descending=True, stable=True).to(torch.int32)
+    X = torch.empty_like(H); W = torch.empty_like(H)
+    def chain():
+        Hf, dead = cabi.gptq_prepare_hessian(H, perm, 0.01); cabi.gptq_hinv_factor(Hf, X, W)
+    print(f"hinv chain K={K}: {timeit(chain):.2f} ms", flush=True)
+    N = 4096
+    Hf, dead = cabi.gptq_prepare_hessian(H, perm, 0.01); U, info = cabi.gptq_hinv_factor(Hf, X, W)
+    w = (torch.randn((N,K), device="cuda")*0.02).to(torch.bfloat16)
+    wp = cabi.gptq_permute_in(w, perm, dead); scale = torch.empty((N,K//128), device="cuda"); zp = torch.empty_like(scale)
+    def loop():
+        wq = wp.clone(); cabi.gptq_quantize_weight(wq, U, scale, zp, None, 128, 4, True, 0)
+    print(f"gptq loop N={N} K={K}: {timeit(loop):.2f} ms", flush=True)
+    del H, X, W, Hf, U; torch.cuda.empty_cache()
