@@ -105,10 +105,19 @@ int qt_gptq_permute_in(const void* W, int dtype, const int* perm, const uint8_t*
                        void* stream);
 int qt_gptq_permute_out(const float* Wp, const int* inv_perm, void* out, int dtype, int N, int K, void* stream);
 /* blocked column loop (block 128).  mode 0: re-fit group qparams at group starts (group_size 32/64/128),
- * 1: static scales looked up through g_idx (actorder=weight), 2: one scale per row.  W in/out. */
-int qt_gptq_quantize_weight(float* W, const float* U, float* err_scratch, float* scale, float* zp, const int* g_idx,
-                            float* losses, int N, int K, int G, int group_size, int num_bits, int symmetric, int mode,
-                            void* stream);
+ * 1: static scales looked up through g_idx (actorder=weight), 2: one scale per row.  W in/out.
+ * U_hi/U_lo (qt_split_tf32_transpose of U) non-NULL: lazy update on the tensor cores, err_scratch [2,N,128];
+ * NULL: fp32 FFMA GEMM, err_scratch [N,128]. */
+int qt_gptq_quantize_weight(float* W, const float* U, const float* U_hi, const float* U_lo, float* err_scratch,
+                            float* scale, float* zp, const int* g_idx, float* losses, int N, int K, int G,
+                            int group_size, int num_bits, int symmetric, int mode, void* stream);
+/* tensor-core lazy-batch update (tcgen05 kind::tf32, 3-product split for fp32 fidelity):
+ * x -> hi (tf32-exact) + lo ; W[:, i2:] -= (err_hi+err_lo)[M,128] * U[i1:i1+128, i2:], U^T = u_hi+u_lo */
+int qt_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* ut_hi + ut_lo = U^T (the K-major B operand of the lazy update) */
+int qt_split_tf32_transpose(const float* U, float* ut_hi, float* ut_lo, int K, void* stream);
+int qt_gptq_lazy_update_tf32x3(const float* err_hi, const float* err_lo, const float* u_hi, const float* u_lo,
+                               float* W, int M, int K, int i1, int i2, void* stream);
 
 /* ---- SmoothQuant / AWQ --------------------------------------------------------------------------
  * Replaces UPSTREAM llmcompressor SmoothQuantModifier built at

@@ -51,7 +51,10 @@ _SIGS = {
     "qt_awq_wmean_accumulate": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "qt_awq_scale_qdq": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
     "qt_sq_err_sum": [_vp, _vp, _i32, _i64, _vp, _vp],
-    "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "qt_split_tf32": [_vp, _vp, _vp, _i64, _vp],
+    "qt_split_tf32_transpose": [_vp, _vp, _vp, _i32, _vp],
+    "qt_gptq_lazy_update_tf32x3": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
 }
 _RESTYPE = {"qt_last_error": ctypes.c_char_p, "qt_launch_count": ctypes.c_ulonglong}
 
@@ -308,20 +311,53 @@ def gptq_permute_out(wp: torch.Tensor, inv_perm: Optional[torch.Tensor], dtype: 
 GPTQ_MODE_GROUP_REFIT, GPTQ_MODE_STATIC_GIDX, GPTQ_MODE_CHANNEL = 0, 1, 2
 
 
+def split_tf32(x: torch.Tensor, hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None):
+    """x = hi + lo with hi exactly representable in tf32 (operands of the 3xTF32 tensor-core GEMM)."""
+    _dev(x, "x")
+    hi = hi if hi is not None else torch.empty_like(x)
+    lo = lo if lo is not None else torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(lib().qt_split_tf32(_p(x), _p(hi), _p(lo), x.numel(), _stream()), "qt_split_tf32")
+    return hi, lo
+
+
+def split_tf32_transpose(U: torch.Tensor, hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None):
+    """(hi, lo) with hi + lo = U^T, hi tf32-exact: the B operand of the tensor-core lazy update."""
+    _dev(U, "U")
+    K = U.shape[0]
+    hi = hi if hi is not None else torch.empty_like(U)
+    lo = lo if lo is not None else torch.empty_like(U)
+    with torch.cuda.device(U.device):
+        _check(lib().qt_split_tf32_transpose(_p(U), _p(hi), _p(lo), K, _stream()), "qt_split_tf32_transpose")
+    return hi, lo
+
+
+def gptq_lazy_update_tf32x3(err_hi, err_lo, u_hi, u_lo, W, i1: int, i2: int) -> None:
+    M, K = W.shape
+    with torch.cuda.device(W.device):
+        _check(lib().qt_gptq_lazy_update_tf32x3(_p(err_hi), _p(err_lo), _p(u_hi), _p(u_lo), _p(W), M, K, i1, i2,
+                                                _stream()), "qt_gptq_lazy_update_tf32x3")
+
+
 def gptq_quantize_weight(wp: torch.Tensor, U: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor,
                          g_idx: Optional[torch.Tensor], group_size: int, num_bits: int, symmetric: bool,
-                         mode: int, err_scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Blocked GPTQ column loop, in place on wp (fp32 [N,K], permuted order).  Returns per-row losses."""
+                         mode: int, err_scratch: Optional[torch.Tensor] = None,
+                         U_split: Optional[tuple] = None) -> torch.Tensor:
+    """Blocked GPTQ column loop, in place on wp (fp32 [N,K], permuted order).  Returns per-row losses.
+    U_split = split_tf32_transpose(U) runs the lazy-batch update on the tensor cores."""
     _dev(wp, "wp"); _dev(U, "U"); _dev(scale, "scale"); _dev(zp, "zp")
     N, K = wp.shape
     G = scale.shape[1]
     losses = torch.zeros((N,), dtype=torch.float32, device=wp.device)
-    err = err_scratch if err_scratch is not None else torch.empty((N, 128), dtype=torch.float32, device=wp.device)
+    nerr = 2 if U_split is not None else 1
+    err = err_scratch if err_scratch is not None else torch.empty((nerr, N, 128), dtype=torch.float32, device=wp.device)
+    assert err.numel() >= nerr * N * 128
     if g_idx is not None:
         g_idx = _dev(g_idx.to(torch.int32), "g_idx")
+    uh, ul = U_split if U_split is not None else (None, None)
     with torch.cuda.device(wp.device):
-        _check(lib().qt_gptq_quantize_weight(_p(wp), _p(U), _p(err), _p(scale), _p(zp), _p(g_idx), _p(losses),
-                                             N, K, G, max(group_size, 0), num_bits, int(symmetric), mode,
+        _check(lib().qt_gptq_quantize_weight(_p(wp), _p(U), _p(uh), _p(ul), _p(err), _p(scale), _p(zp), _p(g_idx),
+                                             _p(losses), N, K, G, max(group_size, 0), num_bits, int(symmetric), mode,
                                              _stream()), "qt_gptq_quantize_weight")
     return losses
 

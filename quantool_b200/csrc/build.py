@@ -28,6 +28,7 @@ SOURCES = {
     "linalg.cu": [],
     "gptq.cu": [],
     "hessian.cu": [],
+    "lazy_gemm.cu": [],
     "smooth.cu": [],
     "awq.cu": [],
 }

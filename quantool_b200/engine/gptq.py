@@ -54,7 +54,7 @@ class GPTQResult:
 
 
 def quantize_linear(weight: torch.Tensor, H: torch.Tensor, args: WeightArgs, blocksize: int = 128,
-                    percdamp: float = 0.01, check_info: bool = True) -> GPTQResult:
+                    percdamp: float = 0.01, check_info: bool = True, tensor_core_lazy: bool = True) -> GPTQResult:
     """weight [N, K] (CUDA, model dtype), H finalized [K, K] fp32.  H is not modified."""
     if blocksize != 128:
         raise ValueError("the sm_100a GPTQ kernel is specialised for block_size=128 (upstream default)")
@@ -90,7 +90,9 @@ def quantize_linear(weight: torch.Tensor, H: torch.Tensor, args: WeightArgs, blo
     if check_info and int(info.item()) != 0:
         cabi.set_identity(U)   # upstream: on LinAlgError, Hinv = eye(K)
     wp = cabi.gptq_permute_in(weight, perm, dead)
-    losses = cabi.gptq_quantize_weight(wp, U, scale, zp, g_idx_perm, gs, args.num_bits, args.symmetric, mode)
+    U_split = cabi.split_tf32_transpose(U) if (tensor_core_lazy and K > 128) else None
+    losses = cabi.gptq_quantize_weight(wp, U, scale, zp, g_idx_perm, gs, args.num_bits, args.symmetric, mode,
+                                       U_split=U_split)
     wq = cabi.gptq_permute_out(wp, inv_perm, final_dtype)
     g_idx = None
     if args.strategy == "group" and args.actorder == "group":

@@ -90,6 +90,7 @@ class InputContext:
     U: torch.Tensor
     dead: torch.Tensor
     info: torch.Tensor
+    U_split: Optional[tuple] = None   # (hi, lo) of U^T for the tensor-core lazy-batch update
 
 
 @dataclass
@@ -152,6 +153,16 @@ class GPTQLayerQuantizer:
             d.broadcast(dead, owner % d.world)
         return InputContext(K, perm, inv_perm, U, dead, info)
 
+    def split_for_tensor_cores(self, ctx: InputContext) -> None:
+        """U^T as tf32 hi/lo parts (reuses the chain's scratch buffers); call after any identity fallback."""
+        if ctx.K <= 128:
+            return
+        dev = ctx.U.device
+        X = self._buf("X", (ctx.K, ctx.K), torch.float32, dev)
+        W = self._buf("W", (ctx.K, ctx.K), torch.float32, dev)
+        ctx.U_split = cabi.split_tf32_transpose(ctx.U, X, W)
+        self.launches += 1
+
     # ---- per Linear ---------------------------------------------------------------------
     def quantize_linear(self, weight: torch.Tensor, ctx: InputContext) -> LinearResult:
         a = self.args
@@ -182,9 +193,9 @@ class GPTQLayerQuantizer:
                 scale, zp = cabi.minmax_qparams(wl.float(), gs, a.num_bits, a.symmetric)
                 self.launches += 1
             wp = cabi.gptq_permute_in(wl, ctx.perm, ctx.dead)
-            err = self._buf("err", (nloc, 128), torch.float32, dev)
+            err = self._buf("err", (2, nloc, 128), torch.float32, dev)
             losses = cabi.gptq_quantize_weight(wp, ctx.U, scale, zp, g_idx_perm, gs, a.num_bits, a.symmetric, mode,
-                                               err_scratch=err)
+                                               err_scratch=err, U_split=ctx.U_split)
             wq = cabi.gptq_permute_out(wp, ctx.inv_perm, weight.dtype)
             self.launches += 2 + 2 * ((K + 127) // 128)
             loss = losses.sum()
@@ -217,6 +228,7 @@ class GPTQLayerQuantizer:
             ctx = self.prepare_input(hessians[inp], owner=idx)
             if int(ctx.info.item()) != 0:
                 cabi.set_identity(ctx.U)
+            self.split_for_tensor_cores(ctx)
             for lin in linears:
                 if input_of[lin] == inp:
                     out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx)

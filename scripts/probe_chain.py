@@ -24,5 +24,10 @@ for K in (4096, 14336):
     wp = cabi.gptq_permute_in(w, perm, dead); scale = torch.empty((N,K//128), device="cuda"); zp = torch.empty_like(scale)
     def loop():
         wq = wp.clone(); cabi.gptq_quantize_weight(wq, U, scale, zp, None, 128, 4, True, 0)
-    print(f"gptq loop N={N} K={K}: {timeit(loop):.2f} ms", flush=True)
+    print(f"gptq loop (FFMA lazy) N={N} K={K}: {timeit(loop):.2f} ms", flush=True)
+    us = cabi.split_tf32_transpose(U, X, W)
+    print(f"  split_transpose: {timeit(lambda: cabi.split_tf32_transpose(U, X, W)):.2f} ms")
+    def loop_tc():
+        wq = wp.clone(); cabi.gptq_quantize_weight(wq, U, scale, zp, None, 128, 4, True, 0, U_split=us)
+    print(f"gptq loop (tcgen05 tf32x3 lazy) N={N} K={K}: {timeit(loop_tc):.2f} ms", flush=True)
     del H, X, W, Hf, U; torch.cuda.empty_cache()

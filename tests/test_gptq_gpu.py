@@ -206,3 +206,60 @@ def test_pack_kat():
     v = torch.tensor([[-8, -7, 0, 7, 1, 2, 3, 4, 5, 6, 7, -1, -2, -3, -4, -5]], dtype=torch.int8).cuda()
     p = cabi.pack_int32(v, 4).cpu().numpy().astype(np.uint32)
     assert p.tolist() == [[0xCBA9F810, 0x34567FED]]
+
+
+@pytest.mark.parametrize("M,K,i1,i2", [(256, 1024, 128, 256), (300, 2048, 0, 128), (96, 640, 256, 384)])
+def test_lazy_update_tensor_core_tf32x3(M, K, i1, i2):
+    """3xTF32 tcgen05 lazy-batch update is fp32-faithful: compare with fp64 and with the FFMA GEMM."""
+    from quantool_b200 import cabi
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    W = torch.randn((M, K), device="cuda", generator=g)
+    U = torch.triu(torch.randn((K, K), device="cuda", generator=g)) * 0.1
+    err = torch.randn((M, 128), device="cuda", generator=g)
+    ref = W.double().clone()
+    ref[:, i2:] -= err.double() @ U.double()[i1:i1 + 128, i2:]
+    W_simt = W.clone()
+    cabi.sgemm(err, U[i1:i1 + 128, i2:], W_simt[:, i2:], alpha=-1.0, beta=1.0)
+    uh, ul = cabi.split_tf32_transpose(U)
+    eh, el = cabi.split_tf32(err)
+    assert torch.equal(uh + ul, U.t()) and torch.equal((uh.view(torch.int32) & 0x1FFF), torch.zeros_like(uh, dtype=torch.int32))
+    W_tc = W.clone()
+    cabi.gptq_lazy_update_tf32x3(eh, el, uh, ul, W_tc, i1, i2)
+    assert torch.equal(W_tc[:, :i2], W[:, :i2])                       # untouched columns
+    scale = (err.double().abs() @ U.double().abs()[i1:i1 + 128, i2:]).max().item()
+    e_tc = (W_tc.double() - ref).abs().max().item() / scale
+    e_simt = (W_simt.double() - ref).abs().max().item() / scale
+    assert e_tc < 2e-6, (e_tc, e_simt)
+    assert e_tc < 20 * e_simt + 1e-7, (e_tc, e_simt)
+
+
+@pytest.mark.parametrize("level,actorder,N,K", [("W4A16", "group", 160, 768), ("W8A8", None, 96, 640)])
+def test_gptq_tensor_core_path_vs_oracle(level, actorder, N, K):
+    """Same parity bar as the FFMA path, with the lazy-batch update on the tensor cores."""
+    from quantool_b200 import cabi
+    from quantool_b200.engine import gptq as eg, schemes
+    from oracle import gptq as og
+    from compressed_tensors.quantization import ActivationOrdering
+    g = torch.Generator().manual_seed(K)
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    x = _acts(8 * K, K, seed=K + 5)
+    oargs = og.scheme_weight_args(level)
+    if actorder:
+        oargs.actorder = ActivationOrdering.GROUP
+    Ho, n = og.make_empty_hessian(K), 0
+    for xb in x.reshape(8, K, K):
+        Ho, n = og.accumulate_hessian(xb.unsqueeze(0), Ho, n)
+    _, Wq_o, s_o, z_o, gi_o = og.quantize_weight(W, Ho, oargs)
+    args = schemes.resolve(level, actorder)
+    res = eg.quantize_linear(W.cuda(), Ho.cuda(), args, tensor_core_lazy=True)
+    if args.num_bits == 4:
+        codes_o, _, _ = og.compress_packed(Wq_o, s_o, None, gi_o, oargs)
+        _, codes = eg.compress_linear(res.weight, res.scale, res.zero_point, res.g_idx, args)
+    else:
+        codes_o = og.compress_int8(Wq_o, s_o, None, oargs)
+        _, codes = eg.compress_linear(res.weight, res.scale, res.zero_point, res.g_idx, args, fmt="int-quantized")
+    agree = (codes.cpu() == codes_o).float().mean().item()
+    assert agree >= 0.999, agree
+    e_o = og.layer_error(W, Wq_o, x.float())
+    e_c = og.layer_error(W, res.weight.cpu(), x.float())
+    assert abs(e_c - e_o) <= 0.01 * e_o, (e_c, e_o)
