@@ -65,18 +65,29 @@ struct Sched {
     int nunits;
 };
 
-// tile index -> (im, jn).  Column-block jn holds row-blocks 0..min(2jn+1, NI-1).
+// tile index -> (im, jn).  The upper-triangle tile set {im <= 2 jn + 1} is walked in compact
+// super-tiles of ST_I x ST_J tiles (a 2048 x 2048 patch of H): the ~148 tiles in flight at any
+// time then touch ~4K columns of X instead of all K, so each wave streams a third of X from HBM
+// (K = 14336: 165 GB -> ~50 GB per Hessian) and the rest of the operand re-reads hit L2.
+constexpr int ST_I = 16, ST_J = 8;
 QT_D void tile_coords(const Sched& s, int t, int& im, int& jn) {
-    int j = 0;
-    for (;;) {
-        int cnt = 2 * j + 2;
-        cnt = cnt < s.NI ? cnt : s.NI;
-        if (t < cnt) break;
-        t -= cnt;
-        ++j;
+    for (int sj = 0; sj * ST_J < s.NJ; sj++) {
+        const int j0 = sj * ST_J, j1 = (j0 + ST_J < s.NJ) ? j0 + ST_J : s.NJ;
+        for (int si = 0; si * ST_I < s.NI; si++) {
+            const int lo = si * ST_I;
+            if (lo > 2 * (j1 - 1) + 1) break;          // whole super-tile below the diagonal band
+            for (int j = j0; j < j1; j++) {
+                int hi = 2 * j + 1;
+                hi = hi < s.NI - 1 ? hi : s.NI - 1;
+                hi = hi < lo + ST_I - 1 ? hi : lo + ST_I - 1;
+                const int cnt = hi - lo + 1;
+                if (cnt <= 0) continue;
+                if (t < cnt) { im = lo + t; jn = j; return; }
+                t -= cnt;
+            }
+        }
     }
-    im = t;
-    jn = j;
+    im = 0; jn = 0;   // unreachable for t < ntiles
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -287,17 +298,25 @@ int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* strea
     int dev = 0, nsm = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    // token splits: enough units to balance the SMs (waste <= ~3%), at least ~16 k-blocks per unit
+    // token splits.  Measured on B200 (K = 14336, T = 262144): 53.5 ms at S = 1, 49.2 at S = 8, 47.5 at
+    // S = 16 - the CTAs of one split share a token slab, and the slab has to be small enough
+    // (<= ~512 MB of X) for its re-reads across waves to be served by L2.  Above that floor pick the
+    // split count with the best wave quantisation (+6 k-blocks of per-unit overhead).
     int S = 1;
     if (g_force_splits > 0) {
         S = g_force_splits;
     } else {
-        const int smax = s.nkb / 16 > 1 ? s.nkb / 16 : 1;
+        const double slab_bytes = (double)T * K * 2.0;
+        int smin = (int)((slab_bytes + 536870911.0) / 536870912.0);
+        if (smin < 1) smin = 1;
+        int smax = s.nkb / 16 > 1 ? s.nkb / 16 : 1;
+        if (smin > smax) smin = smax;
+        if (smax > 2 * smin + 8) smax = 2 * smin + 8;
         double best = 1e30;
-        for (int c = 1; c <= smax && c <= 256; c++) {
+        for (int c = smin; c <= smax; c++) {
             const long long units = (long long)s.ntiles * c;
             const long long waves = (units + nsm - 1) / nsm;
-            const double eff_time = (double)waves * ((double)s.nkb / c + 6.0);  // +6 k-blocks of per-unit overhead
+            const double eff_time = (double)waves * ((double)s.nkb / c + 6.0);
             if (eff_time < best * 0.995) { best = eff_time; S = c; }
         }
     }

@@ -124,8 +124,9 @@ class GPTQLayerQuantizer:
         self._scratch.clear()
 
     # ---- per distinct input -------------------------------------------------------------
-    def prepare_input(self, H: torch.Tensor, owner: int = 0) -> InputContext:
-        """H: finalized (scaled, symmetric) fp32 [K,K], identical on every rank."""
+    def prepare_input(self, H: torch.Tensor, owner: int = 0, slot: str = "") -> InputContext:
+        """H: finalized (scaled, symmetric) fp32 [K,K], identical on every rank.  `slot` separates the
+        scratch buffers of inputs that are processed concurrently on different streams."""
         K = H.shape[0]
         dev = H.device
         d = self.dist
@@ -133,17 +134,17 @@ class GPTQLayerQuantizer:
         if self.args.actorder in ("group", "weight"):
             perm = torch.argsort(torch.diagonal(H), descending=True, stable=True).to(torch.int32)
             inv_perm = torch.argsort(perm).to(torch.int32)
-        U = self._buf("U", (K, K), torch.float32, dev)
+        U = self._buf("U" + slot, (K, K), torch.float32, dev)
         info = torch.zeros((1,), dtype=torch.int32, device=dev)
         dead = torch.empty((K,), dtype=torch.uint8, device=dev)
         if (not d.on) or d.rank == owner % d.world:
-            damp = self._buf("damp", (1,), torch.float32, dev)
+            damp = self._buf("damp" + slot, (1,), torch.float32, dev)
             perm_p = perm
             cabi._check(cabi.lib().qt_gptq_prepare_hessian(cabi._p(H), cabi._p(perm_p), K, float(self.percdamp),
                                                            cabi._p(U), cabi._p(dead), cabi._p(damp),
                                                            cabi._stream()), "qt_gptq_prepare_hessian")
-            X = self._buf("X", (K, K), torch.float32, dev)
-            W = self._buf("W", (K, K), torch.float32, dev)
+            X = self._buf("X" + slot, (K, K), torch.float32, dev)
+            W = self._buf("W" + slot, (K, K), torch.float32, dev)
             cabi._check(cabi.lib().qt_gptq_hinv_factor(cabi._p(U), cabi._p(X), cabi._p(W), K, cabi._p(info),
                                                        cabi._stream()), "qt_gptq_hinv_factor")
             self.launches += 2
@@ -151,15 +152,18 @@ class GPTQLayerQuantizer:
             d.broadcast(U, owner % d.world)
             d.broadcast(info, owner % d.world)
             d.broadcast(dead, owner % d.world)
-        return InputContext(K, perm, inv_perm, U, dead, info)
+        ctx = InputContext(K, perm, inv_perm, U, dead, info)
+        ctx.slot = slot
+        return ctx
 
     def split_for_tensor_cores(self, ctx: InputContext) -> None:
         """U^T as tf32 hi/lo parts (reuses the chain's scratch buffers); call after any identity fallback."""
         if ctx.K <= 128:
             return
         dev = ctx.U.device
-        X = self._buf("X", (ctx.K, ctx.K), torch.float32, dev)
-        W = self._buf("W", (ctx.K, ctx.K), torch.float32, dev)
+        slot = getattr(ctx, "slot", "")
+        X = self._buf("X" + slot, (ctx.K, ctx.K), torch.float32, dev)
+        W = self._buf("W" + slot, (ctx.K, ctx.K), torch.float32, dev)
         ctx.U_split = cabi.split_tf32_transpose(ctx.U, X, W)
         self.launches += 1
 
@@ -193,7 +197,7 @@ class GPTQLayerQuantizer:
                 scale, zp = cabi.minmax_qparams(wl.float(), gs, a.num_bits, a.symmetric)
                 self.launches += 1
             wp = cabi.gptq_permute_in(wl, ctx.perm, ctx.dead)
-            err = self._buf("err", (2, nloc, 128), torch.float32, dev)
+            err = self._buf("err" + getattr(ctx, "slot", ""), (2, nloc, 128), torch.float32, dev)
             losses = cabi.gptq_quantize_weight(wp, ctx.U, scale, zp, g_idx_perm, gs, a.num_bits, a.symmetric, mode,
                                                err_scratch=err, U_split=ctx.U_split)
             wq = cabi.gptq_permute_out(wp, ctx.inv_perm, weight.dtype)
@@ -219,19 +223,54 @@ class GPTQLayerQuantizer:
     # ---- one decoder layer from ready-made activations ----------------------------------
     def quantize_layer(self, weights: Dict[str, torch.Tensor], hessians: Dict[str, torch.Tensor],
                        linears=llama.LINEARS, input_of=llama.INPUT_OF) -> Dict[str, LinearResult]:
-        """hessians: finalized H per distinct input name.  Returns per-Linear results; the
-        identity fallback of upstream (LinAlgError -> Hinv = I) is applied per input."""
+        """hessians: finalized H per distinct input name.  Returns per-Linear results.
+
+        The distinct inputs of a layer are independent, and the small-K inverse-factor chains are
+        bound by the latency of their sequential pivots, not by throughput: each input runs on its
+        own CUDA stream (chain -> split -> column loops of its Linears) so that those latency-bound
+        kernels fill the SMs the big-K GEMMs leave idle.  The Cholesky status words are read once,
+        after everything is queued; a failed factorisation (upstream: LinAlgError -> Hinv = I) is
+        redone with the identity, which is rare enough not to matter."""
         names = sorted(hessians, key=lambda n: -hessians[n].shape[0])
         out: Dict[str, LinearResult] = {}
-        # One U buffer per K is reused, so finish all Linears of an input before the next input
+        dev = next(iter(hessians.values())).device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_streams"):
+            self._streams = {}
+        ready = torch.cuda.Event()
+        ready.record(main)
+        ctxs, done = {}, []
         for idx, inp in enumerate(names):
-            ctx = self.prepare_input(hessians[inp], owner=idx)
-            if int(ctx.info.item()) != 0:
+            st = self._streams.get(idx)
+            if st is None:
+                st = self._streams[idx] = torch.cuda.Stream(device=dev)
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                ctx = self.prepare_input(hessians[inp], owner=idx, slot=f"#{idx}")
+                self.split_for_tensor_cores(ctx)
+                for lin in linears:
+                    if input_of[lin] == inp:
+                        out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            ctxs[inp] = ctx
+            done.append(ev)
+            for t in (hessians[inp], *(weights[f"{l}.weight"] for l in linears if input_of[l] == inp)):
+                t.record_stream(st)
+        for ev in done:
+            main.wait_event(ev)
+        for r in out.values():
+            for t in (r.weight, r.scale, r.zero_point, r.loss):
+                t.record_stream(main)
+        infos = torch.cat([ctxs[n].info for n in names]).cpu()          # one sync per layer
+        for idx, inp in enumerate(names):
+            if int(infos[idx]) != 0:
+                ctx = ctxs[inp]
                 cabi.set_identity(ctx.U)
-            self.split_for_tensor_cores(ctx)
-            for lin in linears:
-                if input_of[lin] == inp:
-                    out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx)
+                self.split_for_tensor_cores(ctx)
+                for lin in linears:
+                    if input_of[lin] == inp:
+                        out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx)
         return out
 
 
