@@ -12,9 +12,9 @@
 // dst is the array of packed blocks, back to back, no padding (GGUF tensor data layout).
 //
 // Simple types (32-element blocks) are HBM-bound streaming kernels:
-//   4 lanes per block, one 128-bit load per lane (8 fp16/bf16 elements), 4 blocks in flight
-//   per thread, cross-lane reduction by shuffles, packed bytes staged in shared memory and
-//   written back with coalesced 128-bit stores.
+//   4 lanes per block, each owning the element pairs that share an output byte, 4 blocks in
+//   flight per thread, cross-lane min/max by shuffles, packed bytes staged in shared memory
+//   and written back with coalesced 128-bit stores.
 // K-quants (256-element super-blocks) run a 19-21 candidate scale search per sub-block with
 //   strictly ordered fp32 sums: ~500 ALU ops per element, so they are fp32-ALU-bound, not
 //   HBM-bound; one thread owns one sub-block, input/output staged through shared memory.
@@ -53,14 +53,56 @@ QT_D void copy_out(uint8_t* __restrict__ gdst, const uint8_t* sout, int bytes) {
 
 // ---------------------------------------------------------------------------------------
 // 32-element block types.  256 threads = 64 blocks per pass, U passes per CTA iteration.
+// Lane q (0..3) of a block owns elements 4q..4q+3 and 16+4q..16+4q+3: exactly the pairs that
+// share an output byte in the 4/5-bit formats, so no packed data crosses lanes.  The kernels
+// were issue-bound (29 instructions per element in the first version): the arg-max is tracked
+// as a signed max and min (2 FMNMX per element; the first-wins tie between +a and -a is a rare
+// slow path), and float->int truncation of the non-negative codes uses a round-down magic add
+// instead of the quarter-rate F2I.
 // ---------------------------------------------------------------------------------------
 constexpr int kSimpleU = 4;
 constexpr int kSimpleBlocksPerCta = 64 * kSimpleU;  // 256 blocks: 256*BB is a multiple of 16
 
+QT_D uint2 ldg_stream8(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+// elements 4q..4q+3 -> v[0..3], 16+4q..16+4q+3 -> v[4..7] of block `blk`
+template <int DT>
+QT_D void load_block_quarter(const void* __restrict__ src, int64_t blk, int q, float v[8]) {
+    if (DT == QT_F32) {
+        const char* p = (const char*)src + blk * 128 + q * 16;
+        const uint4 a = ldg_stream(p), b = ldg_stream(p + 64);
+        v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+        v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+    } else {
+        const char* p = (const char*)src + blk * 64 + q * 8;
+        const uint2 a = ldg_stream8(p), b = ldg_stream8(p + 32);
+        const uint32_t w[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (DT == QT_F16) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                v[2 * i] = f.x; v[2 * i + 1] = f.y;
+            } else {
+                v[2 * i] = __uint_as_float(w[i] << 16);
+                v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            }
+        }
+    }
+}
+
+// floor of a float in [0, 2^22) as an integer, without F2I: round-down add of 2^23 leaves the
+// integer in the low mantissa bits.  (C's (int8_t)(x + 8.5f) truncates; the argument is >= 0.5.)
+QT_D int trunc_pos(float t) { return __float_as_int(__fadd_rd(t, 8388608.0f)) & 0x7fffff; }
+
 template <int TYPE>
 QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
-    // lane q (0..3) of the block holds elements 8q..8q+7 in v
+    const unsigned m4 = 0xFu << (threadIdx.x & 28);   // the 4 lanes of this block
     if (TYPE == T_Q8_0) {
+        // Q8_0 keeps the plain mapping: lane q owns elements 8q..8q+7 (one 128-bit load)
         float amax = 0.0f;
 #pragma unroll
         for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
@@ -83,44 +125,39 @@ QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
     constexpr bool kSym = (TYPE == T_Q4_0 || TYPE == T_Q5_0);
     constexpr bool k5 = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
     constexpr int kHdr = kSym ? 2 : 4;
-    uint32_t nib = 0;   // 8 low nibbles
-    uint32_t hb = 0;    // 8 high bits (5-bit types)
+    float mn = v[0], mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) { mn = fminf(mn, v[i]); mx = fmaxf(mx, v[i]); }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    int xi[8];
     if (kSym) {
-        // first element with the largest |v| wins (strict < in a forward scan)
-        float amax = 0.0f, mx = 0.0f;
-        int idx = 8 * q;
+        // signed value of the first element with the largest |v| (strict < in a forward scan)
+        float smax = (mx > -mn) ? mx : mn;
+        if (mx == -mn && mx > 0.f) {
+            // +a and -a both present: the earlier element decides the sign.  Block-uniform, rare.
+            int key = 64;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float a = fabsf(v[i]);
-            if (amax < a) { amax = a; mx = v[i]; idx = 8 * q + i; }
+            for (int i = 7; i >= 0; i--) {
+                const int e = (i < 4) ? 4 * q + i : 16 + 4 * q + (i - 4);
+                if (fabsf(v[i]) == mx) { const int k2 = 2 * e + (v[i] < 0.f ? 1 : 0); key = k2 < key ? k2 : key; }
+            }
+            int o1 = __shfl_xor_sync(m4, key, 1); key = o1 < key ? o1 : key;
+            o1 = __shfl_xor_sync(m4, key, 2); key = o1 < key ? o1 : key;
+            smax = (key & 1) ? mn : mx;
         }
-#pragma unroll
-        for (int off = 1; off <= 2; off <<= 1) {
-            const float oa = __shfl_xor_sync(0xffffffffu, amax, off);
-            const float om = __shfl_xor_sync(0xffffffffu, mx, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
-            if (oa > amax || (oa == amax && oi < idx)) { amax = oa; mx = om; idx = oi; }
-        }
-        const float d = mx / (k5 ? -16 : -8);
+        const float d = smax / (k5 ? -16 : -8);
         const float id = d ? 1.0f / d : 0.0f;
         if (q == 0) sts16(o, __half_as_ushort(__float2half_rn(d)));
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float x0 = v[i] * id;
-            int xi = (int)(signed char)(int)(x0 + (k5 ? 16.5f : 8.5f));
-            xi = xi < (k5 ? 31 : 15) ? xi : (k5 ? 31 : 15);
-            nib |= (uint32_t)(xi & 0xF) << (4 * i);
-            hb |= (uint32_t)((xi >> 4) & 1) << i;
+            const int t = trunc_pos(v[i] * id + (k5 ? 16.5f : 8.5f));
+            xi[i] = t < (k5 ? 31 : 15) ? t : (k5 ? 31 : 15);
         }
     } else {
-        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { mn = fminf(mn, v[i]); mx = fmaxf(mx, v[i]); }
-#pragma unroll
-        for (int off = 1; off <= 2; off <<= 1) {
-            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        }
         const float d = (mx - mn) / (k5 ? 31 : 15);
         const float id = d ? 1.0f / d : 0.0f;
         if (q == 0) {
@@ -129,33 +166,25 @@ QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float x0 = (v[i] - mn) * id;
-            int xi;
-            if (k5) {
-                xi = (int)(unsigned char)(int)(x0 + 0.5f);
-            } else {
-                xi = (int)(signed char)(int)(x0 + 0.5f);
-                xi = xi < 15 ? xi : 15;
-            }
-            nib |= (uint32_t)(xi & 0xF) << (4 * i);
-            hb |= (uint32_t)((xi >> 4) & 1) << i;
+            const int t = trunc_pos((v[i] - mn) * id + 0.5f);
+            xi[i] = k5 ? (t & 0xff) : (t < 15 ? t : 15);
         }
     }
-    // byte j (j<16) = elem j (low nibble) | elem j+16 (high nibble): lanes 0,1 own j = 8q+i
-    const uint32_t other = __shfl_xor_sync(0xffffffffu, nib, 2);
+    // byte j = elem j (low nibble) | elem j+16 (high nibble), j = 4q + i: both live in this lane
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) word |= (uint32_t)((xi[i] & 0xF) | ((xi[i + 4] & 0xF) << 4)) << (8 * i);
     if (k5) {
-        uint32_t qh = hb << (8 * q);   // bit (8q+i): lanes 0,1 -> elems 0..15, lanes 2,3 -> elems 16..31
+        uint32_t qh = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) qh |= (uint32_t)((xi[i] >> 4) & 1) << (4 * q + i) | (uint32_t)((xi[i + 4] >> 4) & 1) << (16 + 4 * q + i);
         qh |= __shfl_xor_sync(0xffffffffu, qh, 1);
         qh |= __shfl_xor_sync(0xffffffffu, qh, 2);
         if (q == 0) { sts16(o + kHdr, qh & 0xffff); sts16(o + kHdr + 2, qh >> 16); }
     }
-    if (q < 2) {
-        const uint32_t w0 = spread4(nib & 0xffff) | (spread4(other & 0xffff) << 4);
-        const uint32_t w1 = spread4(nib >> 16) | (spread4(other >> 16) << 4);
-        uint8_t* qs = o + kHdr + (k5 ? 4 : 0) + 8 * q;
-        sts16(qs, w0 & 0xffff); sts16(qs + 2, w0 >> 16);
-        sts16(qs + 4, w1 & 0xffff); sts16(qs + 6, w1 >> 16);
-    }
+    uint8_t* qs = o + kHdr + (k5 ? 4 : 0) + 4 * q;
+    sts16(qs, word & 0xffff);
+    sts16(qs + 2, word >> 16);
 }
 
 template <int TYPE, int DT, bool VIA_F16>
@@ -171,7 +200,8 @@ __global__ void __launch_bounds__(256) pack_simple_kernel(const void* __restrict
         for (int u = 0; u < kSimpleU; u++) {
             const int64_t blk = base + u * 64 + bl;
             if (blk < nblocks) {
-                load8<DT>(src, blk * 4 + q, v[u]);
+                if (TYPE == T_Q8_0) load8<DT>(src, blk * 4 + q, v[u]);
+                else load_block_quarter<DT>(src, blk, q, v[u]);
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[u][i] = 0.f;
