@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gguf", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--workload", default="gptq", choices=["gptq", "awq", "smoothquant"],
+                    help="gptq = the headline line; awq / smoothquant = BASELINE configs 3 / 4 (extra lines)")
     return ap.parse_args()
 
 
@@ -113,10 +115,10 @@ def cpu_reference_sample(shape, level, actorder, n_samples, seq, threads=None):
     from compressed_tensors.quantization import ActivationOrdering
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    K, N = shape.hidden_size, shape.kv_dim          # k_proj: the smallest Linear of the layer
+    K, N = shape.hidden_size, shape.q_dim           # q_proj
     g = torch.Generator().manual_seed(0)
     W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
-    nb = 2
+    nb = 8
     x = torch.randn((nb, seq, K), generator=g).to(torch.bfloat16)
     args = og.scheme_weight_args(level)
     if actorder:
@@ -137,7 +139,7 @@ def cpu_reference_sample(shape, level, actorder, n_samples, seq, threads=None):
     quant_units = sum(q_work(n_, k_) for (n_, k_) in shape.linear_shapes().values()) / q_work(N, K) * L
     total = t_h * hess_units + t_q * quant_units
     sample = (f"oracle port (torch CPU fp32): Hessian of {nb}x{seq} tokens at K={K} ({t_h:.2f}s) + quantize_weight of "
-              f"k_proj [{N},{K}] ({t_q:.2f}s); extrapolated to {L} layers x 7 Linears x {n_samples} samples by "
+              f"q_proj [{N},{K}] ({t_q:.2f}s); extrapolated to {L} layers x 7 Linears x {n_samples} samples by "
               f"FLOP ratios (samples*K^2 ; 4/3 K^3 + N K^2) - an extrapolation, not a full CPU run")
     return {"value": total, "unit": "s", "cores": threads, "kind": "port", "sample": sample,
             "sample_seconds": t_h + t_q}
@@ -165,6 +167,83 @@ def gguf_probe(device):
         byts = x.numel() * 2 + y.numel()
         out[t] = {"ms": round(ms, 4), "GBps": round(byts / ms / 1e6, 1), "bytes_per_elem": round(byts / x.numel(), 4)}
     return out
+
+
+def side_workload(a, shape, dev):
+    """BASELINE configs 3 (AWQ W4A16 g128 n_grid=20, 128x512) and 4 (SmoothQuant alpha=0.5 scales + fold)
+    on the random-init 8B shape, single GPU, device-resident inputs.  One JSON line each."""
+    from quantool_b200 import cabi
+    from quantool_b200.engine import awq as eawq, llama, schemes, smoothquant as esq
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    n, seq = (a.samples, 512)
+    L = shape.num_hidden_layers
+    g = torch.Generator(device=dev).manual_seed(5)
+    h = (torch.randn((n, seq, shape.hidden_size), device=dev, generator=g)).to(torch.bfloat16)
+    cos, sin = llama.rope_tables(shape, seq, dev, h.dtype)
+
+    def ev_time(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    if a.workload == "smoothquant":
+        def step():
+            for l in range(L):
+                w = llama.random_layer_weights(shape, l % 2, dev)
+                esq.smooth_layer(shape, w, h, cos, sin, 0.5, 8)
+        for _ in range(min(a.warmup, 1)):
+            step()
+        ms = sum(ev_time(step) for _ in range(a.steps)) / a.steps
+        # dominant smoothing kernel: per-channel min/max over [T, 4096] bf16 (HBM streaming)
+        x = h.reshape(-1, shape.hidden_size)
+        mn, mx = cabi.new_minmax(shape.hidden_size, dev)
+        big = torch.cat([x] * 4)                                    # 2 GiB > L2
+        cabi.channel_minmax(big, mn, mx)
+        kms = min(ev_time(lambda: cabi.channel_minmax(big, mn, mx)) for _ in range(5))
+        gbs = big.numel() * 2 / kms / 1e6
+        w = llama.random_layer_weights(shape, 0, dev)
+        wt = w["mlp.gate_proj.weight"]
+        s = torch.rand((wt.shape[1],), device=dev) + 0.5
+        fms = min(ev_time(lambda: cabi.scale_matrix_(wt, s)) for _ in range(5))
+        line = {"metric": "smoothquant_seconds_per_8b_model", "value": ms / 1e3, "unit": "s", "n_gpus": 1,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False,
+                "config": {"workload": f"smoothquant alpha=0.5 scales+fold on random-init {a.model}, {n}x{seq} tokens "
+                                       f"(includes the calibration forward of each layer)"},
+                "roofline": {"kernel": "col_reduce_kernel<MINMAX>", "bound": "hbm", "achieved": gbs, "peak": hbm,
+                             "unit": "GB/s", "frac": gbs / hbm, "traffic": None},
+                "fold_kernel": {"kernel": "scale_kernel", "GBps": wt.numel() * 4 / fms / 1e6,
+                                "frac": wt.numel() * 4 / fms / 1e6 / hbm}}
+        print(json.dumps(line))
+        return
+    args = schemes.resolve("W4A16")
+    layer_ms = []
+
+    def step():
+        for l in range(L if not a.layers else a.layers):
+            w = llama.random_layer_weights(shape, l % 2, dev)
+            eawq.awq_layer(shape, w, h, cos, sin, args, 8)
+    for _ in range(min(a.warmup, 1)):
+        w = llama.random_layer_weights(shape, 0, dev)
+        eawq.awq_layer(shape, w, h, cos, sin, args, 8)
+    ms = sum(ev_time(step) for _ in range(a.steps)) / a.steps
+    wt = llama.random_layer_weights(shape, 0, dev)["mlp.gate_proj.weight"]
+    s = torch.rand((wt.shape[1],), device=dev) + 0.5
+    out = torch.empty_like(wt)
+    kms = min(ev_time(lambda: cabi.awq_scale_qdq(wt, s, 128, 4, True, out=out)) for _ in range(5))
+    gbs = wt.numel() * 4 / kms / 1e6
+    line = {"metric": "awq_seconds_per_8b_model", "value": ms / 1e3, "unit": "s", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False,
+            "config": {"workload": f"awq W4A16 g128 n_grid=20 on random-init {a.model} "
+                                   f"({L if not a.layers else a.layers} layers), {n}x{seq} tokens; parent forwards are torch "
+                                   f"(cuBLAS/SDPA) plumbing"},
+            "roofline": {"kernel": "scale_qdq_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": gbs / hbm, "traffic": None, "algorithmic": "4 B/elem (bf16 read + bf16 write)"}}
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
@@ -208,6 +287,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if a.workload != "gptq":
+        return side_workload(a, shape, dev)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)

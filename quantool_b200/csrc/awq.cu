@@ -67,7 +67,44 @@ __global__ void __launch_bounds__(256) wmean_kernel(const void* __restrict__ W, 
     atomicAdd(colsum + c, acc);
 }
 
+// 4 consecutive elements of a 16/32-bit row
+template <int DT>
+QT_D void ld4(const void* p, long long i, float v[4]) {
+    if (DT == QT_F32) {
+        const float4 a = *reinterpret_cast<const float4*>((const float*)p + i);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else {
+        const uint2 a = *reinterpret_cast<const uint2*>((const char*)p + i * 2);
+        if (DT == QT_F16) {
+            v[0] = f16_bits_to_float(a.x & 0xffffu); v[1] = f16_bits_to_float(a.x >> 16);
+            v[2] = f16_bits_to_float(a.y & 0xffffu); v[3] = f16_bits_to_float(a.y >> 16);
+        } else {
+            v[0] = bf16_bits_to_float(a.x & 0xffffu); v[1] = bf16_bits_to_float(a.x >> 16);
+            v[2] = bf16_bits_to_float(a.y & 0xffffu); v[3] = bf16_bits_to_float(a.y >> 16);
+        }
+    }
+}
+template <int DT>
+QT_D void st4(void* p, long long i, const float v[4]) {
+    if (DT == QT_F32) {
+        *reinterpret_cast<float4*>((float*)p + i) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        uint2 o;
+        if (DT == QT_F16) {
+            o.x = (uint32_t)__half_as_ushort(__float2half_rn(v[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(v[1])) << 16);
+            o.y = (uint32_t)__half_as_ushort(__float2half_rn(v[2])) | ((uint32_t)__half_as_ushort(__float2half_rn(v[3])) << 16);
+        } else {
+            o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[1])) << 16);
+            o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[3])) << 16);
+        }
+        *reinterpret_cast<uint2*>((char*)p + i * 2) = o;
+    }
+}
+
 // out[n][c] = rnd( pq( rnd(W[n][c] * s[c]) ) / s[c] )   (pq = _pseudo_quantize_tensor per group)
+// One warp per row; a group of gs columns is walked in chunks of 128 (lane = 4 consecutive
+// columns, 64/128-bit accesses); the scaled values stay in registers when gs <= 128, which is the
+// preset case (one pass over W), and are recomputed from L1 for larger groups.
 template <int DT>
 __global__ void __launch_bounds__(256) scale_qdq_kernel(const void* __restrict__ W, const float* __restrict__ s,
                                                         int N, int K, int gs, int num_bits, int symmetric,
@@ -76,40 +113,61 @@ __global__ void __launch_bounds__(256) scale_qdq_kernel(const void* __restrict__
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= N) return;
     const int G = K / gs;
+    const float max_int_s = (float)((1 << (num_bits - 1)) - 1), min_int_s = -(float)(1 << (num_bits - 1));
+    const float max_int_a = (float)((1 << num_bits) - 1);
     for (int g = 0; g < G; g++) {
         const long long base = (long long)row * K + (long long)g * gs;
         const float* sg = s + (long long)g * gs;
         float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
-        for (int c = lane; c < gs; c += 32) {
-            const float v = rnd<DT>(ld<DT>(W, base + c) * sg[c]);
-            mn = fminf(mn, v);
-            mx = fmaxf(mx, v);
+        float keep[4], ks[4];
+        for (int c0 = lane * 4; c0 < gs; c0 += 128) {
+            float w4[4];
+            ld4<DT>(W, base + c0, w4);
+            const float4 s4 = *reinterpret_cast<const float4*>(sg + c0);
+            ks[0] = s4.x; ks[1] = s4.y; ks[2] = s4.z; ks[3] = s4.w;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                keep[i] = rnd<DT>(w4[i] * ks[i]);
+                mn = fminf(mn, keep[i]);
+                mx = fmaxf(mx, keep[i]);
+            }
         }
         mn = warp_min(mn);
         mx = warp_max(mx);
+        float sc, z = 0.f;
         if (symmetric) {
-            const float max_int = (float)((1 << (num_bits - 1)) - 1), min_int = -(float)(1 << (num_bits - 1));
             const float max_val = fmaxf(fmaxf(fabsf(mn), fabsf(mx)), rnd<DT>(1e-5f));
-            const float sc = rnd<DT>(max_val / max_int);
-            for (int c = lane; c < gs; c += 32) {
-                const float v = rnd<DT>(ld<DT>(W, base + c) * sg[c]);
-                float q = rintf(rnd<DT>(v / sc));
-                q = fminf(fmaxf(q, min_int), max_int);
-                const float dq = rnd<DT>(q * sc);
-                st<DT>(out, base + c, dq / sg[c]);
-            }
+            sc = rnd<DT>(max_val / max_int_s);
         } else {
-            const float max_int = (float)((1 << num_bits) - 1);
-            const float sc = rnd<DT>(fmaxf(rnd<DT>(mx - mn), rnd<DT>(1e-5f)) / max_int);
-            float z = -rintf(rnd<DT>(mn / sc));
-            z = fminf(fmaxf(z, 0.f), max_int);
-            for (int c = lane; c < gs; c += 32) {
-                const float v = rnd<DT>(ld<DT>(W, base + c) * sg[c]);
-                float q = rnd<DT>(rintf(rnd<DT>(v / sc)) + z);
-                q = fminf(fmaxf(q, 0.f), max_int);
-                const float dq = rnd<DT>(rnd<DT>(q - z) * sc);
-                st<DT>(out, base + c, dq / sg[c]);
+            sc = rnd<DT>(fmaxf(rnd<DT>(mx - mn), rnd<DT>(1e-5f)) / max_int_a);
+            z = -rintf(rnd<DT>(mn / sc));
+            z = fminf(fmaxf(z, 0.f), max_int_a);
+        }
+        for (int c0 = lane * 4; c0 < gs; c0 += 128) {
+            if (gs > 128) {   // values not kept: recompute
+                float w4[4];
+                ld4<DT>(W, base + c0, w4);
+                const float4 s4 = *reinterpret_cast<const float4*>(sg + c0);
+                ks[0] = s4.x; ks[1] = s4.y; ks[2] = s4.z; ks[3] = s4.w;
+#pragma unroll
+                for (int i = 0; i < 4; i++) keep[i] = rnd<DT>(w4[i] * ks[i]);
             }
+            float o4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float dq;
+                if (symmetric) {
+                    float q = rintf(rnd<DT>(keep[i] / sc));
+                    q = fminf(fmaxf(q, min_int_s), max_int_s);
+                    dq = rnd<DT>(q * sc);
+                } else {
+                    float q = rnd<DT>(rintf(rnd<DT>(keep[i] / sc)) + z);
+                    q = fminf(fmaxf(q, 0.f), max_int_a);
+                    dq = rnd<DT>(rnd<DT>(q - z) * sc);
+                }
+                o4[i] = dq / ks[i];
+            }
+            st4<DT>(out, base + c0, o4);
         }
     }
 }
@@ -173,7 +231,7 @@ int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int
                      int symmetric, void* out, void* stream) {
     if (!W || !s || !out || N <= 0 || K <= 0 || num_bits < 2 || num_bits > 8) return QT_ERR_INVALID;
     const int gs = group_size > 0 ? group_size : K;
-    if (K % gs) return QT_ERR_INVALID;
+    if (K % gs || (gs & 3) || (K & 3) || ((uintptr_t)W & 15) || ((uintptr_t)out & 15) || ((uintptr_t)s & 15)) return QT_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = (N + 7) / 8;
     switch (dtype) {

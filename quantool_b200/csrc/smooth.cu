@@ -106,22 +106,46 @@ __global__ void smooth_scales_kernel(const float* __restrict__ amin, const float
     s_out[c] = s;
 }
 
-// W[n][c] (op)= s[c]  (by_row: s[n]) evaluated in W's dtype; s is fp32
+// W[n][c] (op)= s[c]  (by_row: s[n]) evaluated in W's dtype; s is fp32.  One thread = 8 consecutive
+// columns (one 128-bit load + store for 16-bit types); K % 8 == 0.
 template <int DT, bool DIV, bool BY_ROW>
 __global__ void __launch_bounds__(256) scale_kernel(void* __restrict__ W, const float* __restrict__ s, int N, int K) {
-    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int c8 = (blockIdx.x * 256 + threadIdx.x) * 8;
     const int n = blockIdx.y;
-    if (c >= K) return;
-    const long long idx = (long long)n * K + c;
-    const float sv = BY_ROW ? s[n] : s[c];
-    float v;
-    if (DT == QT_F32) v = reinterpret_cast<float*>(W)[idx];
-    else if (DT == QT_F16) v = __half2float(reinterpret_cast<__half*>(W)[idx]);
-    else v = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(W)[idx]);
-    v = DIV ? v / sv : v * sv;
-    if (DT == QT_F32) reinterpret_cast<float*>(W)[idx] = v;
-    else if (DT == QT_F16) reinterpret_cast<__half*>(W)[idx] = __float2half_rn(v);
-    else reinterpret_cast<__nv_bfloat16*>(W)[idx] = __float2bfloat16_rn(v);
+    if (c8 >= K) return;
+    const long long idx = (long long)n * K + c8;
+    float v[8], sv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) sv[i] = BY_ROW ? s[n] : s[c8 + i];
+    if (DT == QT_F32) {
+        const float4 a = *reinterpret_cast<const float4*>((float*)W + idx), b = *reinterpret_cast<const float4*>((float*)W + idx + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 a = *reinterpret_cast<const uint4*>((char*)W + idx * 2);
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (DT == QT_F16) { v[2 * i] = f16_bits_to_float(w[i] & 0xffffu); v[2 * i + 1] = f16_bits_to_float(w[i] >> 16); }
+            else { v[2 * i] = bf16_bits_to_float(w[i] & 0xffffu); v[2 * i + 1] = bf16_bits_to_float(w[i] >> 16); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = DIV ? v[i] / sv[i] : v[i] * sv[i];
+    if (DT == QT_F32) {
+        *reinterpret_cast<float4*>((float*)W + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>((float*)W + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (DT == QT_F16)
+                w[i] = (uint32_t)__half_as_ushort(__float2half_rn(v[2 * i])) | ((uint32_t)__half_as_ushort(__float2half_rn(v[2 * i + 1])) << 16);
+            else
+                w[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * i])) |
+                       ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * i + 1])) << 16);
+        }
+        *reinterpret_cast<uint4*>((char*)W + idx * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
 template <int DT, int OP>
@@ -194,9 +218,9 @@ int qt_smooth_scales(const float* amin, const float* amax, const float* wmin, co
 
 // in place: W[n][c] *= s[c] (divide != 0: /=), or by_row != 0: W[n][c] (op)= s[n]
 int qt_scale_matrix(void* W, int dtype, int N, int K, const float* s, int divide, int by_row, void* stream) {
-    if (!W || !s || N <= 0 || K <= 0 || N > 65535) return QT_ERR_INVALID;
+    if (!W || !s || N <= 0 || K <= 0 || N > 65535 || (K & 7) || ((uintptr_t)W & 15)) return QT_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((K + 255) / 256, N);
+    dim3 grid((K / 8 + 255) / 256, N);
 #define QT_SCALE(DT)                                                                                   \
     if (divide) { if (by_row) scale_kernel<DT, true, true><<<grid, 256, 0, st>>>(W, s, N, K);          \
                   else scale_kernel<DT, true, false><<<grid, 256, 0, st>>>(W, s, N, K); }              \
