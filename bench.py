@@ -110,39 +110,43 @@ def synth_acts(T, K, device, seed):
 # ------------------------------------------------------------------------------------------
 def cpu_reference_sample(shape, level, actorder, n_samples, seq, threads=None):
     """Times the CPU oracle (torch CPU fp32, all host threads) on a bounded sample of the same
-    workload and extrapolates to the whole model by the work ratios stated in `sample`."""
+    workload - one Linear and a few calibration samples per distinct input width - and extrapolates
+    to the whole model by the work ratios stated in `sample` (about 20-30 s of CPU work)."""
     from oracle import gptq as og
     from compressed_tensors.quantization import ActivationOrdering
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    K, N = shape.hidden_size, shape.q_dim           # q_proj
-    g = torch.Generator().manual_seed(0)
-    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
-    nb = 8
-    x = torch.randn((nb, seq, K), generator=g).to(torch.bfloat16)
     args = og.scheme_weight_args(level)
     if actorder:
         args.actorder = ActivationOrdering.GROUP if actorder == "group" else ActivationOrdering.WEIGHT
-    H, n = og.make_empty_hessian(K), 0
-    t0 = time.perf_counter()
-    for b in range(nb):
-        H, n = og.accumulate_hessian(x[b:b + 1], H, n)
-    t_h = time.perf_counter() - t0                   # nb samples of K-wide Hessian
-    t0 = time.perf_counter()
-    og.quantize_weight(W, H, args)
-    t_q = time.perf_counter() - t0
-    # extrapolation by FLOP ratios: Hessian ~ samples * K^2 ; quantize_weight ~ (2/3... chain) K^3 + N K^2
+    g = torch.Generator().manual_seed(0)
     L = shape.num_hidden_layers
-    dims = shape.input_dims()
-    hess_units = sum((n_samples / nb) * (k / K) ** 2 for k in dims.values()) * L
-    q_work = lambda n_, k_: (4.0 / 3.0) * k_ ** 3 + n_ * k_ ** 2
-    quant_units = sum(q_work(n_, k_) for (n_, k_) in shape.linear_shapes().values()) / q_work(N, K) * L
-    total = t_h * hess_units + t_q * quant_units
-    sample = (f"oracle port (torch CPU fp32): Hessian of {nb}x{seq} tokens at K={K} ({t_h:.2f}s) + quantize_weight of "
-              f"q_proj [{N},{K}] ({t_q:.2f}s); extrapolated to {L} layers x 7 Linears x {n_samples} samples by "
-              f"FLOP ratios (samples*K^2 ; 4/3 K^3 + N K^2) - an extrapolation, not a full CPU run")
+    lin = shape.linear_shapes()
+    q_work = lambda n_, k_: (4.0 / 3.0) * k_ ** 3 + n_ * k_ ** 2       # chain + column loop FLOPs
+    total, parts, sample_s = 0.0, [], 0.0
+    for K, nb in sorted({(shape.hidden_size, 8), (shape.intermediate_size, 2)}):
+        N = shape.hidden_size
+        W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+        x = torch.randn((nb, seq, K), generator=g).to(torch.bfloat16)
+        H, n = og.make_empty_hessian(K), 0
+        t0 = time.perf_counter()
+        for b in range(nb):
+            H, n = og.accumulate_hessian(x[b:b + 1], H, n)
+        t_h = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        og.quantize_weight(W, H, args)
+        t_q = time.perf_counter() - t0
+        sample_s += t_h + t_q
+        n_inputs = sum(1 for k in shape.input_dims().values() if k == K)
+        hess = t_h * (n_samples / nb) * n_inputs
+        quant = sum(t_q * q_work(n_, k_) / q_work(N, K) for (n_, k_) in lin.values() if k_ == K)
+        total += L * (hess + quant)
+        parts.append(f"K={K}: Hessian of {nb}x{seq} tokens {t_h:.2f}s, quantize_weight [{N},{K}] {t_q:.2f}s")
+    sample = ("oracle port (torch CPU fp32, restated llm-compressor GPTQ): " + "; ".join(parts) +
+              f"; extrapolated to {L} layers x 7 Linears x {n_samples} samples (Hessian ~ samples, "
+              f"quantize_weight ~ 4/3 K^3 + N K^2 per Linear) - an extrapolation, not a full CPU run")
     return {"value": total, "unit": "s", "cores": threads, "kind": "port", "sample": sample,
-            "sample_seconds": t_h + t_q}
+            "sample_seconds": sample_s}
 
 
 def gguf_probe(device):

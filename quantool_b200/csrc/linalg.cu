@@ -324,6 +324,34 @@ __global__ void __launch_bounds__(256) set_identity_kernel(float* __restrict__ U
     if (j < K) U[(long long)i * K + j] = (i == j) ? 1.f : 0.f;
 }
 
+// Look-ahead resources: the diagonal-block kernel is a single latency-bound CTA (128 sequential
+// pivots), so it is issued on a second, high-priority stream as soon as the NEXT panel column has
+// received its trailing update, and runs underneath the rest of that update.
+struct LookAhead {
+    cudaStream_t side = nullptr;
+    cudaEvent_t panel_ready = nullptr, potrf_done = nullptr;
+    bool ok = false;
+};
+// one side stream per caller stream: chains that the host runs concurrently on different streams
+// must not serialise behind each other's look-ahead kernels
+static LookAhead& lookahead(cudaStream_t st) {
+    static thread_local struct { cudaStream_t key; LookAhead la; } table[16];
+    static thread_local int used = 0;
+    for (int i = 0; i < used; i++)
+        if (table[i].key == st) return table[i].la;
+    const int slot = used < 16 ? used++ : 15;
+    LookAhead& la = table[slot].la;
+    table[slot].key = st;
+    if (!la.side) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.panel_ready, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.potrf_done, cudaEventDisableTiming) == cudaSuccess;
+    }
+    return la;
+}
+
 static int cholesky_lower(float* A, float* X, int K, int* info, cudaStream_t st) {
     const size_t smem = (2 * NB * LDS_ + 64 * 65 + NB) * sizeof(float);
     static bool attr_set = false;
@@ -332,11 +360,18 @@ static int cholesky_lower(float* A, float* X, int K, int* info, cudaStream_t st)
         if (e != cudaSuccess) { set_last_error("potrf smem attr", e); return QT_ERR_CUDA; }
         attr_set = true;
     }
+    LookAhead& la = lookahead(st);
+    bool potrf_ahead = false;   // potrf of the current block was already issued on the side stream
     for (int k = 0; k < K; k += NB) {
         const int nb = (K - k) < NB ? (K - k) : NB;
-        potrf_inv_kernel<<<1, 256, smem, st>>>(A, X, K, nb, k, info);
-        int rc = check_launch("potrf_inv");
-        if (rc) return rc;
+        if (potrf_ahead) {
+            if (cudaStreamWaitEvent(st, la.potrf_done, 0) != cudaSuccess) return QT_ERR_CUDA;
+        } else {
+            potrf_inv_kernel<<<1, 256, smem, st>>>(A, X, K, nb, k, info);
+            int rc = check_launch("potrf_inv");
+            if (rc) return rc;
+        }
+        potrf_ahead = false;
         const int rem = K - k - nb;
         if (rem <= 0) break;
         float* P = A + (long long)(k + nb) * K + k;
@@ -344,14 +379,36 @@ static int cholesky_lower(float* A, float* X, int K, int* info, cudaStream_t st)
         t.A = P; t.B = X + (long long)k * K + k; t.C = P;
         t.M = rem; t.N = nb; t.Kd = nb; t.lda = t.ldb = t.ldc = K;
         t.alpha = 1.f; t.beta = 0.f;
-        rc = sgemm(true, t, 1, st);
+        int rc = sgemm(true, t, 1, st);
         if (rc) return rc;
-        GemmArgs s{};  // SYRK: A22 -= P P^T, lower tiles only
-        s.A = P; s.B = P; s.C = A + (long long)(k + nb) * K + (k + nb);
-        s.M = rem; s.N = rem; s.Kd = nb; s.lda = s.ldb = s.ldc = K;
-        s.alpha = -1.f; s.beta = 1.f; s.lower_tiles_only = 1;
-        rc = sgemm(true, s, 1, st);
+        // SYRK: A22 -= P P^T (lower tiles only), split into the next panel column and the rest
+        const int nb2 = rem < NB ? rem : NB;
+        GemmArgs s1{};
+        s1.A = P; s1.B = P; s1.C = A + (long long)(k + nb) * K + (k + nb);
+        s1.M = rem; s1.N = nb2; s1.Kd = nb; s1.lda = s1.ldb = s1.ldc = K;
+        s1.alpha = -1.f; s1.beta = 1.f; s1.lower_tiles_only = 1;
+        rc = sgemm(true, s1, 1, st);
         if (rc) return rc;
+        const int rem2 = rem - nb2;
+        if (la.ok && rem2 > 0) {
+            // next diagonal block is final: factor it on the side stream while the rest updates
+            if (cudaEventRecord(la.panel_ready, st) != cudaSuccess) return QT_ERR_CUDA;
+            if (cudaStreamWaitEvent(la.side, la.panel_ready, 0) != cudaSuccess) return QT_ERR_CUDA;
+            potrf_inv_kernel<<<1, 256, smem, la.side>>>(A, X, K, nb2, k + nb, info);
+            rc = check_launch("potrf_inv(look-ahead)");
+            if (rc) return rc;
+            if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
+            potrf_ahead = true;
+        }
+        if (rem2 > 0) {
+            float* P2 = P + (long long)nb2 * K;
+            GemmArgs s2{};
+            s2.A = P2; s2.B = P2; s2.C = A + (long long)(k + nb + nb2) * K + (k + nb + nb2);
+            s2.M = rem2; s2.N = rem2; s2.Kd = nb; s2.lda = s2.ldb = s2.ldc = K;
+            s2.alpha = -1.f; s2.beta = 1.f; s2.lower_tiles_only = 1;
+            rc = sgemm(true, s2, 1, st);
+            if (rc) return rc;
+        }
     }
     return QT_OK;
 }
