@@ -311,14 +311,73 @@ def _layer_weights(host_sd, pre: str, dev, res) -> Dict[str, torch.Tensor]:
     return w
 
 
+class _HostSink:
+    """Asynchronous D2H of artifact tensors into pinned host memory on a copy stream."""
+
+    def __init__(self, dev, res: "ModelQuantResult"):
+        self.dev = dev
+        self.res = res
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def put(self, key: str, t: torch.Tensor) -> None:
+        if not t.is_cuda:
+            self.res.tensors[key] = t
+            self.res.d2h_bytes += t.numel() * t.element_size()
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+        t.record_stream(self.stream)
+        self.res.tensors[key] = h
+        self.res.d2h_bytes += h.numel() * h.element_size()
+
+    def finish(self) -> None:
+        self.stream.synchronize()
+
+
+class _WeightPrefetcher:
+    """H2D of the next decoder layer's weights on a copy stream while the current layer computes."""
+
+    def __init__(self, host_sd, dev, res: "ModelQuantResult"):
+        self.host_sd, self.dev, self.res = host_sd, dev, res
+        self.stream = torch.cuda.Stream(device=dev)
+        self.next = None
+
+    def _issue(self, pre: str):
+        w = {}
+        with torch.cuda.stream(self.stream):
+            for k, v in self.host_sd.items():
+                if k.startswith(pre):
+                    w[k[len(pre):]] = v.clone() if v.device == self.dev else v.to(self.dev, non_blocking=True)
+                    self.res.h2d_bytes += v.numel() * v.element_size()
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return pre, w, ev
+
+    def get(self, pre: str, next_pre: Optional[str]):
+        if self.next is None or self.next[0] != pre:
+            self.next = self._issue(pre)
+        _, w, ev = self.next
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_event(ev)
+        for t in w.values():
+            t.record_stream(main)
+        self.next = self._issue(next_pre) if next_pre is not None else None
+        return w
+
+
 def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor], token_ids: torch.Tensor,
                         args: WeightArgs, device, fmt: str = "pack-quantized", percdamp: float = 0.01,
-                        chunk_samples: int = 8, smooth_strength: Optional[float] = None,
+                        chunk_samples: int = 16, smooth_strength: Optional[float] = None,
                         dist: Optional[Dist] = None, ignore=("lm_head",), progress=None) -> ModelQuantResult:
     """Host weights + host token ids -> host artifact tensors.  Everything between the H2D copy
-    of a layer's weights and the D2H copy of its packed tensors stays on the device.
-    `smooth_strength` not None runs the SmoothQuant pass on each layer first (reference recipe
-    [SmoothQuantModifier, GPTQModifier], ref/.../smoothquant/smoothquant.py:77-84)."""
+    of a layer's weights and the D2H copy of its packed tensors stays on the device; the copies
+    themselves run on side streams (next layer's weights in, finished artifacts out) underneath
+    the compute.  `smooth_strength` not None runs the SmoothQuant pass on each layer first
+    (reference recipe [SmoothQuantModifier, GPTQModifier], ref/.../smoothquant/smoothquant.py:77-84)."""
     from .gptq import compress_linear
     dist = dist or Dist()
     res = ModelQuantResult()
@@ -327,7 +386,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
     # sample sharding
     per = row_split(n_total, dist.world)
     s0 = sum(per[: dist.rank])
-    ids = token_ids[s0: s0 + per[dist.rank]].to(dev)
+    ids = token_ids[s0: s0 + per[dist.rank]].to(dev, non_blocking=True)
     res.h2d_bytes += ids.numel() * ids.element_size()
     n_local = ids.shape[0]
     emb = _to_dev(host_sd["model.embed_tokens.weight"], dev)
@@ -337,9 +396,14 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
     cos, sin = llama.rope_tables(shape, seq, dev, h.dtype)
     lq = GPTQLayerQuantizer(args, percdamp=percdamp, dist=dist)
     dims = shape.input_dims()
-    for l in range(shape.num_hidden_layers):
+    sink = _HostSink(dev, res)
+    fetch = _WeightPrefetcher(host_sd, dev, res)
+    losses = {}
+    L = shape.num_hidden_layers
+    chunk_samples = max(1, min(chunk_samples, n_local)) if n_local else 1
+    for l in range(L):
         pre = f"model.layers.{l}."
-        w = _layer_weights(host_sd, pre, dev, res)
+        w = fetch.get(pre, f"model.layers.{l + 1}." if l + 1 < L else None)
         if smooth_strength is not None:
             from .smoothquant import smooth_layer
             smooth_layer(shape, w, h, cos, sin, smooth_strength, chunk_samples, dist)
@@ -367,13 +431,11 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
             lq.launches += 2
             if dist.rank == 0:
                 for k, t in art.items():
-                    th = t.cpu() if t.is_cuda else t
-                    res.tensors[f"{pre}{lin}.{k}"] = th
-                    res.d2h_bytes += th.numel() * th.element_size()
-                res.losses[f"{pre}{lin}"] = float(r.loss.item())
+                    sink.put(f"{pre}{lin}.{k}", t)
+                losses[f"{pre}{lin}"] = r.loss
         if dist.rank == 0:
             for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
-                res.tensors[pre + k] = w[k].cpu()
+                sink.put(pre + k, w[k])
         # pass 2: propagate through the quantized layer
         for c0 in range(0, n_local, chunk_samples):
             h[c0: c0 + chunk_samples] = llama.layer_forward(shape, w, h[c0: c0 + chunk_samples], cos, sin)
@@ -384,6 +446,11 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
         for k in ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight"):
             if k in host_sd:
                 res.tensors[k] = host_sd[k]
+        if losses:
+            vals = torch.stack([v.reshape(()) for v in losses.values()]).cpu().tolist()    # one sync for all losses
+            res.losses = dict(zip(losses.keys(), vals))
+    sink.finish()
+    torch.cuda.current_stream(dev).synchronize()
     res.launches = lq.launches
     return res
 
