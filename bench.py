@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gguf", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
-    ap.add_argument("--workload", default="gptq", choices=["gptq", "awq", "smoothquant"],
+    ap.add_argument("--workload", default="gptq", choices=["gptq", "awq", "smoothquant", "gguf"],
                     help="gptq = the headline line; awq / smoothquant = BASELINE configs 3 / 4 (extra lines)")
     return ap.parse_args()
 
@@ -173,6 +173,54 @@ def gguf_probe(device):
     return out
 
 
+def gguf_workload(a, dev):
+    """BASELINE config 1: GGUF Q8_0 and Q4_K_M of a random-init SmolLM2-135M-shaped Llama: every 2-D
+    tensor packed on the GPU (HBM-resident fp16 in, packed bytes out) vs the C oracle with all host
+    threads on the same tensors; per-tensor types as llama-quantize would choose them."""
+    from quantool_b200 import cabi
+    from quantool_b200.engine import gguf_file, llama
+    from oracle import ggml_quants as oq
+    shape = llama.SHAPES["smollm2-135m"]
+    sd = llama.random_state_dict(shape, seed=0, device=dev)
+    tensors = []
+    for name, t in sd.items():
+        g = gguf_file.hf_to_gguf_name(name, shape.num_hidden_layers)
+        if g is not None and t.dim() == 2:
+            tensors.append((g, t.half().contiguous()))
+    out = {}
+    for ftype in ("Q8_0", "Q4_K_M"):
+        plan = [(x, gguf_file.tensor_type(g, tuple(x.shape), ftype, shape.num_hidden_layers, False)) for g, x in tensors]
+
+        def run():
+            return [cabi.gguf_quantize(x, qt) for x, qt in plan]
+        for _ in range(3):
+            ys = run()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ys = run(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        nelem = sum(x.numel() for x, _ in plan)
+        byts = sum(x.numel() * 2 for x, _ in plan) + sum(y.numel() for y in ys)
+        # CPU oracle on the same tensors (fp32 views of the fp16 weights), all host threads
+        host = [(x.float().cpu().numpy(), qt) for x, qt in plan]
+        t0 = time.perf_counter()
+        refs = [oq.quantize(xh, qt) for xh, qt in host]
+        cpu_s = time.perf_counter() - t0
+        exact = all((y.cpu().numpy() == r).all() for y, r in zip(ys, refs))
+        types = {}
+        for _, qt in plan:
+            types[qt] = types.get(qt, 0) + 1
+        out[ftype] = {"gpu_ms": round(ms, 3), "elements": nelem, "GBps": round(byts / ms / 1e6, 1),
+                      "cpu_oracle_s": round(cpu_s, 3), "cpu_threads": oq.get_threads(), "bit_exact_vs_oracle": bool(exact),
+                      "tensor_types": types}
+    print(json.dumps({"metric": "gguf_pack_smollm2_135m", "unit": "ms", "n_gpus": 1, "config":
+                      {"workload": "GGUF Q8_0 and Q4_K_M of random-init SmolLM2-135M shape (BASELINE config 1)"},
+                      "results": out}))
+
+
 def side_workload(a, shape, dev):
     """BASELINE configs 3 (AWQ W4A16 g128 n_grid=20, 128x512) and 4 (SmoothQuant alpha=0.5 scales + fold)
     on the random-init 8B shape, single GPU, device-resident inputs.  One JSON line each."""
@@ -291,6 +339,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if a.workload == "gguf":
+        return gguf_workload(a, dev)
     if a.workload != "gptq":
         return side_workload(a, shape, dev)
     if world > 1:

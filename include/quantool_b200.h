@@ -100,6 +100,13 @@ int qt_gptq_hinv_factor(float* A, float* X, float* W, int K, int* info, void* st
 int qt_set_identity(float* U, int K, void* stream);
 int qt_sgemm(int b_is_nk, const float* A, const float* B, float* C, int M, int N, int Kd, int lda, int ldb, int ldc,
              float alpha, float beta, int lower_tiles_only, int a_lower_tri, int b_lower_tri, void* stream);
+int qt_sgemm_ex(int b_is_nk, const float* A, const float* B, float* C, int M, int N, int Kd, int lda, int ldb, int ldc,
+                float alpha, float beta, int lower_tiles_only, int a_lower_tri, int b_lower_tri, int tri_row_offset,
+                void* stream);
+/* pieces of the multi-GPU inverse-factor chain: Cholesky + triangular inverse of an n x n block inside
+ * buffers of leading dimension ld (info accumulates), and U[i][j] = X[K-1-i][K-1-j] (upper) */
+int qt_tri_chain_block(float* A, float* X, float* W, int n, int ld, int* info, void* stream);
+int qt_flip_upper(const float* X, float* U, int K, void* stream);
 /* Wp[n][j] = float(W[n][perm[j]]) with dead columns zeroed; out[n][c] = cast(Wp[n][inv_perm[c]]) */
 int qt_gptq_permute_in(const void* W, int dtype, const int* perm, const uint8_t* dead, float* Wp, int N, int K,
                        void* stream);

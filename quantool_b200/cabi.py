@@ -41,6 +41,9 @@ _SIGS = {
     "qt_gptq_hinv_factor": [_vp, _vp, _vp, _i32, _vp, _vp],
     "qt_set_identity": [_vp, _i32, _vp],
     "qt_sgemm": [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _vp],
+    "qt_sgemm_ex": [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _vp],
+    "qt_tri_chain_block": [_vp, _vp, _vp, _i32, _i32, _vp, _vp],
+    "qt_flip_upper": [_vp, _vp, _i32, _vp],
     "qt_gptq_permute_in": [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp],
     "qt_gptq_permute_out": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "qt_fill_f32": [_vp, _i32, _f32, _vp],
@@ -274,14 +277,29 @@ def set_identity(U: torch.Tensor) -> None:
 
 
 def sgemm(A, B, C, alpha=1.0, beta=0.0, b_is_nk=False, lower_tiles_only=False, a_lower_tri=False,
-          b_lower_tri=False):
+          b_lower_tri=False, tri_row_offset=0):
+    """C = alpha * A @ (B^T if b_is_nk else B) + beta * C on fp32 views with unit inner stride (row
+    strides are the leading dimensions, so sub-blocks of larger buffers work in place)."""
     M, Kd = A.shape
     N = C.shape[1]
+    assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
     with torch.cuda.device(A.device):
-        _check(lib().qt_sgemm(int(b_is_nk), _p(A), _p(B), _p(C), M, N, Kd, A.stride(0), B.stride(0), C.stride(0),
-                              float(alpha), float(beta), int(lower_tiles_only), int(a_lower_tri), int(b_lower_tri),
-                              _stream()), "qt_sgemm")
+        _check(lib().qt_sgemm_ex(int(b_is_nk), _p(A), _p(B), _p(C), M, N, Kd, A.stride(0), B.stride(0), C.stride(0),
+                                 float(alpha), float(beta), int(lower_tiles_only), int(a_lower_tri), int(b_lower_tri),
+                                 int(tri_row_offset), _stream()), "qt_sgemm_ex")
     return C
+
+
+def tri_chain_block(A, X, W, n: int, info) -> None:
+    """Cholesky + triangular inverse of the leading n x n block of views A/X/W (same leading dimension)."""
+    assert A.stride(0) == X.stride(0) == W.stride(0) and A.stride(1) == 1
+    with torch.cuda.device(A.device):
+        _check(lib().qt_tri_chain_block(_p(A), _p(X), _p(W), n, A.stride(0), _p(info), _stream()), "qt_tri_chain_block")
+
+
+def flip_upper(X, U) -> None:
+    with torch.cuda.device(X.device):
+        _check(lib().qt_flip_upper(_p(X), _p(U), X.shape[0], _stream()), "qt_flip_upper")
 
 
 def gptq_permute_in(w: torch.Tensor, perm: Optional[torch.Tensor], dead: Optional[torch.Tensor]) -> torch.Tensor:

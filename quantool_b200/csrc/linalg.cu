@@ -352,7 +352,7 @@ static LookAhead& lookahead(cudaStream_t st) {
     return la;
 }
 
-static int cholesky_lower(float* A, float* X, int K, int* info, cudaStream_t st) {
+static int cholesky_lower(float* A, float* X, int K, int ld, int* info, cudaStream_t st) {
     const size_t smem = (2 * NB * LDS_ + 64 * 65 + NB) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -367,25 +367,25 @@ static int cholesky_lower(float* A, float* X, int K, int* info, cudaStream_t st)
         if (potrf_ahead) {
             if (cudaStreamWaitEvent(st, la.potrf_done, 0) != cudaSuccess) return QT_ERR_CUDA;
         } else {
-            potrf_inv_kernel<<<1, 256, smem, st>>>(A, X, K, nb, k, info);
+            potrf_inv_kernel<<<1, 256, smem, st>>>(A, X, ld, nb, k, info);
             int rc = check_launch("potrf_inv");
             if (rc) return rc;
         }
         potrf_ahead = false;
         const int rem = K - k - nb;
         if (rem <= 0) break;
-        float* P = A + (long long)(k + nb) * K + k;
+        float* P = A + (long long)(k + nb) * ld + k;
         GemmArgs t{};  // TRSM as GEMM: P <- P * (L_kk^-1)^T, in place (single column tile)
-        t.A = P; t.B = X + (long long)k * K + k; t.C = P;
-        t.M = rem; t.N = nb; t.Kd = nb; t.lda = t.ldb = t.ldc = K;
+        t.A = P; t.B = X + (long long)k * ld + k; t.C = P;
+        t.M = rem; t.N = nb; t.Kd = nb; t.lda = t.ldb = t.ldc = ld;
         t.alpha = 1.f; t.beta = 0.f;
         int rc = sgemm(true, t, 1, st);
         if (rc) return rc;
         // SYRK: A22 -= P P^T (lower tiles only), split into the next panel column and the rest
         const int nb2 = rem < NB ? rem : NB;
         GemmArgs s1{};
-        s1.A = P; s1.B = P; s1.C = A + (long long)(k + nb) * K + (k + nb);
-        s1.M = rem; s1.N = nb2; s1.Kd = nb; s1.lda = s1.ldb = s1.ldc = K;
+        s1.A = P; s1.B = P; s1.C = A + (long long)(k + nb) * ld + (k + nb);
+        s1.M = rem; s1.N = nb2; s1.Kd = nb; s1.lda = s1.ldb = s1.ldc = ld;
         s1.alpha = -1.f; s1.beta = 1.f; s1.lower_tiles_only = 1;
         rc = sgemm(true, s1, 1, st);
         if (rc) return rc;
@@ -394,17 +394,17 @@ static int cholesky_lower(float* A, float* X, int K, int* info, cudaStream_t st)
             // next diagonal block is final: factor it on the side stream while the rest updates
             if (cudaEventRecord(la.panel_ready, st) != cudaSuccess) return QT_ERR_CUDA;
             if (cudaStreamWaitEvent(la.side, la.panel_ready, 0) != cudaSuccess) return QT_ERR_CUDA;
-            potrf_inv_kernel<<<1, 256, smem, la.side>>>(A, X, K, nb2, k + nb, info);
+            potrf_inv_kernel<<<1, 256, smem, la.side>>>(A, X, ld, nb2, k + nb, info);
             rc = check_launch("potrf_inv(look-ahead)");
             if (rc) return rc;
             if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
             potrf_ahead = true;
         }
         if (rem2 > 0) {
-            float* P2 = P + (long long)nb2 * K;
+            float* P2 = P + (long long)nb2 * ld;
             GemmArgs s2{};
-            s2.A = P2; s2.B = P2; s2.C = A + (long long)(k + nb + nb2) * K + (k + nb + nb2);
-            s2.M = rem2; s2.N = rem2; s2.Kd = nb; s2.lda = s2.ldb = s2.ldc = K;
+            s2.A = P2; s2.B = P2; s2.C = A + (long long)(k + nb + nb2) * ld + (k + nb + nb2);
+            s2.M = rem2; s2.N = rem2; s2.Kd = nb; s2.lda = s2.ldb = s2.ldc = ld;
             s2.alpha = -1.f; s2.beta = 1.f; s2.lower_tiles_only = 1;
             rc = sgemm(true, s2, 1, st);
             if (rc) return rc;
@@ -416,7 +416,7 @@ static int cholesky_lower(float* A, float* X, int K, int* info, cudaStream_t st)
 // X holds the inverses of the NB x NB diagonal blocks of L.  Merge pairs of blocks level by
 // level:  inv([[A,0],[C,B]]) = [[A^-1,0],[-B^-1 C A^-1, B^-1]].  All pairs of one level run as
 // one batched GEMM (+ one more launch for a ragged last pair).
-static int trtri_lower(const float* L, float* X, float* W, int K, cudaStream_t st) {
+static int trtri_lower(const float* L, float* X, float* W, int K, int ld, cudaStream_t st) {
     for (long long s = NB; s < K; s *= 2) {
         const long long nblk = (K + s - 1) / s;
         const long long npairs = nblk / 2;  // pairs whose B block exists
@@ -431,17 +431,17 @@ static int trtri_lower(const float* L, float* X, float* W, int K, cudaStream_t s
             const long long p0 = pass == 0 ? 0 : nfull;
             const long long sB = pass == 0 ? s : lastSB;
             const long long a0 = 2 * p0 * s, b0 = a0 + s;
-            const long long stride = 2 * s * ((long long)K + 1);
+            const long long stride = 2 * s * ((long long)ld + 1);
             GemmArgs g1{};  // T = C * A^-1   (A^-1 lower-triangular as the [k][n] operand)
-            g1.A = L + b0 * K + a0; g1.B = X + a0 * K + a0; g1.C = W + b0 * K + a0;
-            g1.M = (int)sB; g1.N = (int)s; g1.Kd = (int)s; g1.lda = g1.ldb = g1.ldc = K;
+            g1.A = L + b0 * ld + a0; g1.B = X + a0 * ld + a0; g1.C = W + b0 * ld + a0;
+            g1.M = (int)sB; g1.N = (int)s; g1.Kd = (int)s; g1.lda = g1.ldb = g1.ldc = ld;
             g1.alpha = 1.f; g1.beta = 0.f; g1.b_lower_tri = 1;
             g1.strideA = g1.strideB = g1.strideC = stride;
             int rc = sgemm(false, g1, (int)batch, st);
             if (rc) return rc;
             GemmArgs g2{};  // X[C] = -B^-1 * T   (B^-1 lower-triangular as the [m][k] operand)
-            g2.A = X + b0 * K + b0; g2.B = W + b0 * K + a0; g2.C = X + b0 * K + a0;
-            g2.M = (int)sB; g2.N = (int)s; g2.Kd = (int)sB; g2.lda = g2.ldb = g2.ldc = K;
+            g2.A = X + b0 * ld + b0; g2.B = W + b0 * ld + a0; g2.C = X + b0 * ld + a0;
+            g2.M = (int)sB; g2.N = (int)s; g2.Kd = (int)sB; g2.lda = g2.ldb = g2.ldc = ld;
             g2.alpha = -1.f; g2.beta = 0.f; g2.a_lower_tri = 1;
             g2.strideA = g2.strideB = g2.strideC = stride;
             rc = sgemm(false, g2, (int)batch, st);
@@ -458,6 +458,10 @@ using namespace qt;
 using namespace qt::linalg;
 
 extern "C" {
+
+int qt_sgemm_ex(int b_is_nk, const float* A, const float* B, float* C, int M, int N, int Kd, int lda, int ldb, int ldc,
+                float alpha, float beta, int lower_tiles_only, int a_lower_tri, int b_lower_tri, int tri_row_offset,
+                void* stream);
 
 int qt_gptq_prepare_hessian(const float* H, const int* perm, int K, float percdamp, float* Hf, uint8_t* dead,
                             float* damp_scratch, void* stream) {
@@ -477,12 +481,31 @@ int qt_gptq_hinv_factor(float* A, float* X, float* W, int K, int* info, void* st
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
     if (e != cudaSuccess) { set_last_error("memset info", e); return QT_ERR_CUDA; }
-    int rc = cholesky_lower(A, X, K, info, st);
+    int rc = cholesky_lower(A, X, K, K, info, st);
     if (rc) return rc;
-    rc = trtri_lower(A, X, W, K, st);
+    rc = trtri_lower(A, X, W, K, K, st);
     if (rc) return rc;
     dim3 grid((K + 255) / 256, K);
     flip_upper_kernel<<<grid, 256, 0, st>>>(X, A, K);
+    return check_launch("flip_upper");
+}
+
+// Building blocks of the multi-GPU chain (engine/pipeline.py): Cholesky + triangular inverse of an n x n
+// block living inside larger buffers of leading dimension ld (A: in lower(H block) -> out L; X: out L^-1;
+// W: scratch), and the final index reversal.  info is accumulated (first failure wins), not reset.
+int qt_tri_chain_block(float* A, float* X, float* W, int n, int ld, int* info, void* stream) {
+    if (!A || !X || !W || !info || n <= 0 || (n & 3) || (ld & 3) || ld < n) return QT_ERR_INVALID;
+    if (((uintptr_t)A & 15) || ((uintptr_t)X & 15) || ((uintptr_t)W & 15)) return QT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cholesky_lower(A, X, n, ld, info, st);
+    if (rc) return rc;
+    return trtri_lower(A, X, W, n, ld, st);
+}
+
+int qt_flip_upper(const float* X, float* U, int K, void* stream) {
+    if (!X || !U || K <= 0) return QT_ERR_INVALID;
+    dim3 grid((K + 255) / 256, K);
+    flip_upper_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, U, K);
     return check_launch("flip_upper");
 }
 
@@ -496,7 +519,17 @@ int qt_set_identity(float* U, int K, void* stream) {
 // exposed for tests and for the bench's roofline probe of the fp32 GEMM
 int qt_sgemm(int b_is_nk, const float* A, const float* B, float* C, int M, int N, int Kd, int lda, int ldb, int ldc,
              float alpha, float beta, int lower_tiles_only, int a_lower_tri, int b_lower_tri, void* stream) {
+    return qt_sgemm_ex(b_is_nk, A, B, C, M, N, Kd, lda, ldb, ldc, alpha, beta, lower_tiles_only, a_lower_tri, b_lower_tri,
+                       0, stream);
+}
+
+// tri_row_offset: the M rows of this call start at that row of the triangular structure (row-sliced SYRK /
+// triangular-A products on one rank of a multi-GPU split)
+int qt_sgemm_ex(int b_is_nk, const float* A, const float* B, float* C, int M, int N, int Kd, int lda, int ldb, int ldc,
+                float alpha, float beta, int lower_tiles_only, int a_lower_tri, int b_lower_tri, int tri_row_offset,
+                void* stream) {
     GemmArgs g{};
+    g.tri_row_offset = tri_row_offset;
     g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.Kd = Kd; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
     g.alpha = alpha; g.beta = beta;
     g.lower_tiles_only = lower_tiles_only; g.a_lower_tri = a_lower_tri; g.b_lower_tri = b_lower_tri;

@@ -26,6 +26,7 @@ struct GemmArgs {
     int lower_tiles_only;  // 1: skip tiles entirely above the diagonal (SYRK into a lower triangle)
     int a_lower_tri;       // 1: A[m][k] == 0 for k > m  -> k range ends at the tile's last row
     int b_lower_tri;       // 1: B[k][n] == 0 for k < n  -> k range starts at the tile's first col
+    int tri_row_offset;    // rows of this call start at this row of the triangular structure (row slices)
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 16;
@@ -37,13 +38,13 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g) {
     __shared__ __align__(16) float Bs[2][GBK][GLD];
 
     const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-    if (g.lower_tiles_only && n0 > m0 + GBM - 1) return;
+    if (g.lower_tiles_only && n0 > m0 + g.tri_row_offset + GBM - 1) return;
     const float* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
     const float* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
     float* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
 
     int k_begin = 0, k_end = g.Kd;
-    if (g.a_lower_tri) { const int e = m0 + GBM; k_end = e < k_end ? e : k_end; }
+    if (g.a_lower_tri) { const int e = m0 + g.tri_row_offset + GBM; k_end = e < k_end ? e : k_end; }
     if (g.b_lower_tri) { k_begin = (n0 / GBK) * GBK; }
 
     const int tid = threadIdx.x;

@@ -156,6 +156,104 @@ class GPTQLayerQuantizer:
         ctx.slot = slot
         return ctx
 
+    # ---- inverse-Hessian factor of ONE input computed by ALL ranks ---------------------------
+    DIST_CHAIN_MIN_K = 8192
+
+    def _bcast_view(self, view: torch.Tensor, src: int) -> None:
+        """Broadcast a strided 2-D block (sub-matrix of a K x K buffer) from `src` into the same view."""
+        d = self.dist
+        tmp = view.contiguous() if d.rank == src else torch.empty(view.shape, dtype=view.dtype, device=view.device)
+        d.broadcast(tmp, src)
+        if d.rank != src:
+            view.copy_(tmp)
+
+    @staticmethod
+    def _area_bounds(n: int, parts: int, grow: bool) -> List[int]:
+        """Split [0, n) in `parts` 128-aligned ranges of equal triangular area: work per row grows with the
+        row index (grow=True, lower-triangular rows) or shrinks with the column index (grow=False)."""
+        import math
+        b = [0]
+        for i in range(1, parts):
+            f = math.sqrt(i / parts) if grow else 1.0 - math.sqrt(1.0 - i / parts)
+            b.append(min(n, max(b[-1], int(round(n * f / 128.0)) * 128)))
+        b.append(n)
+        return b
+
+    def prepare_input_distributed(self, H: torch.Tensor, slot: str = "") -> InputContext:
+        """2 x 2 block form of the chain, shared by all ranks (SURVEY.md §8e "Cholesky / Hinv"):
+            Lf = [[L11, 0], [L21, L22]],  X = Lf^-1 = [[X11, 0], [-X22 L21 X11, X22]]
+        The two half-size chains (L11,X11 then L22,X22) run on rank 0 and are broadcast; the three large
+        GEMM stages between and after them - L21 = Hf21 X11^T, the Schur complement Hf22 - L21 L21^T and
+        X21 = -X22 (L21 X11), 3/4 of all flops - are split across ranks (row / column ranges of equal
+        triangular area) and re-assembled with broadcasts of each rank's slab.  Every rank ends with the
+        full X and flips it to U locally, so U itself is never broadcast."""
+        d = self.dist
+        K = H.shape[0]
+        dev = H.device
+        perm = inv_perm = None
+        if self.args.actorder in ("group", "weight"):
+            perm = torch.argsort(torch.diagonal(H), descending=True, stable=True).to(torch.int32)
+            inv_perm = torch.argsort(perm).to(torch.int32)
+        A = self._buf("U" + slot, (K, K), torch.float32, dev)
+        X = self._buf("X" + slot, (K, K), torch.float32, dev)
+        W = self._buf("W" + slot, (K, K), torch.float32, dev)
+        info = torch.zeros((1,), dtype=torch.int32, device=dev)
+        dead = torch.empty((K,), dtype=torch.uint8, device=dev)
+        damp = self._buf("damp" + slot, (1,), torch.float32, dev)
+        cabi._check(cabi.lib().qt_gptq_prepare_hessian(cabi._p(H), cabi._p(perm), K, float(self.percdamp), cabi._p(A),
+                                                       cabi._p(dead), cabi._p(damp), cabi._stream()),
+                    "qt_gptq_prepare_hessian")          # identical on every rank (H is all-reduced)
+        n1 = (K // 256) * 128
+        n2 = K - n1
+        G, r = d.world, d.rank
+        X.zero_()
+        # 1. first half on rank 0
+        if r == 0:
+            cabi.tri_chain_block(A, X, W, n1, info)
+        self._bcast_view(X[:n1, :n1], 0)
+        # 2. L21 = Hf21 * X11^T, rows split evenly; result assembled into A[n1:, :n1] everywhere
+        rb = [min(n2, ((n2 * i // G) // 128) * 128) for i in range(G)] + [n2]
+        a, b = rb[r], rb[r + 1]
+        if b > a:
+            cabi.sgemm(A[n1 + a:n1 + b, :n1], X[:n1, :n1], W[n1 + a:n1 + b, :n1], b_is_nk=True)
+        for g in range(G):
+            ga, gb = rb[g], rb[g + 1]
+            if gb > ga:
+                if g == r:
+                    A[n1 + ga:n1 + gb, :n1].copy_(W[n1 + ga:n1 + gb, :n1])
+                self._bcast_view(A[n1 + ga:n1 + gb, :n1], g)
+        # 3. Schur complement (lower tiles): rows split by equal triangular area
+        sb = self._area_bounds(n2, G, grow=True)
+        a, b = sb[r], sb[r + 1]
+        if b > a:
+            cabi.sgemm(A[n1 + a:n1 + b, :n1], A[n1:n1 + b, :n1], A[n1 + a:n1 + b, n1:n1 + b], alpha=-1.0, beta=1.0,
+                       b_is_nk=True, lower_tiles_only=True, tri_row_offset=a)
+        for g in range(G):
+            ga, gb = sb[g], sb[g + 1]
+            if gb > ga:
+                self._bcast_view(A[n1 + ga:n1 + gb, n1:n1 + gb], g)
+        # 4. second half on rank 0
+        if r == 0:
+            cabi.tri_chain_block(A[n1:, n1:], X[n1:, n1:], W[n1:, n1:], n2, info)
+        self._bcast_view(X[n1:, n1:], 0)
+        d.broadcast(info, 0)
+        # 5. X21 = -X22 * (L21 * X11): column ranges of equal work (X11 is lower-triangular)
+        cb = self._area_bounds(n1, G, grow=False)
+        a, b = cb[r], cb[r + 1]
+        if b > a:
+            cabi.sgemm(A[n1:, a:n1], X[a:n1, a:b], W[n1:, a:b], b_lower_tri=True)           # T = L21 X11[:, a:b]
+            cabi.sgemm(X[n1:, n1:], W[n1:, a:b], X[n1:, a:b], alpha=-1.0, a_lower_tri=True)  # X21 = -X22 T
+        for g in range(G):
+            ga, gb = cb[g], cb[g + 1]
+            if gb > ga:
+                self._bcast_view(X[n1:, ga:gb], g)
+        # 6. U = flip(X), locally
+        cabi.flip_upper(X, A)
+        self.launches += 8
+        ctx = InputContext(K, perm, inv_perm, A, dead, info)
+        ctx.slot = slot
+        return ctx
+
     def split_for_tensor_cores(self, ctx: InputContext) -> None:
         """U^T as tf32 hi/lo parts (reuses the chain's scratch buffers); call after any identity fallback."""
         if ctx.K <= 128:
@@ -246,7 +344,10 @@ class GPTQLayerQuantizer:
                 st = self._streams[idx] = torch.cuda.Stream(device=dev)
             st.wait_event(ready)
             with torch.cuda.stream(st):
-                ctx = self.prepare_input(hessians[inp], owner=idx, slot=f"#{idx}")
+                if self.dist.on and hessians[inp].shape[0] >= self.DIST_CHAIN_MIN_K:
+                    ctx = self.prepare_input_distributed(hessians[inp], slot=f"#{idx}")
+                else:
+                    ctx = self.prepare_input(hessians[inp], owner=idx, slot=f"#{idx}")
                 self.split_for_tensor_cores(ctx)
                 for lin in linears:
                     if input_of[lin] == inp:
