@@ -6,7 +6,7 @@
 //   B_NK = false : B is [Kd, N] (n contiguous)          "NN"
 //   B_NK = true  : B is [N, Kd] (k contiguous)          "NT"  (C += A * B^T)
 //
-// 128x128x16 CTA tile, 256 threads, 8x8 register micro-tile (two 4-wide halves per
+// 128x128x16 CTA tile, 256 threads, 8x8 register micro-tile of packed f32x2 FMAs (two 4-wide halves per
 // dimension so every shared-memory read is a conflict-free LDS.128), global->register
 // prefetch of the next k-slab overlapped with the FMAs of the current one, two shared
 // buffers, one __syncthreads per slab.  Triangular structure is skipped at tile granularity.
@@ -102,11 +102,15 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g) {
         }
     };
 
-    float acc[8][8];
+    // accumulators as packed fp32 pairs (acc2[i][jp] = {acc[i][2jp], acc[i][2jp+1]}): Blackwell's
+    // fma.rn.f32x2 (SASS FFMA2) retires two FMAs per issue slot, and this kernel is issue-bound on
+    // plain FFMA: 44.6 -> 49-52 TFLOP/s at 8192^3.  (Keeping A pre-duplicated in shared memory to
+    // drop the {a,a} register moves was slower - 43 TFLOP/s - the extra LDS cost more than the moves.)
+    unsigned long long acc2[8][4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; j++) acc2[i][j] = 0ull;
 
     const int nslab = (k_end - k_begin + GBK - 1) / GBK;
     if (nslab > 0) {
@@ -123,11 +127,19 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g) {
                 const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
                 const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
                 const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                unsigned long long bp[4];
+                asm("mov.b64 %0, {%1, %2};" : "=l"(bp[0]) : "f"(b0.x), "f"(b0.y));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(bp[1]) : "f"(b0.z), "f"(b0.w));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(bp[2]) : "f"(b1.x), "f"(b1.y));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(bp[3]) : "f"(b1.z), "f"(b1.w));
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int i = 0; i < 8; i++) {
+                    unsigned long long ap;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(ap) : "f"(a[i]));
 #pragma unroll
-                    for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < 4; j++)
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(ap), "l"(bp[j]));
+                }
             }
             if (s + 1 < nslab) {
                 store_slab(buf ^ 1);
@@ -149,7 +161,9 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g) {
                 if (n >= g.N) continue;  // N % 4 == 0 is enforced by the host wrapper
                 float* cp = C + (long long)m * g.ldc + n;
                 float4 o;
-                const float* v = &acc[4 * ih + i][4 * jh];
+                float v[4];
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(acc2[4 * ih + i][2 * jh]));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(acc2[4 * ih + i][2 * jh + 1]));
                 if (g.beta != 0.f) {
                     const float4 c = *reinterpret_cast<const float4*>(cp);
                     o.x = g.alpha * v[0] + g.beta * c.x; o.y = g.alpha * v[1] + g.beta * c.y;

@@ -14,3 +14,12 @@ for t in ("Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q4_K", "Q6_K"):
         a.record(); cabi.gguf_quantize(x, t, out=y); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     ms = sorted(ts)[len(ts)//2]; byts = x.numel()*2 + y.numel()
     print(f"{t}: {ms:.3f} ms  {byts/ms/1e6:.0f} GB/s  ({byts/ms/1e6/6533.5*100:.0f}% of measured HBM peak)")
+for t in ("Q8_0", "Q4_0", "Q5_0", "Q4_K", "Q6_K"):
+    y = cabi.gguf_quantize(x, t)
+    for _ in range(2): cabi.gguf_dequantize(y, t, k)
+    torch.cuda.synchronize(); ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); cabi.gguf_dequantize(y, t, k); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[len(ts)//2]; byts = x.numel()*4 + y.numel()
+    print(f"dequant {t}: {ms:.3f} ms  {byts/ms/1e6:.0f} GB/s  ({byts/ms/1e6/6533.5*100:.0f}% of measured HBM peak)")
