@@ -272,8 +272,9 @@ int qt_hessian_set_splits(int s) { g_force_splits = s; return QT_OK; }
 // H[K,K] (fp32, zero-initialised by the caller before the first batch) += X^T X over the upper
 // triangle tiles.  X: [T, K] bf16 row-major.  K % 8 == 0.
 int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* stream) {
-    if (!X || !H || T < 0 || K <= 0 || (K & 7)) return QT_ERR_INVALID;
-    if (T == 0) return QT_OK;
+    if (T < 0 || K <= 0 || (K & 7) || !H) return QT_ERR_INVALID;
+    if (T == 0) return QT_OK;     // an empty batch adds nothing (X may be a null pointer then)
+    if (!X) return QT_ERR_INVALID;
     if (((uintptr_t)X & 15) || ((uintptr_t)H & 15)) return QT_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     EncodeTiledFn enc = get_encode();

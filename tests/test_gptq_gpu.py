@@ -263,3 +263,50 @@ def test_gptq_tensor_core_path_vs_oracle(level, actorder, N, K):
     e_o = og.layer_error(W, Wq_o, x.float())
     e_c = og.layer_error(W, res.weight.cpu(), x.float())
     assert abs(e_c - e_o) <= 0.01 * e_o, (e_c, e_o)
+
+
+def test_dead_columns_and_identity_fallback_vs_oracle():
+    """Edge cases upstream handles explicitly: a calibration column that is always zero
+    (diag(H) == 0 -> H[d,d] = 1, W[:, d] = 0) and a Hessian whose factorisation fails (Hinv = I)."""
+    from quantool_b200 import cabi
+    from quantool_b200.engine import gptq as eg, schemes
+    from oracle import gptq as og
+    N, K = 64, 256
+    g = torch.Generator().manual_seed(3)
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    x = _acts(4 * K, K, seed=9)
+    x[:, 17] = 0
+    x[:, 200] = 0
+    oargs = og.scheme_weight_args("W4A16")
+    Ho, n = og.make_empty_hessian(K), 0
+    for xb in x.reshape(4, K, K):
+        Ho, n = og.accumulate_hessian(xb.unsqueeze(0), Ho, n)
+    assert Ho[17, 17] == 0 and Ho[200, 200] == 0
+    _, Wq_o, s_o, z_o, _ = og.quantize_weight(W, Ho, oargs)
+    args = schemes.resolve("W4A16")
+    res = eg.quantize_linear(W.cuda(), Ho.cuda(), args)
+    assert int(res.info.item()) == 0
+    assert torch.all(res.weight[:, 17] == 0) and torch.all(res.weight[:, 200] == 0)
+    codes_o, _, _ = og.compress_packed(Wq_o, s_o, None, None, oargs)
+    _, codes = eg.compress_linear(res.weight, res.scale, res.zero_point, None, args)
+    assert (codes.cpu() == codes_o).float().mean().item() >= 0.999
+    # not positive definite: upstream catches LinAlgError and uses Hinv = I (plain RTN with no feedback)
+    Hbad = -torch.eye(K)
+    _, Wq_b, s_b, _, _ = og.quantize_weight(W, Hbad.clone(), oargs)
+    res_b = eg.quantize_linear(W.cuda(), Hbad.cuda(), args)
+    assert int(res_b.info.item()) != 0
+    codes_ob, _, _ = og.compress_packed(Wq_b, s_b, None, None, oargs)
+    _, codes_b = eg.compress_linear(res_b.weight, res_b.scale, res_b.zero_point, None, args)
+    assert (codes_b.cpu() == codes_ob).float().mean().item() >= 0.999
+
+
+def test_hessian_empty_and_unaligned_errors():
+    from quantool_b200 import cabi
+    H = torch.zeros((64, 64), device="cuda")
+    cabi.hessian_accumulate(torch.empty((0, 64), device="cuda", dtype=torch.bfloat16), H)   # empty batch: no-op
+    assert float(H.abs().sum()) == 0.0
+    with pytest.raises(cabi.QtError):
+        cabi.hessian_accumulate(torch.zeros((8, 60), device="cuda", dtype=torch.bfloat16),
+                                torch.zeros((60, 60), device="cuda"))                        # K % 8 != 0
+    with pytest.raises(cabi.QtError):
+        cabi.hessian_accumulate(torch.zeros((8, 64), device="cuda"), H)                      # fp32 activations
