@@ -38,6 +38,8 @@ extern "C" {
 #define QT_GGML_Q5_0 6
 #define QT_GGML_Q5_1 7
 #define QT_GGML_Q8_0 8
+#define QT_GGML_Q2_K 10
+#define QT_GGML_Q3_K 11
 #define QT_GGML_Q4_K 12
 #define QT_GGML_Q5_K 13
 #define QT_GGML_Q6_K 14

@@ -17,7 +17,7 @@
  *   - Q8_0 / Q4_0 / Q4_1 / Q5_0 / Q5_1 packed bytes == gguf-py `gguf.quants.quantize`
  *     (GGUFPY/quants.py:220-239, 291-311, 378-393; "bit-exact same results as reference
  *     implementation in ggml-quants.c") and the sha256 KATs in SURVEY.md §8c.
- *   - Q4_K / Q5_K / Q6_K: PARITY UNPINNED against llama.cpp itself (no quantize twin on
+ *   - Q2_K / Q3_K / Q4_K / Q5_K / Q6_K: PARITY UNPINNED against llama.cpp itself (no quantize twin on
  *     disk); pinned only by (a) an independent numpy restatement (oracle/ggml_quants_np.py)
  *     agreeing byte-for-byte and (b) gguf-py's dequantizers (GGUFPY/quants.py:475-572)
  *     reading the packed layout back to within the format's error.
@@ -106,6 +106,8 @@ typedef struct { uint16_t d; int8_t qs[32]; } block_q8_0;                  /* 34
 typedef struct { uint16_t d; uint16_t dmin; uint8_t scales[12]; uint8_t qs[128]; } block_q4_K; /* 144 B */
 typedef struct { uint16_t d; uint16_t dmin; uint8_t scales[12]; uint8_t qh[32]; uint8_t qs[128]; } block_q5_K; /* 176 B */
 typedef struct { uint8_t ql[128]; uint8_t qh[64]; int8_t scales[16]; uint16_t d; } block_q6_K; /* 210 B */
+typedef struct { uint8_t scales[16]; uint8_t qs[64]; uint16_t d; uint16_t dmin; } block_q2_K; /* 84 B */
+typedef struct { uint8_t hmask[32]; uint8_t qs[64]; uint8_t scales[12]; uint16_t d; } block_q3_K; /* 110 B */
 #pragma pack(pop)
 
 /* ---- D.1 Q8_0 ------------------------------------------------------------------- */
@@ -225,9 +227,10 @@ static void row_q5_1(const float *x, block_q5_1 *y, int64_t k) {
     }
 }
 
-/* ---- D.4 make_qkx2_quants (shared by Q4_K / Q5_K) ------------------------------- */
+/* ---- D.4 make_qkx2_quants (shared by Q2_K / Q4_K / Q5_K) ------------------------------- */
 static float make_qkx2_quants(int n, int nmax, const float *x, const float *weights, uint8_t *L,
-                              float *the_min, uint8_t *Laux, float rmin, float rdelta, int nstep) {
+                              float *the_min, uint8_t *Laux, float rmin, float rdelta, int nstep,
+                              int use_mad) {
     float min = x[0];
     float max = x[0];
     float sum_w = weights[0];
@@ -252,7 +255,7 @@ static float make_qkx2_quants(int n, int nmax, const float *x, const float *weig
         int l = nearest_int(iscale * (x[i] - min));
         L[i] = (uint8_t)MAXI(0, MINI(nmax, l));
         float diff = scale * L[i] + min - x[i];
-        diff = diff * diff;
+        diff = use_mad ? fabsf(diff) : diff * diff;
         float w = weights[i];
         best_error += w * diff;
     }
@@ -283,7 +286,7 @@ static float make_qkx2_quants(int n, int nmax, const float *x, const float *weig
             float cur_error = 0;
             for (int i = 0; i < n; ++i) {
                 float diff = this_scale * Laux[i] + this_min - x[i];
-                diff = diff * diff;
+                diff = use_mad ? fabsf(diff) : diff * diff;
                 float w = weights[i];
                 cur_error += w * diff;
             }
@@ -324,7 +327,7 @@ static void k45_scales(const float *x, int nmax, float rmin, float rdelta, int n
         float av_x = sqrtf(sum_x2 / 32);
         for (int l = 0; l < 32; ++l) weights[l] = av_x + fabsf(x[32 * j + l]);
         scales[j] = make_qkx2_quants(32, nmax, x + 32 * j, weights, L + 32 * j, &mins[j], Laux, rmin,
-                                     rdelta, nstep);
+                                     rdelta, nstep, 0);
         float scale = scales[j];
         if (scale > max_scale) max_scale = scale;
         float min = mins[j];
@@ -397,6 +400,187 @@ static void row_q5_K(const float *x, block_q5_K *y, int64_t k) {
             m1 <<= 2;
             m2 <<= 2;
             ql += 32;
+        }
+        x += QK_K;
+    }
+}
+
+/* ---- Q2_K: 16 sub-blocks x 16, 2-bit codes, 4-bit scale + 4-bit min per sub-block -------------
+ * llama.cpp quantize_row_q2_K_ref: make_qkx2_quants(16, 3, x, |x|, .., -0.5, 0.1, 15, use_mad=true). */
+static void row_q2_K(const float *x, block_q2_K *y, int64_t k) {
+    const int64_t nb = k / QK_K;
+    uint8_t L[QK_K];
+    uint8_t Laux[16];
+    float weights[16];
+    float mins[QK_K / 16];
+    float scales[QK_K / 16];
+    const float q4scale = 15.f;
+    for (int64_t i = 0; i < nb; i++) {
+        float max_scale = 0;
+        float max_min = 0;
+        for (int j = 0; j < QK_K / 16; ++j) {
+            for (int l = 0; l < 16; ++l) weights[l] = fabsf(x[16 * j + l]);
+            scales[j] = make_qkx2_quants(16, 3, x + 16 * j, weights, L + 16 * j, &mins[j], Laux, -0.5f, 0.1f, 15, 1);
+            float scale = scales[j];
+            if (scale > max_scale) max_scale = scale;
+            float min = mins[j];
+            if (min > max_min) max_min = min;
+        }
+        if (max_scale > 0) {
+            float iscale = q4scale / max_scale;
+            for (int j = 0; j < QK_K / 16; ++j) {
+                int l = nearest_int(iscale * scales[j]);
+                y[i].scales[j] = (uint8_t)l;
+            }
+            y[i].d = f32_to_f16(max_scale / q4scale);
+        } else {
+            for (int j = 0; j < QK_K / 16; ++j) y[i].scales[j] = 0;
+            y[i].d = f32_to_f16(0.f);
+        }
+        if (max_min > 0) {
+            float iscale = q4scale / max_min;
+            for (int j = 0; j < QK_K / 16; ++j) {
+                int l = nearest_int(iscale * mins[j]);
+                y[i].scales[j] |= (uint8_t)(l << 4);
+            }
+            y[i].dmin = f32_to_f16(max_min / q4scale);
+        } else {
+            y[i].dmin = f32_to_f16(0.f);
+        }
+        for (int j = 0; j < QK_K / 16; ++j) {
+            const float d = f16_to_f32(y[i].d) * (y[i].scales[j] & 0xF);
+            if (!d) continue;
+            const float dm = f16_to_f32(y[i].dmin) * (y[i].scales[j] >> 4);
+            for (int ii = 0; ii < 16; ++ii) {
+                int l = nearest_int((x[16 * j + ii] + dm) / d);
+                l = MAXI(0, MINI(3, l));
+                L[16 * j + ii] = (uint8_t)l;
+            }
+        }
+        for (int j = 0; j < QK_K; j += 128) {
+            for (int l = 0; l < 32; ++l) {
+                y[i].qs[j / 4 + l] = (uint8_t)(L[j + l] | (L[j + l + 32] << 2) | (L[j + l + 64] << 4) | (L[j + l + 96] << 6));
+            }
+        }
+        x += QK_K;
+    }
+}
+
+/* ---- Q3_K: 16 sub-blocks x 16, 3-bit codes (2 low bits + high-bit mask), 6-bit signed scales ---
+ * llama.cpp make_q3_quants(n=16, nmax=4, do_rmse=true): greedy start at -nmax/max, then up to five
+ * sweeps of coordinate descent on the x^2-weighted fit. */
+static float make_q3_quants(int n, int nmax, const float *x, int8_t *L, int do_rmse) {
+    float max = 0;
+    float amax = 0;
+    for (int i = 0; i < n; ++i) {
+        float ax = fabsf(x[i]);
+        if (ax > amax) { amax = ax; max = x[i]; }
+    }
+    if (amax < GROUP_MAX_EPS) {
+        for (int i = 0; i < n; ++i) L[i] = 0;
+        return 0.f;
+    }
+    float iscale = -nmax / max;
+    if (do_rmse) {
+        float sumlx = 0;
+        float suml2 = 0;
+        for (int i = 0; i < n; ++i) {
+            int l = nearest_int(iscale * x[i]);
+            l = MAXI(-nmax, MINI(nmax - 1, l));
+            L[i] = (int8_t)l;
+            float w = x[i] * x[i];
+            sumlx += w * x[i] * l;
+            suml2 += w * l * l;
+        }
+        for (int itry = 0; itry < 5; ++itry) {
+            int n_changed = 0;
+            for (int i = 0; i < n; ++i) {
+                float w = x[i] * x[i];
+                float slx = sumlx - w * x[i] * L[i];
+                if (slx > 0) {
+                    float sl2 = suml2 - w * L[i] * L[i];
+                    int new_l = nearest_int(x[i] * sl2 / slx);
+                    new_l = MAXI(-nmax, MINI(nmax - 1, new_l));
+                    if (new_l != L[i]) {
+                        slx += w * x[i] * new_l;
+                        sl2 += w * new_l * new_l;
+                        if (sl2 > 0 && slx * slx * suml2 > sumlx * sumlx * sl2) {
+                            L[i] = (int8_t)new_l; sumlx = slx; suml2 = sl2;
+                            ++n_changed;
+                        }
+                    }
+                }
+            }
+            if (!n_changed) break;
+        }
+        for (int i = 0; i < n; ++i) L[i] += nmax;
+        return sumlx / suml2;
+    }
+    for (int i = 0; i < n; ++i) {
+        int l = nearest_int(iscale * x[i]);
+        l = MAXI(-nmax, MINI(nmax - 1, l));
+        L[i] = (int8_t)(l + nmax);
+    }
+    return 1 / iscale;
+}
+
+static void row_q3_K(const float *x, block_q3_K *y, int64_t k) {
+    const int64_t nb = k / QK_K;
+    int8_t L[QK_K];
+    float scales[QK_K / 16];
+    for (int64_t i = 0; i < nb; i++) {
+        float max_scale = 0;
+        float amax = 0;
+        for (int j = 0; j < QK_K / 16; ++j) {
+            scales[j] = make_q3_quants(16, 4, x + 16 * j, L + 16 * j, 1);
+            float scale = fabsf(scales[j]);
+            if (scale > amax) { amax = scale; max_scale = scales[j]; }
+        }
+        memset(y[i].scales, 0, 12);
+        if (max_scale) {
+            float iscale = -32.f / max_scale;
+            for (int j = 0; j < QK_K / 16; ++j) {
+                int8_t l = (int8_t)nearest_int(iscale * scales[j]);
+                l = (int8_t)(MAXI(-32, MINI(31, l)) + 32);
+                if (j < 8) {
+                    y[i].scales[j] = l & 0xF;
+                } else {
+                    y[i].scales[j - 8] |= ((l & 0xF) << 4);
+                }
+                l >>= 4;
+                y[i].scales[j % 4 + 8] |= (l << (2 * (j / 4)));
+            }
+            y[i].d = f32_to_f16(1 / iscale);
+        } else {
+            y[i].d = f32_to_f16(0.f);
+        }
+        int8_t sc;
+        for (int j = 0; j < QK_K / 16; ++j) {
+            sc = j < 8 ? y[i].scales[j] & 0xF : y[i].scales[j - 8] >> 4;
+            sc = (int8_t)((sc | (((y[i].scales[8 + j % 4] >> (2 * (j / 4))) & 3) << 4)) - 32);
+            float d = f16_to_f32(y[i].d) * sc;
+            if (!d) continue;
+            for (int ii = 0; ii < 16; ++ii) {
+                int l = nearest_int(x[16 * j + ii] / d);
+                l = MAXI(-4, MINI(3, l));
+                L[16 * j + ii] = (int8_t)(l + 4);
+            }
+        }
+        memset(y[i].hmask, 0, QK_K / 8);
+        /* high bit of the first 32 codes -> bit 0 of hmask[0..31], the next 32 -> bit 1, ... */
+        int m = 0;
+        uint8_t hm = 1;
+        for (int j = 0; j < QK_K; ++j) {
+            if (L[j] > 3) {
+                y[i].hmask[m] |= hm;
+                L[j] -= 4;
+            }
+            if (++m == QK_K / 8) { m = 0; hm <<= 1; }
+        }
+        for (int j = 0; j < QK_K; j += 128) {
+            for (int l = 0; l < 32; ++l) {
+                y[i].qs[j / 4 + l] = (uint8_t)(L[j + l] | (L[j + l + 32] << 2) | (L[j + l + 64] << 4) | (L[j + l + 96] << 6));
+            }
         }
         x += QK_K;
     }
@@ -562,6 +746,60 @@ static void deq_q5_1(const block_q5_1 *x, float *y, int64_t k) {
         }
     }
 }
+static void deq_q2_K(const block_q2_K *x, float *y, int64_t k) {
+    const int64_t nb = k / QK_K;
+    for (int64_t i = 0; i < nb; i++) {
+        const float d = f16_to_f32(x[i].d);
+        const float min = f16_to_f32(x[i].dmin);
+        const uint8_t *q = x[i].qs;
+        int is = 0;
+        for (int n = 0; n < QK_K; n += 128) {
+            int shift = 0;
+            for (int j = 0; j < 4; ++j) {
+                uint8_t sc = x[i].scales[is++];
+                float dl = d * (sc & 0xF), ml = min * (sc >> 4);
+                for (int l = 0; l < 16; ++l) *y++ = dl * ((int8_t)((q[l] >> shift) & 3)) - ml;
+                sc = x[i].scales[is++];
+                dl = d * (sc & 0xF); ml = min * (sc >> 4);
+                for (int l = 0; l < 16; ++l) *y++ = dl * ((int8_t)((q[l + 16] >> shift) & 3)) - ml;
+                shift += 2;
+            }
+            q += 32;
+        }
+    }
+}
+
+static void deq_q3_K(const block_q3_K *x, float *y, int64_t k) {
+    const int64_t nb = k / QK_K;
+    for (int64_t i = 0; i < nb; i++) {
+        const float d_all = f16_to_f32(x[i].d);
+        const uint8_t *q = x[i].qs;
+        const uint8_t *hm = x[i].hmask;
+        uint8_t m = 1;
+        int8_t scales[16];
+        for (int j = 0; j < 16; ++j) {
+            int lo = j < 8 ? x[i].scales[j] & 0xF : x[i].scales[j - 8] >> 4;
+            int hi = (x[i].scales[8 + j % 4] >> (2 * (j / 4))) & 3;
+            scales[j] = (int8_t)((lo | (hi << 4)) - 32);
+        }
+        int is = 0;
+        for (int n = 0; n < QK_K; n += 128) {
+            int shift = 0;
+            for (int j = 0; j < 4; ++j) {
+                float dl = d_all * scales[is++];
+                for (int l = 0; l < 16; ++l)
+                    *y++ = dl * ((int8_t)((q[l + 0] >> shift) & 3) - ((hm[l + 0] & m) ? 0 : 4));
+                dl = d_all * scales[is++];
+                for (int l = 0; l < 16; ++l)
+                    *y++ = dl * ((int8_t)((q[l + 16] >> shift) & 3) - ((hm[l + 16] & m) ? 0 : 4));
+                shift += 2;
+                m <<= 1;
+            }
+            q += 32;
+        }
+    }
+}
+
 static void deq_q4_K(const block_q4_K *x, float *y, int64_t k) {
     for (int64_t i = 0; i < k / QK_K; i++) {
         const uint8_t *q = x[i].qs;
@@ -630,19 +868,19 @@ static void deq_q6_K(const block_q6_K *x, float *y, int64_t k) {
 
 /* ---- exported entry points --------------------------------------------------------- */
 /* ggml_type ids (GGUFPY/constants.py GGMLQuantizationType) */
-enum { T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
+enum { T_Q2_K = 10, T_Q3_K = 11, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
 
 int oracle_block_elems(int t) {
     switch (t) {
         case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: return QK;
-        case T_Q4_K: case T_Q5_K: case T_Q6_K: return QK_K;
+        case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: return QK_K;
         default: return -1;
     }
 }
 int oracle_block_bytes(int t) {
     switch (t) {
         case T_Q4_0: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24;
-        case T_Q8_0: return 34; case T_Q4_K: return 144; case T_Q5_K: return 176; case T_Q6_K: return 210;
+        case T_Q8_0: return 34; case T_Q2_K: return 84; case T_Q3_K: return 110; case T_Q4_K: return 144; case T_Q5_K: return 176; case T_Q6_K: return 210;
         default: return -1;
     }
 }
@@ -697,6 +935,8 @@ static void quant_rows(int64_t lo, int64_t hi, void *p) {
             case T_Q5_0: row_q5_0(xr, (block_q5_0 *)yr, c->ncols); break;
             case T_Q5_1: row_q5_1(xr, (block_q5_1 *)yr, c->ncols); break;
             case T_Q8_0: row_q8_0(xr, (block_q8_0 *)yr, c->ncols); break;
+            case T_Q2_K: row_q2_K(xr, (block_q2_K *)yr, c->ncols); break;
+            case T_Q3_K: row_q3_K(xr, (block_q3_K *)yr, c->ncols); break;
             case T_Q4_K: row_q4_K(xr, (block_q4_K *)yr, c->ncols); break;
             case T_Q5_K: row_q5_K(xr, (block_q5_K *)yr, c->ncols); break;
             case T_Q6_K: row_q6_K(xr, (block_q6_K *)yr, c->ncols); break;
@@ -714,6 +954,8 @@ static void deq_rows(int64_t lo, int64_t hi, void *p) {
             case T_Q5_0: deq_q5_0((const block_q5_0 *)xr, yr, c->ncols); break;
             case T_Q5_1: deq_q5_1((const block_q5_1 *)xr, yr, c->ncols); break;
             case T_Q8_0: deq_q8_0((const block_q8_0 *)xr, yr, c->ncols); break;
+            case T_Q2_K: deq_q2_K((const block_q2_K *)xr, yr, c->ncols); break;
+            case T_Q3_K: deq_q3_K((const block_q3_K *)xr, yr, c->ncols); break;
             case T_Q4_K: deq_q4_K((const block_q4_K *)xr, yr, c->ncols); break;
             case T_Q5_K: deq_q5_K((const block_q5_K *)xr, yr, c->ncols); break;
             case T_Q6_K: deq_q6_K((const block_q6_K *)xr, yr, c->ncols); break;

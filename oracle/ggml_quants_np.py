@@ -1,8 +1,8 @@
 """ORACLE — test infrastructure only.  Second, independent restatement (numpy, vectorised
 over blocks) of llama.cpp's K-quant reference quantizers, used to cross-check
 oracle/ggml_quants.c byte-for-byte (SURVEY.md §7 hard part 1: "two independent GGUF
-implementations must agree").  Follows SURVEY.md §D.4 (Q4_K / Q5_K, `make_qkx2_quants`) and
-§D.5 (Q6_K, `make_qx_quants` rmse_type=1).
+implementations must agree").  Follows SURVEY.md §D.4 (Q4_K / Q5_K, `make_qkx2_quants`; Q2_K uses the same
+search with use_mad), §D.5 (Q6_K, `make_qx_quants` rmse_type=1) and llama.cpp `make_q3_quants` (Q3_K).
 
 Every in-block accumulation is a sequential fp32 sum in element order (python loop over the
 32 / 16 elements of a sub-block; numpy vectors run over blocks), so rounding matches the C
@@ -20,7 +20,7 @@ def nearest_int(v):
     return (i & 0x007FFFFF) - 0x00400000
 
 
-def _qkx2(x, w, nmax, rmin, rdelta, nstep):
+def _qkx2(x, w, nmax, rmin, rdelta, nstep, use_mad=False):
     """x, w: [B, n] fp32.  Returns scale [B], the_min [B], L [B, n] (uint8)."""
     B, n = x.shape
     mn = x[:, 0].copy()
@@ -43,7 +43,7 @@ def _qkx2(x, w, nmax, rmin, rdelta, nstep):
         l = np.clip(nearest_int((iscale * (x[:, i] - mn).astype(f32)).astype(f32)), 0, nmax)
         L[:, i] = l
         diff = (((scale * l.astype(f32)).astype(f32) + mn).astype(f32) - x[:, i]).astype(f32)
-        diff = (diff * diff).astype(f32)
+        diff = np.abs(diff) if use_mad else (diff * diff).astype(f32)
         best = (best + (w[:, i] * diff).astype(f32)).astype(f32)
     cur_min = mn.copy()
     for step in range(nstep + 1):
@@ -77,7 +77,7 @@ def _qkx2(x, w, nmax, rmin, rdelta, nstep):
         err = np.zeros(B, dtype=f32)
         for i in range(n):
             diff = (((this_scale * Laux[:, i].astype(f32)).astype(f32) + this_min).astype(f32) - x[:, i]).astype(f32)
-            diff = (diff * diff).astype(f32)
+            diff = np.abs(diff) if use_mad else (diff * diff).astype(f32)
             err = (err + (w[:, i] * diff).astype(f32)).astype(f32)
         adopt = ok & (err < best) & ~flat
         L[adopt] = Laux[adopt]
@@ -271,4 +271,152 @@ def quantize_q6_K(x):
     return out.reshape(nrows, -1)
 
 
-QUANTIZE = {"Q4_K": quantize_q4_K, "Q5_K": quantize_q5_K, "Q6_K": quantize_q6_K}
+def _pack2(L):
+    """[B,256] 2-bit codes -> [B,64]: byte l of each 128-half = L[l] | L[l+32]<<2 | L[l+64]<<4 | L[l+96]<<6."""
+    B = L.shape[0]
+    Lh = L.reshape(B, 2, 4, 32)
+    return (Lh[:, :, 0, :] | (Lh[:, :, 1, :] << 2) | (Lh[:, :, 2, :] << 4) | (Lh[:, :, 3, :] << 6)).astype(np.uint8).reshape(B, 64)
+
+
+def quantize_q2_K(x):
+    """llama.cpp quantize_row_q2_K_ref: qkx2(16, 3, |x| weights, -0.5, 0.1, 15, use_mad), 4-bit scales/mins."""
+    x = np.ascontiguousarray(x, dtype=f32)
+    nrows, ncols = x.shape
+    xb = x.reshape(-1, 256)
+    B = xb.shape[0]
+    xs = xb.reshape(B * 16, 16)
+    sc, mins, L = _qkx2(xs, np.abs(xs).astype(f32), 3, -0.5, 0.1, 15, use_mad=True)
+    sc, mins, L = sc.reshape(B, 16), mins.reshape(B, 16), L.reshape(B, 256)
+    max_scale = np.zeros(B, dtype=f32)
+    max_min = np.zeros(B, dtype=f32)
+    for j in range(16):
+        max_scale = np.where(sc[:, j] > max_scale, sc[:, j], max_scale)
+        max_min = np.where(mins[:, j] > max_min, mins[:, j], max_min)
+    has_s, has_m = max_scale > 0, max_min > 0
+    with np.errstate(all="ignore"):
+        isc = (f32(15) / np.where(has_s, max_scale, f32(1))).astype(f32)
+        imn = (f32(15) / np.where(has_m, max_min, f32(1))).astype(f32)
+    ls = np.where(has_s[:, None], nearest_int((isc[:, None] * sc).astype(f32)), 0)
+    lm = np.where(has_m[:, None], nearest_int((imn[:, None] * mins).astype(f32)), 0)
+    scales = ((ls & 0xFF) | ((lm << 4) & 0xFF)).astype(np.uint8)
+    d16 = np.where(has_s, (max_scale / f32(15)).astype(f32), f32(0)).astype(np.float16)
+    m16 = np.where(has_m, (max_min / f32(15)).astype(f32), f32(0)).astype(np.float16)
+    dq, mq = d16.astype(f32), m16.astype(f32)
+    for j in range(16):
+        d = (dq * (scales[:, j] & 0xF).astype(f32)).astype(f32)
+        dm = (mq * (scales[:, j] >> 4).astype(f32)).astype(f32)
+        nz = d != 0
+        ds = np.where(nz, d, f32(1)).astype(f32)
+        for ii in range(16):
+            l = np.clip(nearest_int(((xb[:, 16 * j + ii] + dm).astype(f32) / ds).astype(f32)), 0, 3)
+            L[:, 16 * j + ii] = np.where(nz, l, L[:, 16 * j + ii])
+    out = np.zeros((B, 84), dtype=np.uint8)
+    out[:, 0:16] = scales
+    out[:, 16:80] = _pack2(L)
+    out[:, 80:82] = d16.view(np.uint8).reshape(B, 2)
+    out[:, 82:84] = m16.view(np.uint8).reshape(B, 2)
+    return out.reshape(nrows, -1)
+
+
+def _q3_rmse(x, nmax):
+    """llama.cpp make_q3_quants(do_rmse=true).  x: [B, n] -> scale [B], L [B, n] offset by +nmax."""
+    B, n = x.shape
+    amax = np.zeros(B, dtype=f32)
+    mx = np.zeros(B, dtype=f32)
+    for i in range(n):
+        ax = np.abs(x[:, i])
+        upd = ax > amax
+        amax = np.where(upd, ax, amax)
+        mx = np.where(upd, x[:, i], mx)
+    tiny = amax < f32(1e-15)
+    iscale = (f32(-nmax) / np.where(tiny, f32(1), mx)).astype(f32)
+    L = np.empty((B, n), dtype=np.int32)
+    sumlx = np.zeros(B, dtype=f32)
+    suml2 = np.zeros(B, dtype=f32)
+    w = (x * x).astype(f32)
+    wx = (w * x).astype(f32)
+    for i in range(n):
+        l = np.clip(nearest_int((iscale * x[:, i]).astype(f32)), -nmax, nmax - 1)
+        L[:, i] = l
+        lf = l.astype(f32)
+        sumlx = (sumlx + (wx[:, i] * lf).astype(f32)).astype(f32)
+        suml2 = (suml2 + ((w[:, i] * lf).astype(f32) * lf).astype(f32)).astype(f32)
+    active = ~tiny
+    with np.errstate(all="ignore"):
+        for _ in range(5):
+            changed = np.zeros(B, dtype=bool)
+            for i in range(n):
+                lf = L[:, i].astype(f32)
+                slx = (sumlx - (wx[:, i] * lf).astype(f32)).astype(f32)
+                sl2 = (suml2 - ((w[:, i] * lf).astype(f32) * lf).astype(f32)).astype(f32)
+                pos = slx > 0
+                q = ((x[:, i] * sl2).astype(f32) / np.where(pos, slx, f32(1))).astype(f32)
+                new_l = np.clip(nearest_int(q), -nmax, nmax - 1)
+                nf = new_l.astype(f32)
+                slx2 = (slx + (wx[:, i] * nf).astype(f32)).astype(f32)
+                sl22 = (sl2 + ((w[:, i] * nf).astype(f32) * nf).astype(f32)).astype(f32)
+                better = ((slx2 * slx2).astype(f32) * suml2).astype(f32) > ((sumlx * sumlx).astype(f32) * sl22).astype(f32)
+                adopt = active & pos & (new_l != L[:, i]) & (sl22 > 0) & better
+                L[:, i] = np.where(adopt, new_l, L[:, i])
+                sumlx = np.where(adopt, slx2, sumlx).astype(f32)
+                suml2 = np.where(adopt, sl22, suml2).astype(f32)
+                changed |= adopt
+            active = active & changed     # a block that made no change stops sweeping
+            if not active.any():
+                break
+        scale = (sumlx / suml2).astype(f32)
+    scale = np.where(tiny, f32(0), scale).astype(f32)
+    L = L + nmax
+    L[tiny] = 0
+    return scale, L
+
+
+def quantize_q3_K(x):
+    x = np.ascontiguousarray(x, dtype=f32)
+    nrows, ncols = x.shape
+    xb = x.reshape(-1, 256)
+    B = xb.shape[0]
+    sc, L = _q3_rmse(xb.reshape(B * 16, 16), 4)
+    sc, L = sc.reshape(B, 16), L.reshape(B, 256)
+    max_scale = np.zeros(B, dtype=f32)
+    amax = np.zeros(B, dtype=f32)
+    for j in range(16):
+        a = np.abs(sc[:, j])
+        upd = a > amax
+        amax = np.where(upd, a, amax)
+        max_scale = np.where(upd, sc[:, j], max_scale)
+    has = max_scale != 0
+    with np.errstate(all="ignore"):
+        iscale = (f32(-32) / np.where(has, max_scale, f32(1))).astype(f32)
+        d16 = np.where(has, (f32(1) / iscale).astype(f32), f32(0)).astype(np.float16)
+    l6 = np.clip(nearest_int((iscale[:, None] * sc).astype(f32)).astype(np.int8).astype(np.int32), -32, 31) + 32
+    l6 = np.where(has[:, None], l6, 0)
+    scales = np.zeros((B, 12), dtype=np.int32)
+    for j in range(16):
+        if j < 8:
+            scales[:, j] = l6[:, j] & 0xF
+        else:
+            scales[:, j - 8] |= (l6[:, j] & 0xF) << 4
+        scales[:, j % 4 + 8] |= (l6[:, j] >> 4) << (2 * (j // 4))
+    dq = d16.astype(f32)
+    sc6 = np.where(has[:, None], l6 - 32, -32)     # decoded exactly as the C re-reads the packed bytes
+    for j in range(16):
+        d = (dq * sc6[:, j].astype(f32)).astype(f32)
+        nz = d != 0
+        ds = np.where(nz, d, f32(1)).astype(f32)
+        for ii in range(16):
+            l = np.clip(nearest_int((xb[:, 16 * j + ii] / ds).astype(f32)), -4, 3) + 4
+            L[:, 16 * j + ii] = np.where(nz, l, L[:, 16 * j + ii])
+    hi = (L > 3).astype(np.int32).reshape(B, 8, 32)
+    hmask = np.zeros((B, 32), dtype=np.int32)
+    for b in range(8):
+        hmask |= hi[:, b, :] << b
+    out = np.zeros((B, 110), dtype=np.uint8)
+    out[:, 0:32] = hmask.astype(np.uint8)
+    out[:, 32:96] = _pack2(L & 3)
+    out[:, 96:108] = scales.astype(np.uint8)
+    out[:, 108:110] = d16.view(np.uint8).reshape(B, 2)
+    return out.reshape(nrows, -1)
+
+
+QUANTIZE = {"Q2_K": quantize_q2_K, "Q3_K": quantize_q3_K, "Q4_K": quantize_q4_K, "Q5_K": quantize_q5_K, "Q6_K": quantize_q6_K}

@@ -4,7 +4,7 @@
 //
 // Replaces: the `llama-quantize` child process of the reference,
 //   ref/src/quantool/methods/llama_cpp/llama_cpp.py:165-178 (`GGUF._quantize_gguf`)
-// i.e. llama.cpp ggml-quants.c quantize_row_{q8_0,q4_0,q4_1,q5_0,q5_1,q4_K,q5_K,q6_K}_ref
+// i.e. llama.cpp ggml-quants.c quantize_row_{q8_0,q4_0,q4_1,q5_0,q5_1,q2_K,q3_K,q4_K,q5_K,q6_K}_ref
 // and dequantize_row_* (§D.1-§D.5).
 //
 // Data layout in HBM: src is the tensor as a flat row-major array (rows are a multiple of the
@@ -24,16 +24,17 @@ namespace qt {
 namespace gguf {
 
 enum : int {
-    T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14
+    T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
+    T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14
 };
 
 __host__ __device__ constexpr int block_elems(int t) {
-    return (t == T_Q4_K || t == T_Q5_K || t == T_Q6_K) ? 256
+    return (t == T_Q2_K || t == T_Q3_K || t == T_Q4_K || t == T_Q5_K || t == T_Q6_K) ? 256
          : (t == T_Q4_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_Q8_0) ? 32 : -1;
 }
 __host__ __device__ constexpr int block_bytes(int t) {
     return t == T_Q4_0 ? 18 : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q8_0 ? 34
-         : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210 : -1;
+         : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210 : -1;
 }
 
 QT_D void sts16(uint8_t* p, uint32_t v) { *reinterpret_cast<unsigned short*>(p) = (unsigned short)v; }
@@ -52,7 +53,7 @@ QT_D void copy_out(uint8_t* __restrict__ gdst, const uint8_t* sout, int bytes) {
 }
 
 // ---------------------------------------------------------------------------------------
-// 32-element block types.  256 threads = 64 blocks per pass, U passes per CTA iteration.
+// 32-element block types.  A warp covers 8 blocks per pass (4 lanes each), U passes per iteration.
 // Lane q (0..3) of a block owns elements 4q..4q+3 and 16+4q..16+4q+3: exactly the pairs that
 // share an output byte in the 4/5-bit formats, so no packed data crosses lanes.  The kernels
 // were issue-bound (29 instructions per element in the first version): the arg-max is tracked
@@ -94,9 +95,16 @@ QT_D void load_block_quarter(const void* __restrict__ src, int64_t blk, int q, f
     }
 }
 
-// floor of a float in [0, 2^22) as an integer, without F2I: round-down add of 2^23 leaves the
-// integer in the low mantissa bits.  (C's (int8_t)(x + 8.5f) truncates; the argument is >= 0.5.)
-QT_D int trunc_pos(float t) { return __float_as_int(__fadd_rd(t, 8388608.0f)) & 0x7fffff; }
+// low bytes of four 32-bit values -> one word (3 PRMT)
+QT_D uint32_t gather_b0(float a, float b, float c, float d) {
+    const uint32_t ab = __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x0040);
+    const uint32_t cd = __byte_perm(__float_as_uint(c), __float_as_uint(d), 0x0040);
+    return __byte_perm(ab, cd, 0x5410);
+}
+
+// Float -> code without F2I: a round-down add of 2^23 to t in [0, 2^22) leaves floor(t) in the low
+// mantissa bits.  (C's (int8_t)(x + 8.5f) truncates; the argument is >= 0.)
+constexpr float kMagic = 8388608.0f;
 
 template <int TYPE>
 QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
@@ -133,7 +141,9 @@ QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     }
-    int xi[8];
+    // Codes stay in the low mantissa byte of "magic" floats (2^23 + n, see kMagic): the byte
+    // gathers below read only that byte, so no mask or F2I is needed.
+    float tf[8];
     if (kSym) {
         // signed value of the first element with the largest |v| (strict < in a forward scan)
         float smax = (mx > -mn) ? mx : mn;
@@ -152,11 +162,10 @@ QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
         const float d = smax / (k5 ? -16 : -8);
         const float id = d ? 1.0f / d : 0.0f;
         if (q == 0) sts16(o, __half_as_ushort(__float2half_rn(d)));
+        // MIN(15, (int8_t)(x*id + 8.5f)): the clamp commutes with the truncation
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int t = trunc_pos(v[i] * id + (k5 ? 16.5f : 8.5f));
-            xi[i] = t < (k5 ? 31 : 15) ? t : (k5 ? 31 : 15);
-        }
+        for (int i = 0; i < 8; i++)
+            tf[i] = __fadd_rd(fminf(v[i] * id + (k5 ? 16.5f : 8.5f), k5 ? 31.0f : 15.0f), kMagic);
     } else {
         const float d = (mx - mn) / (k5 ? 31 : 15);
         const float id = d ? 1.0f / d : 0.0f;
@@ -166,21 +175,26 @@ QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int t = trunc_pos((v[i] - mn) * id + 0.5f);
-            xi[i] = k5 ? (t & 0xff) : (t < 15 ? t : 15);
+            const float t = (v[i] - mn) * id + 0.5f;
+            tf[i] = __fadd_rd(k5 ? t : fminf(t, 15.0f), kMagic);   // Q5_1 casts to uint8_t unclamped
         }
     }
+    // lo = codes of elements 4q..4q+3, hi = codes of 16+4q..16+4q+3, one byte each
+    const uint32_t lo = gather_b0(tf[0], tf[1], tf[2], tf[3]);
+    const uint32_t hi = gather_b0(tf[4], tf[5], tf[6], tf[7]);
     // byte j = elem j (low nibble) | elem j+16 (high nibble), j = 4q + i: both live in this lane
-    uint32_t word = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) word |= (uint32_t)((xi[i] & 0xF) | ((xi[i + 4] & 0xF) << 4)) << (8 * i);
+    uint32_t word;
     if (k5) {
-        uint32_t qh = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) qh |= (uint32_t)((xi[i] >> 4) & 1) << (4 * q + i) | (uint32_t)((xi[i + 4] >> 4) & 1) << (16 + 4 * q + i);
+        word = (lo & 0x0F0F0F0Fu) | ((hi << 4) & 0xF0F0F0F0u);
+        // bit 4 of each of the four bytes -> a nibble (the multiply lines them up at bits 28..31)
+        const uint32_t nl = ((lo & 0x10101010u) * 0x01020408u) >> 28;
+        const uint32_t nh = ((hi & 0x10101010u) * 0x01020408u) >> 28;
+        uint32_t qh = (nl << (4 * q)) | (nh << (16 + 4 * q));
         qh |= __shfl_xor_sync(0xffffffffu, qh, 1);
         qh |= __shfl_xor_sync(0xffffffffu, qh, 2);
         if (q == 0) { sts16(o + kHdr, qh & 0xffff); sts16(o + kHdr + 2, qh >> 16); }
+    } else {
+        word = lo + (hi << 4);   // codes are <= 15
     }
     uint8_t* qs = o + kHdr + (k5 ? 4 : 0) + 4 * q;
     sts16(qs, word & 0xffff);
@@ -190,21 +204,37 @@ QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
 template <int TYPE, int DT, bool VIA_F16>
 __global__ void __launch_bounds__(256) pack_simple_kernel(const void* __restrict__ src,
                                                           uint8_t* __restrict__ dst, int64_t nblocks) {
+    // Each warp owns 32 consecutive blocks per iteration (8 blocks x kSimpleU passes): 32*BB bytes
+    // of output is a multiple of 16 for every type, so the warp stages and stores its own slice
+    // and the CTA never synchronises - warps drift apart and cover each other's load latency.
     constexpr int BB = block_bytes(TYPE);
+    constexpr int kWarpBlocks = 8 * kSimpleU;
+    static_assert((kWarpBlocks * BB) % 16 == 0, "warp slice must be 16-byte granular");
     __shared__ __align__(16) uint8_t sout[kSimpleBlocksPerCta * BB];
-    const int tid = threadIdx.x, q = tid & 3, bl = tid >> 2;
-    for (int64_t base = (int64_t)blockIdx.x * kSimpleBlocksPerCta; base < nblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3, bl = lane >> 2;
+    uint8_t* wout = sout + warp * kWarpBlocks * BB;
+    for (int64_t base = (int64_t)blockIdx.x * kSimpleBlocksPerCta + warp * kWarpBlocks; base < nblocks;
          base += (int64_t)gridDim.x * kSimpleBlocksPerCta) {
         float v[kSimpleU][8];
+        const bool full = base + kWarpBlocks <= nblocks;
+        if (full) {
+            // one base pointer, compile-time offsets, all loads issued before any math
 #pragma unroll
-        for (int u = 0; u < kSimpleU; u++) {
-            const int64_t blk = base + u * 64 + bl;
-            if (blk < nblocks) {
-                if (TYPE == T_Q8_0) load8<DT>(src, blk * 4 + q, v[u]);
-                else load_block_quarter<DT>(src, blk, q, v[u]);
-            } else {
+            for (int u = 0; u < kSimpleU; u++) {
+                if (TYPE == T_Q8_0) load8<DT>(src, (base + bl) * 4 + q + u * 32, v[u]);
+                else load_block_quarter<DT>(src, base + bl + u * 8, q, v[u]);
+            }
+        } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[u][i] = 0.f;
+            for (int u = 0; u < kSimpleU; u++) {
+                const int64_t blk = base + u * 8 + bl;
+                if (blk < nblocks) {
+                    if (TYPE == T_Q8_0) load8<DT>(src, blk * 4 + q, v[u]);
+                    else load_block_quarter<DT>(src, blk, q, v[u]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[u][i] = 0.f;
+                }
             }
         }
 #pragma unroll
@@ -213,13 +243,21 @@ __global__ void __launch_bounds__(256) pack_simple_kernel(const void* __restrict
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[u][i] = round_via_f16(v[u][i]);
             }
-            pack_simple_block<TYPE>(v[u], q, sout + (u * 64 + bl) * BB);
+            pack_simple_block<TYPE>(v[u], q, wout + (u * 8 + bl) * BB);
         }
-        __syncthreads();
-        const int64_t left = nblocks - base;
-        const int nvalid = left < kSimpleBlocksPerCta ? (int)left : kSimpleBlocksPerCta;
-        copy_out(dst + base * BB, sout, nvalid * BB);
-        __syncthreads();
+        __syncwarp();
+        uint8_t* gdst = dst + base * BB;
+        if (full) {
+#pragma unroll
+            for (int i = lane; i < kWarpBlocks * BB / 16; i += 32)
+                stg_stream(gdst + 16 * i, *reinterpret_cast<const uint4*>(wout + 16 * i));
+        } else {
+            const int bytes = (int)(nblocks - base) * BB;
+            for (int i = lane; i < (bytes >> 4); i += 32)
+                stg_stream(gdst + 16 * i, *reinterpret_cast<const uint4*>(wout + 16 * i));
+            for (int i = (bytes & ~15) + lane; i < bytes; i += 32) gdst[i] = wout[i];
+        }
+        __syncwarp();
     }
 }
 
@@ -295,6 +333,39 @@ __global__ void __launch_bounds__(256) pack_q6k_kernel(const void* __restrict__ 
         kq::q6k_phase_c(t, s);
         __syncthreads();
         copy_out(dst + base * 210, s.out, nvalid * 210);
+        __syncthreads();
+    }
+}
+
+template <int TYPE, int DT, bool VIA_F16>
+__global__ void __launch_bounds__(256) pack_k23_kernel(const void* __restrict__ src, uint8_t* __restrict__ dst,
+                                                       int64_t nsuper) {
+    constexpr int BB = block_bytes(TYPE);
+    using S = kq::K23Shared<kK6Nsb, BB>;
+    __shared__ S s;
+    const int t = threadIdx.x;
+    for (int64_t base = (int64_t)blockIdx.x * kK6Nsb; base < nsuper; base += (int64_t)gridDim.x * kK6Nsb) {
+        const int64_t left = nsuper - base;
+        const int nvalid = left < kK6Nsb ? (int)left : kK6Nsb;
+        stage_in<DT, VIA_F16, 16, 17, kK6Nsb * 256>(src, base * 256, (int64_t)nvalid * 256, s.x);
+        __syncthreads();
+        if constexpr (TYPE == T_Q2_K) {
+            kq::K2Thread th;
+            kq::q2k_phase_a(t, s, th);
+            __syncthreads();
+            kq::q2k_phase_b(t, s, th);
+            __syncthreads();
+            kq::q2k_phase_c(t, s);
+        } else {
+            kq::K3Thread th;
+            kq::q3k_phase_a(t, s, th);
+            __syncthreads();
+            kq::q3k_phase_b(t, s, th);
+            __syncthreads();
+            kq::q3k_phase_c(t, s);
+        }
+        __syncthreads();
+        copy_out(dst + base * BB, s.out, nvalid * BB);
         __syncthreads();
     }
 }
@@ -379,6 +450,30 @@ __global__ void __launch_bounds__(256) dequant_k_kernel(const uint8_t* __restric
             if (TYPE == T_Q5_K) x += ((qh[l] >> j) & 1) ? 16 : 0;
             out[l] = d1 * x - m1;
         }
+    } else if (TYPE == T_Q2_K || TYPE == T_Q3_K) {
+        // element e = 32j + l -> half n = j/4, shift 2*(j%4); sub-block scale index 2j + l/16
+        const int n = j >> 2, sh = 2 * (j & 3);
+        const uint8_t* q = b + (TYPE == T_Q2_K ? 16 : 32) + 32 * n;
+        if (TYPE == T_Q2_K) {
+            const float d = ld_f16(b + 80), mn = ld_f16(b + 82);
+#pragma unroll
+            for (int l = 0; l < 32; l++) {
+                const uint8_t sc = b[2 * j + l / 16];
+                const float dl = d * (sc & 0xF), ml = mn * (sc >> 4);
+                out[l] = dl * (float)((q[l] >> sh) & 3) - ml;
+            }
+        } else {
+            const float d = ld_f16(b + 108);
+            const uint8_t* scb = b + 96;
+#pragma unroll
+            for (int l = 0; l < 32; l++) {
+                const int is = 2 * j + l / 16;
+                const int lo = is < 8 ? (scb[is] & 0xF) : (scb[is - 8] >> 4);
+                const int hi = (scb[8 + is % 4] >> (2 * (is / 4))) & 3;
+                const float dl = d * (float)((int)(signed char)(lo | (hi << 4)) - 32);
+                out[l] = dl * (float)((int)((q[l] >> sh) & 3) - (((b[l] >> j) & 1) ? 0 : 4));
+            }
+        }
     } else {  // Q6_K: element e = 32j + l -> half n=e/128, quarter k=(e%128)/32
         const float d = ld_f16(b + 208);
         const int n = j >> 2, k = j & 3;
@@ -414,6 +509,9 @@ static void launch_pack(const void* src, uint8_t* dst, int64_t nblk, cudaStream_
     } else if constexpr (TYPE == T_Q6_K) {
         const int64_t iters = (nblk + kK6Nsb - 1) / kK6Nsb;
         pack_q6k_kernel<DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
+    } else if constexpr (TYPE == T_Q2_K || TYPE == T_Q3_K) {
+        const int64_t iters = (nblk + kK6Nsb - 1) / kK6Nsb;
+        pack_k23_kernel<TYPE, DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
     } else {
         const int64_t iters = (nblk + kK45Nsb - 1) / kK45Nsb;
         pack_k45_kernel<TYPE, DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
@@ -457,6 +555,8 @@ int qt_gguf_quantize(int ggml_type, const void* src, int src_dtype, int round_vi
         case T_Q5_0: return dispatch_dt<T_Q5_0>(src, src_dtype, round_via_f16, d, nblk, st);
         case T_Q5_1: return dispatch_dt<T_Q5_1>(src, src_dtype, round_via_f16, d, nblk, st);
         case T_Q8_0: return dispatch_dt<T_Q8_0>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q2_K: return dispatch_dt<T_Q2_K>(src, src_dtype, round_via_f16, d, nblk, st);
+        case T_Q3_K: return dispatch_dt<T_Q3_K>(src, src_dtype, round_via_f16, d, nblk, st);
         case T_Q4_K: return dispatch_dt<T_Q4_K>(src, src_dtype, round_via_f16, d, nblk, st);
         case T_Q5_K: return dispatch_dt<T_Q5_K>(src, src_dtype, round_via_f16, d, nblk, st);
         case T_Q6_K: return dispatch_dt<T_Q6_K>(src, src_dtype, round_via_f16, d, nblk, st);
@@ -487,6 +587,8 @@ int qt_gguf_dequantize(int ggml_type, const void* src, int64_t nrows, int64_t nc
         const int64_t nthreads = nblk * 8;
         const unsigned grid = (unsigned)((nthreads + 255) / 256);
         switch (ggml_type) {
+            case T_Q2_K: dequant_k_kernel<T_Q2_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_Q3_K: dequant_k_kernel<T_Q3_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;
             case T_Q4_K: dequant_k_kernel<T_Q4_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;
             case T_Q5_K: dequant_k_kernel<T_Q5_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;
             case T_Q6_K: dequant_k_kernel<T_Q6_K><<<grid, 256, 0, st>>>(s, dst, nblk); break;

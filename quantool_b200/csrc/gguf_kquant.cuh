@@ -1,4 +1,4 @@
-// K-quant (Q4_K / Q5_K / Q6_K) block math, written as phase functions that run once per
+// K-quant (Q2_K / Q3_K / Q4_K / Q5_K / Q6_K) block math, written as phase functions that run once per
 // thread with every cross-thread exchange going through a plain "shared" struct.  On the
 // GPU the struct lives in shared memory and phases are separated by __syncthreads(); the
 // host test harness (tests/host_emul.cu) runs the same phase functions in a loop over
@@ -390,6 +390,297 @@ QT_HD void q6k_phase_c(int t, S& s) {
         const uint8_t* Lh = L + 128 * h;
         o[128 + b] = (uint8_t)((Lh[l] >> 4) | ((Lh[l + 32] >> 4) << 2) | ((Lh[l + 64] >> 4) << 4) |
                                ((Lh[l + 96] >> 4) << 6));
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Q2_K / Q3_K: 16 threads per super-block (one per 16-elem sub-block), like Q6_K.
+//   Q2_K = llama.cpp quantize_row_q2_K_ref: make_qkx2_quants(16, 3, x, weights=|x|, -0.5, 0.1, 15,
+//          use_mad=true), 4-bit scale and 4-bit min per sub-block against fp16 d / dmin.
+//   Q3_K = quantize_row_q3_K_ref: make_q3_quants(16, 4, x, do_rmse=true) (coordinate descent,
+//          sequential per sub-block), 6-bit signed sub-scales against fp16 d.
+// ------------------------------------------------------------------------------------
+template <int NSB, int OUT_BYTES>
+struct K23Shared {
+    float x[NSB * 16][17];
+    float sc[NSB * 16];
+    float mn[NSB * 16];
+    uint8_t l6[NSB * 16];
+    uint8_t L[NSB][256];
+    alignas(16) uint8_t out[NSB * OUT_BYTES];
+};
+
+struct K2Thread {
+    float x[16];
+    Qkx2Result r;
+};
+
+// make_qkx2_quants(n=16, nmax=3, weights=|x|, rmin=-0.5, rdelta=0.1, nstep=15, use_mad=true)
+QT_HD void qkx2_search_q2(const float (&x)[16], Qkx2Result& r) {
+    const int nmax = 3, nstep = 15;
+    const float rmin = -0.5f, rdelta = 0.1f;
+    float mn = x[0], mx = x[0];
+    float sum_w = fabsf(x[0]);
+    float sum_x = sum_w * x[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+        if (x[i] < mn) mn = x[i];
+        if (x[i] > mx) mx = x[i];
+        const float w = fabsf(x[i]);
+        sum_w += w;
+        sum_x += w * x[i];
+    }
+    if (mn > 0) mn = 0;
+    if (mx == mn) {
+        r.scale = 0.f; r.the_min = -mn; r.l_iscale = 0.f; r.l_min = mn; r.all_zero = 1;
+        return;
+    }
+    float iscale = nmax / (mx - mn);
+    float scale = 1 / iscale;
+    float best_mad = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
+        const float diff = fabsf(scale * l + mn - x[i]);
+        best_mad += fabsf(x[i]) * diff;
+    }
+    r.l_iscale = iscale; r.l_min = mn; r.all_zero = 0;
+    for (int is = 0; is <= nstep; ++is) {
+        iscale = (rmin + rdelta * is + nmax) / (mx - mn);
+        float lf[16];
+        float sum_l = 0, sum_l2 = 0, sum_xl = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
+            lf[i] = (float)l;
+            const float wl = fabsf(x[i]) * lf[i];
+            sum_l += wl;
+            sum_l2 += wl * lf[i];
+            sum_xl += wl * x[i];
+        }
+        const float D = sum_w * sum_l2 - sum_l * sum_l;
+        if (D > 0) {
+            float this_scale = (sum_w * sum_xl - sum_x * sum_l) / D;
+            float this_min = (sum_l2 * sum_x - sum_l * sum_xl) / D;
+            if (this_min > 0) {
+                this_min = 0;
+                this_scale = sum_xl / sum_l2;
+            }
+            float mad = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float diff = fabsf(this_scale * lf[i] + this_min - x[i]);
+                mad += fabsf(x[i]) * diff;
+            }
+            if (mad < best_mad) {
+                r.l_iscale = iscale; r.l_min = mn;
+                best_mad = mad;
+                scale = this_scale;
+                mn = this_min;
+            }
+        }
+    }
+    r.scale = scale;
+    r.the_min = -mn;
+}
+
+template <class S>
+QT_HD void q2k_phase_a(int t, S& s, K2Thread& th) {
+#pragma unroll
+    for (int l = 0; l < 16; ++l) th.x[l] = s.x[t][l];
+    qkx2_search_q2(th.x, th.r);
+    s.sc[t] = th.r.scale;
+    s.mn[t] = th.r.the_min;
+}
+
+template <class S>
+QT_HD void q2k_phase_b(int t, S& s, const K2Thread& th) {
+    const int sb = t >> 4, j = t & 15;
+    float max_scale = 0, max_min = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float scale = s.sc[sb * 16 + k];
+        if (scale > max_scale) max_scale = scale;
+        const float m = s.mn[sb * 16 + k];
+        if (m > max_min) max_min = m;
+    }
+    const float q4scale = 15.f;
+    uint8_t byte = 0;
+    __half dh = __float2half_rn(0.f), mh = __float2half_rn(0.f);
+    if (max_scale > 0) {
+        const float iscale = q4scale / max_scale;
+        byte = (uint8_t)nearest_int(iscale * th.r.scale);
+        dh = __float2half_rn(max_scale / q4scale);
+    }
+    if (max_min > 0) {
+        const float iscale = q4scale / max_min;
+        const int l = nearest_int(iscale * th.r.the_min);
+        byte |= (uint8_t)(l << 4);
+        mh = __float2half_rn(max_min / q4scale);
+    }
+    uint8_t* o = s.out + sb * 84;
+    o[j] = byte;
+    if (j == 0) {
+        const unsigned short db = __half_as_ushort(dh), mb = __half_as_ushort(mh);
+        o[80] = (uint8_t)(db & 0xff); o[81] = (uint8_t)(db >> 8);
+        o[82] = (uint8_t)(mb & 0xff); o[83] = (uint8_t)(mb >> 8);
+    }
+    const float d = __half2float(dh) * (byte & 0xF);
+    uint8_t* L = &s.L[sb][16 * j];
+    if (d != 0.f) {
+        const float dm = __half2float(mh) * (byte >> 4);
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) L[ii] = (uint8_t)clampi(nearest_int((th.x[ii] + dm) / d), 0, 3);
+    } else if (th.r.all_zero) {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) L[ii] = 0;
+    } else {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii)
+            L[ii] = (uint8_t)clampi(nearest_int(th.r.l_iscale * (th.x[ii] - th.r.l_min)), 0, 3);
+    }
+}
+
+// qs byte b (0..63): half h=b/32, l=b%32 -> 2-bit codes of elements 128h + l + {0,32,64,96}
+QT_HD uint8_t pack2_byte(const uint8_t* L, int b) {
+    const uint8_t* Lh = L + 128 * (b >> 5) + (b & 31);
+    return (uint8_t)((Lh[0] & 3) | ((Lh[32] & 3) << 2) | ((Lh[64] & 3) << 4) | ((Lh[96] & 3) << 6));
+}
+
+template <class S>
+QT_HD void q2k_phase_c(int t, S& s) {
+    const int sb = t >> 4, j = t & 15;
+    uint8_t* q = s.out + sb * 84 + 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[4 * j + i] = pack2_byte(s.L[sb], 4 * j + i);
+}
+
+struct K3Thread {
+    float x[16];
+    float scale;
+    int L[16];       // make_q3_quants result, already offset by +4 (0 for an all-zero sub-block)
+};
+
+// make_q3_quants(n=16, nmax=4, x, L, do_rmse=true)
+QT_HD void q3_search(K3Thread& th) {
+    const int nmax = 4;
+    float mx = 0, amax = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float ax = fabsf(th.x[i]);
+        if (ax > amax) { amax = ax; mx = th.x[i]; }
+    }
+    if (amax < 1e-15f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) th.L[i] = 0;
+        th.scale = 0.f;
+        return;
+    }
+    const float iscale = -nmax / mx;
+    float sumlx = 0, suml2 = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int l = clampi(nearest_int(iscale * th.x[i]), -nmax, nmax - 1);
+        th.L[i] = l;
+        const float w = th.x[i] * th.x[i];
+        sumlx += w * th.x[i] * l;
+        suml2 += w * l * l;
+    }
+#pragma unroll 1
+    for (int itry = 0; itry < 5; ++itry) {
+        int n_changed = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float w = th.x[i] * th.x[i];
+            float slx = sumlx - w * th.x[i] * th.L[i];
+            if (slx > 0) {
+                float sl2 = suml2 - w * th.L[i] * th.L[i];
+                int new_l = nearest_int(th.x[i] * sl2 / slx);
+                new_l = clampi(new_l, -nmax, nmax - 1);
+                if (new_l != th.L[i]) {
+                    slx += w * th.x[i] * new_l;
+                    sl2 += w * new_l * new_l;
+                    if (sl2 > 0 && slx * slx * suml2 > sumlx * sumlx * sl2) {
+                        th.L[i] = new_l; sumlx = slx; suml2 = sl2;
+                        ++n_changed;
+                    }
+                }
+            }
+        }
+        if (!n_changed) break;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) th.L[i] += nmax;
+    th.scale = sumlx / suml2;
+}
+
+template <class S>
+QT_HD void q3k_phase_a(int t, S& s, K3Thread& th) {
+#pragma unroll
+    for (int l = 0; l < 16; ++l) th.x[l] = s.x[t][l];
+    q3_search(th);
+    s.sc[t] = th.scale;
+}
+
+template <class S>
+QT_HD void q3k_phase_b(int t, S& s, const K3Thread& th) {
+    const int sb = t >> 4, j = t & 15;
+    float max_scale = 0, amax = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float v = s.sc[sb * 16 + k];
+        const float a = fabsf(v);
+        if (a > amax) { amax = a; max_scale = v; }
+    }
+    uint8_t* o = s.out + sb * 110;
+    int l6 = 0;          // stored 6-bit value; the packed bytes stay zero when max_scale == 0
+    __half dh = __float2half_rn(0.f);
+    if (max_scale != 0.f) {
+        const float iscale = -32.f / max_scale;
+        const int8_t l = (int8_t)nearest_int(iscale * th.scale);
+        l6 = clampi((int)l, -32, 31) + 32;
+        dh = __float2half_rn(1 / iscale);
+    }
+    s.l6[t] = (uint8_t)l6;
+    if (j == 0) {
+        const unsigned short db = __half_as_ushort(dh);
+        o[108] = (uint8_t)(db & 0xff); o[109] = (uint8_t)(db >> 8);
+    }
+    const int sc = l6 - 32;   // what the C re-reads from the packed bytes (0 - 32 when they are zero)
+    const float d = __half2float(dh) * sc;
+    uint8_t* L = &s.L[sb][16 * j];
+    if (d != 0.f) {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) L[ii] = (uint8_t)(clampi(nearest_int(th.x[ii] / d), -4, 3) + 4);
+    } else {
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) L[ii] = (uint8_t)th.L[ii];
+    }
+}
+
+template <class S>
+QT_HD void q3k_phase_c(int t, S& s) {
+    const int sb = t >> 4, j = t & 15;
+    const uint8_t* L = s.L[sb];
+    uint8_t* o = s.out + sb * 110;
+    // hmask byte m (0..31): bit b <- code of element 32b + m has its high bit set
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = 2 * j + i;
+        uint8_t h = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) h |= (uint8_t)((L[32 * b + m] > 3 ? 1 : 0) << b);
+        o[m] = h;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[32 + 4 * j + i] = pack2_byte(L, 4 * j + i);
+    // 6-bit scales: bytes 0..7 = low nibbles of sub-blocks b and b+8; bytes 8..11 = the 2 high bits
+    const uint8_t* l6 = &s.l6[sb * 16];
+    if (j < 8) {
+        o[96 + j] = (uint8_t)((l6[j] & 0xF) | ((l6[j + 8] & 0xF) << 4));
+    } else if (j < 12) {
+        const int k = j - 8;
+        o[96 + j] = (uint8_t)((l6[k] >> 4) | ((l6[k + 4] >> 4) << 2) | ((l6[k + 8] >> 4) << 4) | ((l6[k + 12] >> 4) << 6));
     }
 }
 

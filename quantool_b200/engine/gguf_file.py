@@ -18,11 +18,14 @@ import torch
 
 from .. import cabi
 
-# file types implemented here; the rest of the reference's QuantType list is a "next" row
+# default tensor type of each file type in the reference's QuantType list (llama_cpp.py:15-31)
 BASE_TYPE = {"Q4_0": "Q4_0", "Q4_1": "Q4_1", "Q5_0": "Q5_0", "Q5_1": "Q5_1", "Q8_0": "Q8_0",
+             "Q2_K": "Q2_K", "Q3_K_S": "Q3_K", "Q3_K_M": "Q3_K", "Q3_K_L": "Q3_K",
              "Q4_K_S": "Q4_K", "Q4_K_M": "Q4_K", "Q5_K_S": "Q5_K", "Q5_K_M": "Q5_K", "Q6_K": "Q6_K"}
-UNIMPLEMENTED = ("Q2_K", "Q3_K_S", "Q3_K_M", "Q3_K_L")
-FALLBACK = {"Q4_K": "Q5_0", "Q5_K": "Q5_1", "Q6_K": "Q8_0"}
+UNIMPLEMENTED = ()
+# row length not a multiple of 256 (llama.cpp falls back per tensor).  Q2_K / Q3_K fall back to IQ4_NL,
+# whose quantizer is not implemented by the sm_100a packers: such a tensor raises NotImplementedError.
+FALLBACK = {"Q4_K": "Q5_0", "Q5_K": "Q5_1", "Q6_K": "Q8_0", "Q2_K": "IQ4_NL", "Q3_K": "IQ4_NL"}
 
 
 def use_more_bits(i_layer: int, n_layers: int) -> bool:
@@ -45,22 +48,40 @@ def tensor_type(name: str, shape: Tuple[int, ...], ftype: str, n_layers: int, ha
         elif new != "Q8_0":
             new = "Q6_K"
     elif name.endswith("attn_v.weight"):
-        if ftype in ("Q4_K_M", "Q5_K_M") and use_more_bits(layer, n_layers):
+        n_gqa = n_head // n_head_kv if n_head and n_head_kv else 1
+        if ftype == "Q2_K":
+            new = "Q4_K" if n_gqa >= 4 else "Q3_K"
+        elif ftype == "Q3_K_M":
+            new = "Q5_K" if layer < 2 else "Q4_K"
+        elif ftype == "Q3_K_L":
+            new = "Q5_K"
+        elif ftype in ("Q4_K_M", "Q5_K_M") and use_more_bits(layer, n_layers):
             new = "Q6_K"
         elif ftype == "Q4_K_S" and layer < 4:
             new = "Q5_K"
-        if n_head and n_head_kv and n_head // n_head_kv >= 8 and n_layers == 80 and new in ("Q4_K",):
+        if n_gqa >= 8 and n_layers == 80 and new in ("Q3_K", "Q4_K"):
             new = "Q5_K"   # 70B: 8 heads share attn_v
     elif name.endswith("ffn_down.weight"):
-        if ftype in ("Q4_K_M", "Q5_K_M") and use_more_bits(layer, n_layers):
+        if ftype == "Q2_K":
+            new = "Q3_K"
+        elif ftype == "Q3_K_M":
+            new = "Q5_K" if layer < n_layers // 16 else "Q4_K"
+        elif ftype == "Q3_K_L":
+            new = "Q5_K"
+        elif ftype in ("Q4_K_M", "Q5_K_M") and use_more_bits(layer, n_layers):
             new = "Q6_K"
         elif ftype == "Q4_K_S" and layer < n_layers // 8:
             new = "Q5_K"
+    elif name.endswith("attn_output.weight"):
+        new = {"Q2_K": "Q3_K", "Q3_K_M": "Q4_K", "Q3_K_L": "Q5_K"}.get(ftype, new)
     be = 256 if new.endswith("_K") else 32
     if ncols % be != 0:
         new = FALLBACK.get(new, new)
         if ncols % 32 != 0:
             new = "F16"
+        elif new == "IQ4_NL":
+            raise NotImplementedError(f"{name}: row length {ncols} is not a multiple of 256, llama.cpp falls back to "
+                                      f"IQ4_NL for {ftype}, which the sm_100a packers do not implement")
     return new
 
 
@@ -148,9 +169,6 @@ def assign_devices(sizes: List[int], n_dev: int) -> List[int]:
 def quantize_gguf(input_gguf: str, out_file: str, ftype: str, devices: Optional[List[int]] = None) -> str:
     """f16 GGUF -> `ftype` GGUF.  Every 2-D weight goes host -> HBM -> CUDA packer -> host."""
     import gguf
-    if ftype in UNIMPLEMENTED:
-        raise NotImplementedError(f"GGUF level {ftype} is not implemented by the sm_100a packers yet "
-                                  f"(implemented: {sorted(BASE_TYPE)})")
     if ftype not in BASE_TYPE:
         raise ValueError(f"unknown GGUF level {ftype}")
     if not torch.cuda.is_available():

@@ -30,7 +30,28 @@ static void emul_k45(const float* x, uint8_t* out, int64_t nsuper) {
     free(s);
 }
 
+template <int BB, bool Q3>
+static void emul_k23(const float* x, uint8_t* out, int64_t nsuper) {
+    constexpr int NSB = 16;
+    using S = K23Shared<NSB, BB>;
+    S* s = (S*)malloc(sizeof(S));
+    std::vector<K2Thread> t2(NSB * 16);
+    std::vector<K3Thread> t3(NSB * 16);
+    for (int64_t base = 0; base < nsuper; base += NSB) {
+        const int nvalid = (int)((nsuper - base) < NSB ? (nsuper - base) : NSB);
+        for (int e = 0; e < NSB * 256; e++)
+            s->x[e / 16][e % 16] = (e < nvalid * 256) ? x[base * 256 + e] : 0.f;
+        for (int t = 0; t < NSB * 16; t++) { if (Q3) q3k_phase_a(t, *s, t3[t]); else q2k_phase_a(t, *s, t2[t]); }
+        for (int t = 0; t < NSB * 16; t++) { if (Q3) q3k_phase_b(t, *s, t3[t]); else q2k_phase_b(t, *s, t2[t]); }
+        for (int t = 0; t < NSB * 16; t++) { if (Q3) q3k_phase_c(t, *s); else q2k_phase_c(t, *s); }
+        memcpy(out + base * BB, s->out, (size_t)nvalid * BB);
+    }
+    free(s);
+}
+
 extern "C" {
+void emul_q2_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k23<84, false>(x, out, nsuper); }
+void emul_q3_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k23<110, true>(x, out, nsuper); }
 void emul_q4_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k45<144, false>(x, out, nsuper); }
 void emul_q5_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k45<176, true>(x, out, nsuper); }
 void emul_q6_K(const float* x, uint8_t* out, int64_t nsuper) {

@@ -7,7 +7,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-ALL = ["Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q4_K", "Q5_K", "Q6_K"]
+ALL = ["Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"]
 KAT = {"Q8_0": "d8b3256c9fd9ae4c", "Q4_0": "d153bbca62836335", "Q5_0": "c9154c30f4008bbe",
        "Q4_1": "f1844724bdbc3ca3", "Q5_1": "2cce57372f71162a"}
 
@@ -82,7 +82,7 @@ def test_empty_and_errors(qtype):
         cabi.gguf_quantize(torch.zeros((2, be)), qtype)  # CPU tensor: no fallback
 
 
-@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q4_K", "Q6_K"])
+@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q2_K", "Q3_K", "Q4_K", "Q6_K"])
 def test_full_size_roundtrip_property(qtype):
     """BASELINE config 1 scale (SmolLM2 ffn_down 576x1536 x 30 layers at once): size-independent
     properties — pack is deterministic, dequant(pack(x)) is within the format's step of x, and
@@ -96,7 +96,7 @@ def test_full_size_roundtrip_property(qtype):
     d = cabi.gguf_dequantize(y1, qtype, 1536)
     err = (d - x.float()).abs().max().item()
     amax = x.float().abs().max().item()
-    tol = {"Q8_0": 1 / 127, "Q4_0": 1 / 7, "Q4_K": 1 / 7, "Q6_K": 1 / 30}[qtype]
+    tol = {"Q8_0": 1 / 127, "Q4_0": 1 / 7, "Q2_K": 0.8, "Q3_K": 0.4, "Q4_K": 1 / 7, "Q6_K": 1 / 30}[qtype]
     assert err <= tol * amax, (err, amax)
     if qtype == "Q8_0":
         y3 = cabi.gguf_quantize(d, qtype, round_via_f16=False)

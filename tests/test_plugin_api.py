@@ -157,3 +157,30 @@ def test_gguf_tensor_type_table_smollm_and_llama():
     assert t("token_embd.weight", (128256, 4096), L=32, out=True) == "Q4_K"
     assert t("blk.1.ffn_gate.weight", (14336, 4096), "Q8_0", 32, True) == "Q8_0"
     assert t("output.weight", (128256, 4096), "Q8_0", 32, True) == "Q8_0"
+
+
+def test_gguf_tensor_type_table_low_bit_levels():
+    """Q2_K / Q3_K_{S,M,L} per-tensor choices of llama.cpp llama_tensor_get_type (llama arch, no imatrix)."""
+    from quantool_b200.engine.gguf_file import tensor_type
+    t = lambda n, s, f, L=32, kv=8, h=32: tensor_type(n, s, f, L, True, h, kv)
+    for f, base in (("Q2_K", "Q2_K"), ("Q3_K_S", "Q3_K"), ("Q3_K_M", "Q3_K"), ("Q3_K_L", "Q3_K")):
+        assert t("blk.5.attn_q.weight", (4096, 4096), f) == base
+        assert t("blk.5.ffn_gate.weight", (14336, 4096), f) == base
+        assert t("output.weight", (128256, 4096), f) == "Q6_K"
+        assert t("token_embd.weight", (128256, 4096), f) == base
+    assert t("blk.5.attn_v.weight", (1024, 4096), "Q2_K") == "Q4_K"            # n_gqa = 4
+    assert t("blk.5.attn_v.weight", (4096, 4096), "Q2_K", kv=32) == "Q3_K"
+    assert t("blk.5.ffn_down.weight", (4096, 14336), "Q2_K") == "Q3_K"
+    assert t("blk.5.attn_output.weight", (4096, 4096), "Q2_K") == "Q3_K"
+    assert t("blk.5.attn_v.weight", (1024, 4096), "Q3_K_S") == "Q3_K"
+    assert t("blk.1.attn_v.weight", (1024, 4096), "Q3_K_M") == "Q5_K"
+    assert t("blk.2.attn_v.weight", (1024, 4096), "Q3_K_M") == "Q4_K"
+    assert t("blk.1.ffn_down.weight", (4096, 14336), "Q3_K_M") == "Q5_K"       # i_layer < n_layer/16
+    assert t("blk.2.ffn_down.weight", (4096, 14336), "Q3_K_M") == "Q4_K"
+    assert t("blk.9.attn_output.weight", (4096, 4096), "Q3_K_M") == "Q4_K"
+    assert t("blk.9.attn_v.weight", (1024, 4096), "Q3_K_L") == "Q5_K"
+    assert t("blk.9.ffn_down.weight", (4096, 14336), "Q3_K_L") == "Q5_K"
+    assert t("blk.9.attn_output.weight", (4096, 4096), "Q3_K_L") == "Q5_K"
+    assert t("blk.9.attn_v.weight", (1024, 8192), "Q3_K_S", L=80, h=64) == "Q5_K"    # 70B: shared attn_v
+    with pytest.raises(NotImplementedError):                                   # 576 % 256 != 0 -> IQ4_NL
+        t("blk.0.attn_q.weight", (576, 576), "Q3_K_S", L=30, kv=3)

@@ -116,6 +116,41 @@ def test_gguf_plugin_end_to_end_bit_exact_vs_oracle(tmp_path):
         q.quantize(model=path, level="Q3_K_S", output_dir=str(tmp_path / "gg2"))
 
 
+def test_gguf_low_bit_levels_bit_exact_vs_oracle(tmp_path):
+    """The reference's own GGUF config asks for Q3_K_S (ref/test_gguf_config.yaml) on a 768-wide Llama:
+    Q2_K / Q3_K_S / Q3_K_M files, every packed tensor bit-exact vs the C oracle."""
+    import gguf
+    import quantool_b200.methods  # noqa: F401
+    from quantool_b200 import QuantizerRegistry
+    from quantool_b200.engine import gguf_file
+    from oracle import ggml_quants as oq
+    shape, sd, path = _write_model(tmp_path, layers=2, hidden=768, inter=2048, heads=12, kv=12, vocab=1024)
+    q = QuantizerRegistry.create("gguf", model_id="org/tiny-llama")
+    levels = ["Q2_K", "Q3_K_S", "Q3_K_M"]
+    outs = q.quantize(model=path, level=levels, output_dir=str(tmp_path / "gg"))
+    want_types = {"Q2_K": {"Q2_K", "Q3_K", "Q6_K"}, "Q3_K_S": {"Q3_K", "Q6_K"}, "Q3_K_M": {"Q3_K", "Q4_K", "Q5_K", "Q6_K"}}
+    for out, ftype in zip(outs, levels):
+        r = gguf.GGUFReader(out)
+        names = {t.name: t for t in r.tensors}
+        seen = set()
+        for hf_name, w in sd.items():
+            gname = gguf_file.hf_to_gguf_name(hf_name, shape.num_hidden_layers)
+            t = names[gname]
+            if hf_name.endswith("q_proj.weight"):
+                w = gguf_file._permute_qk(w, shape.num_attention_heads)
+            elif hf_name.endswith("k_proj.weight"):
+                w = gguf_file._permute_qk(w, shape.num_key_value_heads)
+            want = gguf_file.tensor_type(gname, tuple(w.shape), ftype, shape.num_hidden_layers, False,
+                                         shape.num_attention_heads, shape.num_key_value_heads)
+            assert t.tensor_type.name == want, (gname, t.tensor_type.name, want)
+            seen.add(want)
+            if want in ("F32", "F16"):
+                continue
+            ref = oq.quantize(oq.round_f16(w.float().numpy()), want)
+            assert np.array_equal(np.asarray(t.data).reshape(ref.shape), ref), (gname, want)
+        assert want_types[ftype] <= seen, (ftype, seen)
+
+
 def test_autogptq_view_is_a_pure_repack():
     from quantool_b200 import cabi
     from quantool_b200.engine import artifacts
