@@ -151,6 +151,19 @@ int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int
 /* *out (device double) += sum (a-b)^2 */
 int qt_sq_err_sum(const void* a, const void* b, int dtype, int64_t n, double* out, void* stream);
 
+/* ---- calibration forward, elementwise pieces ----------------------------------------------------
+ * The reference runs calibration data through the HF model inside llm-compressor `oneshot`
+ * (ref/src/quantool/methods/llm_compressor/base.py:162); these are one-pass replacements for the
+ * normalisation / rotary / gated-activation modules between the GEMMs of that forward
+ * (transformers LlamaRMSNorm, apply_rotary_pos_emb, LlamaMLP), with the same rounding points. */
+/* out[t] = weight * (x[t].float() * rsqrt(mean(x[t]^2) + eps)).to(dtype); x, out: [T, H], H % 8 == 0 */
+int qt_rms_norm(const void* x, const void* weight, void* out, int dtype, int64_t T, int H, float eps, void* stream);
+/* in place x = x*cos + rotate_half(x)*sin on x[T, n_heads*head_dim]; cos/sin [seq, head_dim]; position = t % seq */
+int qt_rope_inplace(void* x, const void* cos_t, const void* sin_t, int dtype, int64_t T, int seq, int n_heads,
+                    int head_dim, void* stream);
+/* out = silu(gate) * up, n elements, n % 8 == 0 */
+int qt_silu_mul(const void* gate, const void* up, void* out, int dtype, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

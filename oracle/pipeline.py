@@ -1,8 +1,8 @@
 """ORACLE — test infrastructure only.  CPU sequential-calibration driver built from the oracle
 restatements (oracle/gptq.py, oracle/awq.py, oracle/smoothquant.py): what `llmcompressor.oneshot`
 does layer by layer under the reference's call at ref/src/quantool/methods/llm_compressor/base.py:159-161
-(SURVEY.md §3.1).  The decoder-layer forward is shared plumbing (quantool_b200.engine.llama, plain
-torch ops); all quantization arithmetic here is the oracle's.  Parity unpinned (see oracle/gptq.py).
+(SURVEY.md §3.1).  The decoder-layer forward is the oracle's plain-torch restatement
+(oracle/llama_forward.py); only shape bookkeeping (LlamaShape, rope tables) is shared with the product.  Parity unpinned (see oracle/gptq.py).
 """
 from typing import Dict, Optional
 
@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from quantool_b200.engine import llama
 
 from . import awq as oawq
+from . import llama_forward as lf
 from . import gptq as og
 from . import smoothquant as osq
 
@@ -33,7 +34,7 @@ def run_gptq(shape, sd: Dict[str, torch.Tensor], token_ids: torch.Tensor, oargs,
         w = _layer(sd, l)
         if smooth_strength is not None:
             cap = {k: torch.empty((n * seq, d), dtype=h.dtype) for k, d in dims.items()}
-            llama.layer_forward(shape, w, h, cos, sin, capture=cap)
+            lf.layer_forward(shape, w, h, cos, sin, capture=cap)
             for smooth, balance, inp in (("input_layernorm", ["self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj"], "attn_in"),
                                          ("post_attention_layernorm", ["mlp.gate_proj", "mlp.up_proj"], "mlp_in")):
                 mn, mx = osq.update_channel_minmax(cap[inp], None, None)
@@ -42,7 +43,7 @@ def run_gptq(shape, sd: Dict[str, torch.Tensor], token_ids: torch.Tensor, oargs,
                 osq.apply_smoothing(w[f"{smooth}.weight"], bw, s)
                 out[f"model.layers.{l}.{smooth}.smooth_scales"] = s
         cap = {k: torch.empty((n * seq, d), dtype=h.dtype) for k, d in dims.items()}
-        llama.layer_forward(shape, w, h, cos, sin, capture=cap)
+        lf.layer_forward(shape, w, h, cos, sin, capture=cap)
         H = {}
         for k in dims:
             Hk, cnt = og.make_empty_hessian(dims[k]), 0
@@ -54,7 +55,7 @@ def run_gptq(shape, sd: Dict[str, torch.Tensor], token_ids: torch.Tensor, oargs,
             loss, Wq, s, z, gi = og.quantize_weight(w[f"{lin}.weight"], H[llama.INPUT_OF[lin]], oargs, percdamp=percdamp)
             out[f"model.layers.{l}.{lin}"] = (Wq, s, z, gi, w[f"{lin}.weight"].clone(), cap[llama.INPUT_OF[lin]])
             w[f"{lin}.weight"] = Wq
-        h = llama.layer_forward(shape, w, h, cos, sin)
+        h = lf.layer_forward(shape, w, h, cos, sin)
     return out, h
 
 
@@ -68,7 +69,7 @@ def run_awq(shape, sd, token_ids, symmetric: bool, bits: int, group_size: int, n
     for l in range(shape.num_hidden_layers):
         w = _layer(sd, l)
         cap = {k: torch.empty((n * seq, d), dtype=h.dtype) for k, d in dims.items()}
-        llama.layer_forward(shape, w, h, cos, sin, capture=cap)
+        lf.layer_forward(shape, w, h, cos, sin, capture=cap)
         for mp in llama_mappings(shape):
             x_all = cap[mp.inp]
             ssum, cnt = oawq.accumulate_mean(x_all, None)
@@ -82,9 +83,9 @@ def run_awq(shape, sd, token_ids, symmetric: bool, bits: int, group_size: int, n
                 for name, t in zip(_mp.balance, patched):
                     ww[f"{name}.weight"] = t
                 if _mp.parent == "self_attn":
-                    return [llama.attention_forward(shape, ww, _xin, cos, sin)]
+                    return [lf.attention_forward(shape, ww, _xin, cos, sin)]
                 if _mp.parent == "mlp":
-                    return [llama.mlp_forward(ww, _xin)]
+                    return [lf.mlp_forward(ww, _xin)]
                 return [F.linear(_xin, ww[f"{_mp.balance[0]}.weight"])]
 
             ref = parent(bw)
@@ -93,5 +94,5 @@ def run_awq(shape, sd, token_ids, symmetric: bool, bits: int, group_size: int, n
             out[f"model.layers.{l}.{mp.smooth}"] = (s, ratio, hist, x_mean, w_mean)
         for lin in llama.LINEARS:
             out[f"model.layers.{l}.{lin}.weight"] = w[f"{lin}.weight"].clone()
-        h = llama.layer_forward(shape, w, h, cos, sin)
+        h = lf.layer_forward(shape, w, h, cos, sin)
     return out, h

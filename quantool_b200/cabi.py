@@ -51,6 +51,9 @@ _SIGS = {
     "qt_channel_abs_sum": [_vp, _i32, _i64, _i32, _vp, _vp],
     "qt_smooth_scales": [_vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _i32, _vp],
     "qt_scale_matrix": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
+    "qt_rms_norm": [_vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp],
+    "qt_rope_inplace": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
+    "qt_silu_mul": [_vp, _vp, _vp, _i32, _i64, _vp],
     "qt_awq_wmean_accumulate": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "qt_awq_scale_qdq": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
     "qt_sq_err_sum": [_vp, _vp, _i32, _i64, _vp, _vp],
@@ -432,6 +435,42 @@ def scale_matrix_(w: torch.Tensor, s: torch.Tensor, divide: bool = False, by_row
             sp = ctypes.c_void_p(s.data_ptr() + (r0 * 4 if by_row else 0))
             _check(lib().qt_scale_matrix(ptr, _DT[w.dtype], n, K, sp, int(divide), int(by_row), _stream()),
                    "qt_scale_matrix")
+
+
+def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LlamaRMSNorm over the last dim of a contiguous x, one pass."""
+    _dev(x, "x"); _dev(weight, "weight")
+    assert x.is_contiguous() and weight.dtype == x.dtype and weight.numel() == x.shape[-1]
+    H = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    assert out.is_contiguous() and out.shape == x.shape and out.dtype == x.dtype
+    with torch.cuda.device(x.device):
+        _check(lib().qt_rms_norm(_p(x), _p(weight), _p(out), _DT[x.dtype], x.numel() // H, H, float(eps), _stream()),
+               "qt_rms_norm")
+    return out
+
+
+def rope_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq: int, n_heads: int, head_dim: int) -> torch.Tensor:
+    """In place rotary embedding on the projection output x[..., n_heads*head_dim] (token-major, contiguous)."""
+    _dev(x, "x"); _dev(cos, "cos"); _dev(sin, "sin")
+    assert x.is_contiguous() and cos.is_contiguous() and sin.is_contiguous()
+    assert cos.dtype == x.dtype and sin.dtype == x.dtype and cos.shape == (seq, head_dim) and sin.shape == cos.shape
+    assert x.shape[-1] == n_heads * head_dim
+    T = x.numel() // (n_heads * head_dim)
+    with torch.cuda.device(x.device):
+        _check(lib().qt_rope_inplace(_p(x), _p(cos), _p(sin), _DT[x.dtype], T, seq, n_heads, head_dim, _stream()),
+               "qt_rope_inplace")
+    return x
+
+
+def silu_mul(gate: torch.Tensor, up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(gate, "gate"); _dev(up, "up")
+    assert gate.is_contiguous() and up.is_contiguous() and gate.shape == up.shape and gate.dtype == up.dtype
+    out = torch.empty_like(gate) if out is None else out
+    assert out.is_contiguous() and out.shape == gate.shape and out.dtype == gate.dtype
+    with torch.cuda.device(gate.device):
+        _check(lib().qt_silu_mul(_p(gate), _p(up), _p(out), _DT[gate.dtype], gate.numel(), _stream()), "qt_silu_mul")
+    return out
 
 
 def awq_wmean(weights, group_size: int) -> torch.Tensor:

@@ -31,6 +31,7 @@ SOURCES = {
     "lazy_gemm.cu": [],
     "smooth.cu": [],
     "awq.cu": [],
+    "forward.cu": [],
 }
 
 

@@ -121,7 +121,7 @@ def awq_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tens
     cache = {n: torch.empty((T, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
     for c0 in range(0, n_local, chunk_samples):
         hb = h[c0: c0 + chunk_samples]
-        llama.layer_forward(shape, w, hb, cos, sin, capture=cache, row0=c0 * seq)
+        llama.layer_forward(shape, w, hb, cos, sin, capture=cache, row0=c0 * seq, stop_after="down_in")
     out = {}
     for mp in llama_mappings(shape):
         x_all = cache[mp.inp]

@@ -2,9 +2,10 @@
 
 What upstream's SequentialPipeline gets from `transformers` (SURVEY.md §3.1 "HOT LOOP 1/2"):
 run one decoder layer at a time over the calibration batches, exposing the inputs of every
-Linear.  This is plumbing around the quantization kernels - plain torch ops (cuBLAS GEMMs,
-SDPA) on the device - written functionally so a layer's weights can be swapped for their
-quantized versions between the two passes.
+Linear.  This is plumbing around the quantization kernels - library GEMMs (cuBLAS) and SDPA, with the
+normalisation / rotary / gated-activation steps between them as one-pass CUDA kernels
+(csrc/forward.cu) - written functionally so a layer's weights can be swapped for their quantized
+versions between the two passes.  CUDA only: the CPU restatement lives in oracle/llama_forward.py.
 
 Weights follow the HF checkpoint naming (`model.layers.{i}.self_attn.q_proj.weight`, ...).
 """
@@ -14,6 +15,8 @@ from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
+
+from .. import cabi
 
 LINEARS = ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
            "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj")
@@ -123,10 +126,9 @@ def random_state_dict(shape: LlamaShape, dtype=torch.bfloat16, seed: int = 0, de
     return sd
 
 
-def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
-    xf = x.float()
-    xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
-    return (w * xf.to(x.dtype))
+def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LlamaRMSNorm (fp32 statistics, weight multiply in the model dtype), one fused pass."""
+    return cabi.rms_norm(x, w, eps, out=out)
 
 
 def rope_tables(shape: LlamaShape, seq: int, device, dtype):
@@ -138,56 +140,68 @@ def rope_tables(shape: LlamaShape, seq: int, device, dtype):
     return emb.cos().to(dtype), emb.sin().to(dtype)
 
 
-def _rot_half(x):
-    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
-    return torch.cat((-x2, x1), dim=-1)
+def _qkv_rope(shape: LlamaShape, w: Dict[str, torch.Tensor], x: torch.Tensor, cos, sin):
+    """q/k/v projections + in-place rotary embedding; returns SDPA-layout views [B, heads, S, hd]."""
+    B, S, _ = x.shape
+    nh, nkv, hd = shape.num_attention_heads, shape.num_key_value_heads, shape.head_dim
+    q = F.linear(x, w["self_attn.q_proj.weight"])
+    k = F.linear(x, w["self_attn.k_proj.weight"])
+    v = F.linear(x, w["self_attn.v_proj.weight"])
+    cabi.rope_(q, cos, sin, S, nh, hd)
+    cabi.rope_(k, cos, sin, S, nkv, hd)
+    return (q.view(B, S, nh, hd).transpose(1, 2), k.view(B, S, nkv, hd).transpose(1, 2),
+            v.view(B, S, nkv, hd).transpose(1, 2))
+
+
+def _attend(shape: LlamaShape, q, k, v, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Causal SDPA; the head-major result is copied once into token-major [B, S, heads*hd] (`out`)."""
+    B, nh, S, hd = q.shape
+    a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=(k.shape[1] != nh))
+    if out is None:
+        out = torch.empty((B, S, nh * hd), dtype=a.dtype, device=a.device)
+    out.view(B, S, nh, hd).copy_(a.transpose(1, 2))
+    return out
 
 
 def layer_forward(shape: LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor, cos, sin,
-                  capture: Optional[Dict[str, torch.Tensor]] = None, row0: int = 0) -> torch.Tensor:
-    """h: [B, S, hidden].  If `capture` is given, the inputs of the Linears are written into
-    capture[name][row0 : row0 + B*S] (preallocated [T, K] buffers)."""
+                  capture: Optional[Dict[str, torch.Tensor]] = None, row0: int = 0,
+                  stop_after: Optional[str] = None) -> Optional[torch.Tensor]:
+    """h: [B, S, hidden] contiguous.  If `capture` is given, the inputs of the Linears are produced
+    directly in capture[name][row0 : row0 + B*S] (preallocated [T, K] buffers).  `stop_after` names a
+    captured input ("mlp_in", "down_in") after which the rest of the layer is skipped (statistics
+    passes do not need the layer output); the function then returns None."""
     B, S, _ = h.shape
-    nh, nkv, hd = shape.num_attention_heads, shape.num_key_value_heads, shape.head_dim
 
-    def cap(name, t):
-        if capture is not None:
-            capture[name][row0: row0 + B * S].copy_(t.reshape(B * S, -1))
+    def slot(name):
+        if capture is None:
+            return None
+        buf = capture[name]
+        return buf[row0: row0 + B * S].view(B, S, buf.shape[1])
 
-    x = rms_norm(h, w["input_layernorm.weight"], shape.rms_norm_eps)
-    cap("attn_in", x)
-    q = F.linear(x, w["self_attn.q_proj.weight"]).view(B, S, nh, hd).transpose(1, 2)
-    k = F.linear(x, w["self_attn.k_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
-    v = F.linear(x, w["self_attn.v_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
-    c, s = cos[None, None], sin[None, None]
-    q = q * c + _rot_half(q) * s
-    k = k * c + _rot_half(k) * s
-    a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=(nkv != nh))
-    a = a.transpose(1, 2).reshape(B, S, nh * hd)
-    cap("o_in", a)
+    x = rms_norm(h, w["input_layernorm.weight"], shape.rms_norm_eps, out=slot("attn_in"))
+    q, k, v = _qkv_rope(shape, w, x, cos, sin)
+    a = _attend(shape, q, k, v, out=slot("o_in"))
+    del q, k, v
     h = h + F.linear(a, w["self_attn.o_proj.weight"])
-    x = rms_norm(h, w["post_attention_layernorm.weight"], shape.rms_norm_eps)
-    cap("mlp_in", x)
-    d = F.silu(F.linear(x, w["mlp.gate_proj.weight"])) * F.linear(x, w["mlp.up_proj.weight"])
-    cap("down_in", d)
+    x = rms_norm(h, w["post_attention_layernorm.weight"], shape.rms_norm_eps, out=slot("mlp_in"))
+    if stop_after == "mlp_in":
+        return None
+    g = F.linear(x, w["mlp.gate_proj.weight"])
+    u = F.linear(x, w["mlp.up_proj.weight"])
+    d = cabi.silu_mul(g, u, out=slot("down_in"))
+    del g, u
+    if stop_after == "down_in":
+        return None
     return h + F.linear(d, w["mlp.down_proj.weight"])
 
 
 def attention_forward(shape: LlamaShape, w: Dict[str, torch.Tensor], x: torch.Tensor, cos, sin) -> torch.Tensor:
     """self_attn(x) on normed input x [B,S,hidden] -> [B,S,hidden] (AWQ parent module of q/k/v)."""
-    B, S, _ = x.shape
-    nh, nkv, hd = shape.num_attention_heads, shape.num_key_value_heads, shape.head_dim
-    q = F.linear(x, w["self_attn.q_proj.weight"]).view(B, S, nh, hd).transpose(1, 2)
-    k = F.linear(x, w["self_attn.k_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
-    v = F.linear(x, w["self_attn.v_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
-    c, s = cos[None, None], sin[None, None]
-    q = q * c + _rot_half(q) * s
-    k = k * c + _rot_half(k) * s
-    a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=(nkv != nh))
-    a = a.transpose(1, 2).reshape(B, S, nh * hd)
-    return F.linear(a, w["self_attn.o_proj.weight"])
+    q, k, v = _qkv_rope(shape, w, x, cos, sin)
+    return F.linear(_attend(shape, q, k, v), w["self_attn.o_proj.weight"])
 
 
 def mlp_forward(w: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
-    return F.linear(F.silu(F.linear(x, w["mlp.gate_proj.weight"])) * F.linear(x, w["mlp.up_proj.weight"]),
-                    w["mlp.down_proj.weight"])
+    g = F.linear(x, w["mlp.gate_proj.weight"])
+    u = F.linear(x, w["mlp.up_proj.weight"])
+    return F.linear(cabi.silu_mul(g, u), w["mlp.down_proj.weight"])

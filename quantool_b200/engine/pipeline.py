@@ -514,7 +514,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
         for c0 in range(0, n_local, chunk_samples):
             hb = h[c0: c0 + chunk_samples]
             rows = hb.shape[0] * seq
-            llama.layer_forward(shape, w, hb, cos, sin, capture=cap, row0=0)
+            llama.layer_forward(shape, w, hb, cos, sin, capture=cap, row0=0, stop_after="down_in")
             for n in dims:
                 accs[n].add(cap[n][:rows], hb.shape[0])
                 lq.launches += 1

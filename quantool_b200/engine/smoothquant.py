@@ -47,7 +47,7 @@ def smooth_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], h: torch.T
     for c0 in range(0, n_local, chunk_samples):
         hb = h[c0: c0 + chunk_samples]
         rows = hb.shape[0] * seq
-        llama.layer_forward(shape, w, hb, cos, sin, capture=cap, row0=0)
+        llama.layer_forward(shape, w, hb, cos, sin, capture=cap, row0=0, stop_after="mlp_in")
         for n in names:
             cabi.channel_minmax(cap[n][:rows], *stats[n])
     out = {}
