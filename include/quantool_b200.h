@@ -151,6 +151,14 @@ int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int
 /* *out (device double) += sum (a-b)^2 */
 int qt_sq_err_sum(const void* a, const void* b, int dtype, int64_t n, double* out, void* stream);
 
+/* fp32-faithful tensor-core GEMM of the inverse-Hessian chain (3xTF32, tcgen05): C (op)= +-A B^T with
+ * A = a_hi + a_lo [M,Kd], B = b_hi + b_lo [N,Kd] (qt_split_tf32 outputs), row-major, contraction over columns.
+ * flags: bit0 negate, bit1 accumulate into C (TMA reduce-add), bit2 lower tiles only, bits 4-5 / 6-7: A / B
+ * triangular (1 lower, 2 upper; the k range is trimmed).  Kd % 32 == 0.  Stands in for the cuBLAS fp32 GEMMs
+ * inside torch.linalg.cholesky / cholesky_inverse of UPSTREAM gptq_quantize.py. */
+int qt_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* C, int M, int N,
+                   int Kd, int lda, int ldb, int ldc, int flags, void* stream);
+
 /* ---- calibration forward, elementwise pieces ----------------------------------------------------
  * The reference runs calibration data through the HF model inside llm-compressor `oneshot`
  * (ref/src/quantool/methods/llm_compressor/base.py:162); these are one-pass replacements for the

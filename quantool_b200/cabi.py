@@ -51,6 +51,7 @@ _SIGS = {
     "qt_channel_abs_sum": [_vp, _i32, _i64, _i32, _vp, _vp],
     "qt_smooth_scales": [_vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _i32, _vp],
     "qt_scale_matrix": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
+    "qt_gemm_tf32x3": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "qt_rms_norm": [_vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp],
     "qt_rope_inplace": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp],
     "qt_silu_mul": [_vp, _vp, _vp, _i32, _i64, _vp],
@@ -435,6 +436,25 @@ def scale_matrix_(w: torch.Tensor, s: torch.Tensor, divide: bool = False, by_row
             sp = ctypes.c_void_p(s.data_ptr() + (r0 * 4 if by_row else 0))
             _check(lib().qt_scale_matrix(ptr, _DT[w.dtype], n, K, sp, int(divide), int(by_row), _stream()),
                    "qt_scale_matrix")
+
+
+def gemm_tf32x3(a_split, b_split, C: torch.Tensor, negate=False, accumulate=False, lower_tiles_only=False,
+                a_tri: int = 0, b_tri: int = 0) -> torch.Tensor:
+    """C (op)= +-A @ B.T on the tensor cores; a_split / b_split = (hi, lo) pairs from split_tf32 (views allowed)."""
+    (ah, al), (bh, bl) = a_split, b_split
+    for t in (ah, al, bh, bl, C):
+        if not t.is_cuda:
+            raise QtError("operand must be a CUDA tensor (no CPU fallback)")
+        assert t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1
+    M, Kd = ah.shape
+    N = bh.shape[0]
+    assert al.shape == ah.shape and bl.shape == bh.shape and bh.shape[1] == Kd and C.shape == (M, N)
+    assert al.stride(0) == ah.stride(0) and bl.stride(0) == bh.stride(0)
+    flags = int(negate) | (int(accumulate) << 1) | (int(lower_tiles_only) << 2) | (a_tri << 4) | (b_tri << 6)
+    with torch.cuda.device(C.device):
+        _check(lib().qt_gemm_tf32x3(_p(ah), _p(al), _p(bh), _p(bl), _p(C), M, N, Kd, ah.stride(0), bh.stride(0),
+                                    C.stride(0), flags, _stream()), "qt_gemm_tf32x3")
+    return C
 
 
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -32,6 +32,7 @@ SOURCES = {
     "smooth.cu": [],
     "awq.cu": [],
     "forward.cu": [],
+    "tgemm.cu": [],
 }
 
 

@@ -1,0 +1,281 @@
+// fp32-faithful GEMM on the 5th-gen tensor cores for the inverse-Hessian chain:
+//     C (op)= +-A * B^T,   A [M,Kd], B [N,Kd] both row-major = K-major, fp32 in, fp32 out.
+//
+// Replaces the fp32 cuSOLVER/cuBLAS work behind `torch.linalg.cholesky` / `cholesky_inverse` in UPSTREAM
+// llmcompressor gptq_quantize.py, i.e. the trailing SYRK updates of the blocked Cholesky and the
+// block merges of the triangular inverse, which were FFMA GEMMs at ~50 TFLOP/s in the first version.
+//
+// tcgen05 kind::tf32 with operand splitting ("3xTF32"): x = hi + lo, hi = tf32(x) exact, lo = x - hi, and
+//     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi   (dropped lo*lo term ~2^-22 relative), fp32 accumulation in TMEM.
+// Callers hand in the split operands (they are produced once per panel / block by the split kernels and reused
+// by many tiles).  Same pipeline as the lazy-batch kernel (lazy_gemm.cu), generalised: arbitrary inner
+// dimension, batches of diagonal blocks, triangular operands (k range trimmed per tile), lower-tiles-only
+// SYRK, and two epilogues - TMA store (C =) or TMA reduce-add in L2 (C +=), so C is never read by the SM.
+//
+// Tile 128 x 256, k chunks of 32 floats (one 128-byte swizzle row); stage = A_hi,A_lo (2 x 16 KB) + B_hi,B_lo
+// (2 x 32 KB) = 96 KB, 2 stages; 2 TMEM accumulators (2 x 256 columns); warp 0 = TMA producer, warp 1 = MMA
+// issuer, warps 2-5 = epilogue (32 rows each, 32 x 32 sub-tiles through swizzled staging + TMA).
+#include "tgemm.cuh"
+
+#include "tc_ptx.cuh"
+
+namespace qt {
+namespace tgemm {
+using namespace qt::tc;
+
+constexpr int BM = 128, BN = 256, KC = 32;
+constexpr int UMMA_K = 8;  // tf32
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * KC * 4;
+constexpr int B_BYTES = BN * KC * 4;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int EPI_BYTES = 4 * 2 * 4096;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+constexpr int NTHREADS = 192;
+
+// kind::tf32: D=f32 (bit 4), A=B=TF32 (2 at bits 7,10), negate A (bit 13), A and B both K-major
+constexpr uint32_t make_idesc(bool negate) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((negate ? 1u : 0u) << 13) | ((uint32_t)(BN >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Args {
+    int m_tiles, n_tiles, batch, kchunks;
+    int M, N;
+    int a_row0, a_col0, b_row0, b_col0, c_row0, c_col0;
+    int a_sr, a_sc, b_sr, b_sc, c_sr, c_sc;
+    int accumulate, lower_only, a_tri, b_tri;
+    uint32_t idesc;
+};
+
+struct Tile {
+    int b, tm, tn, kc0, kc1;
+};
+
+// decode tile index t; false = nothing to do for this tile (above the diagonal, or empty k range)
+QT_D bool decode(const Args& a, int t, Tile& o) {
+    const int per = a.m_tiles * a.n_tiles;
+    o.b = t / per;
+    const int r = t - o.b * per;
+    o.tn = r / a.m_tiles;       // n-major: consecutive CTAs share the same B rows (L2 reuse)
+    o.tm = r - o.tn * a.m_tiles;
+    if (a.lower_only && o.tn * BN > o.tm * BM + BM - 1) return false;
+    int k0 = 0, k1 = a.kchunks * KC;
+    if (a.a_tri == 1) k1 = min(k1, o.tm * BM + BM);
+    if (a.a_tri == 2) k0 = max(k0, o.tm * BM);
+    if (a.b_tri == 1) k1 = min(k1, o.tn * BN + BN);
+    if (a.b_tri == 2) k0 = max(k0, o.tn * BN);
+    o.kc0 = k0 / KC;
+    o.kc1 = (k1 + KC - 1) / KC;
+    return o.kc1 > o.kc0;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+             const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+             const __grid_constant__ CUtensorMap map_c, const Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* epi = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi + EPI_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = a.batch * a.m_tiles * a.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ahi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+        for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            Tile tl;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                if (!decode(a, t, tl)) continue;
+                const int ra = a.a_row0 + tl.b * a.a_sr + tl.tm * BM, ca = a.a_col0 + tl.b * a.a_sc;
+                const int rb = a.b_row0 + tl.b * a.b_sr + tl.tn * BN, cb = a.b_col0 + tl.b * a.b_sc;
+                for (int kc = tl.kc0; kc < tl.kc1; kc++, it++) {
+                    const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[stage], ph ^ 1);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t* s = smem + stage * STAGE_BYTES;
+                    tma_load_2d(s, &map_ahi, &full[stage], ca + kc * KC, ra);
+                    tma_load_2d(s + A_BYTES, &map_alo, &full[stage], ca + kc * KC, ra);
+                    tma_load_2d(s + 2 * A_BYTES, &map_bhi, &full[stage], cb + kc * KC, rb);
+                    tma_load_2d(s + 2 * A_BYTES + B_BYTES, &map_blo, &full[stage], cb + kc * KC, rb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, li = 0;
+            Tile tl;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                if (!decode(a, t, tl)) continue;
+                const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+                li++;
+                mbar_wait(&tempty[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kc = tl.kc0; kc < tl.kc1; kc++, it++) {
+                    const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full[stage], ph);
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sa_lo = sa_hi + A_BYTES;
+                    const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+                    const uint32_t sb_lo = sb_hi + B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KC / UMMA_K; k++) {
+                        // K-major SW128: rows of 128 B, 8-row groups 1 KB apart; k-step = 32 B inside the row
+                        const uint64_t ahi = make_desc_sw128(sa_hi + k * UMMA_K * 4, 16, 1024);
+                        const uint64_t alo = make_desc_sw128(sa_lo + k * UMMA_K * 4, 16, 1024);
+                        const uint64_t bhi = make_desc_sw128(sb_hi + k * UMMA_K * 4, 16, 1024);
+                        const uint64_t blo = make_desc_sw128(sb_lo + k * UMMA_K * 4, 16, 1024);
+                        tc_mma_tf32(d_tmem, ahi, bhi, a.idesc, (kc > tl.kc0 || k > 0) ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, ahi, blo, a.idesc, 1u);
+                        tc_mma_tf32(d_tmem, alo, bhi, a.idesc, 1u);
+                    }
+                    tc_commit(&empty[stage]);
+                }
+                tc_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        uint8_t* my = epi + (warp - 2) * 2 * 4096;
+        uint32_t li = 0, nstore = 0;
+        Tile tl;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            if (!decode(a, t, tl)) continue;
+            const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+            li++;
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const int row_local = tl.tm * BM + lg * 32;
+            const int crow = a.c_row0 + tl.b * a.c_sr + row_local;
+            const int ccol0 = a.c_col0 + tl.b * a.c_sc + tl.tn * BN;
+            if (row_local < a.M) {
+#pragma unroll 1
+                for (int cc = 0; cc < BN / 32; cc++) {
+                    if (tl.tn * BN + cc * 32 >= a.N) break;
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + cc * 32, r);
+                    uint8_t* buf = my + (nstore & 1) * 4096;
+                    nstore++;
+                    // the buffer used two stores ago must have been read by the TMA engine
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+                    // row = lane (128 B), 16-byte chunk c stored at c ^ (lane & 7): SWIZZLE_128B, conflict-free
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const uint4 v = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (a.accumulate) tma_reduce_add_2d(&map_c, buf, ccol0 + cc * 32, crow);
+                        else tma_store_2d(&map_c, buf, ccol0 + cc * 32, crow);
+                        bulk_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
+        if (lane == 0) bulk_wait<0>();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+int launch(const Problem& p, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return QT_OK;
+    if (p.Kd <= 0 || (p.Kd % KC) || !p.A.hi || !p.A.lo || !p.B.hi || !p.B.lo || !p.C) return QT_ERR_INVALID;
+    if (p.batch > 1 && ((p.M % BM) || (p.N % BN))) return QT_ERR_INVALID;
+    if ((p.A.ld & 3) || (p.B.ld & 3) || (p.ldc & 3)) return QT_ERR_INVALID;
+    const CUtensorMapDataType F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle SW = CU_TENSOR_MAP_SWIZZLE_128B;
+    // stores / reduce-adds are clipped to the last batch's sub-block
+    int crows = p.c_row0 + (p.batch - 1) * p.c_sr + p.M, ccols = p.c_col0 + (p.batch - 1) * p.c_sc + p.N;
+    if (crows > p.c_rows || ccols > p.c_cols) return QT_ERR_INVALID;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc;
+    bool ok = make_map_2d(&ma_hi, F32, p.A.hi, p.A.cols, p.A.rows, (uint64_t)p.A.ld * 4, KC, BM, SW) &&
+              make_map_2d(&ma_lo, F32, p.A.lo, p.A.cols, p.A.rows, (uint64_t)p.A.ld * 4, KC, BM, SW) &&
+              make_map_2d(&mb_hi, F32, p.B.hi, p.B.cols, p.B.rows, (uint64_t)p.B.ld * 4, KC, BN, SW) &&
+              make_map_2d(&mb_lo, F32, p.B.lo, p.B.cols, p.B.rows, (uint64_t)p.B.ld * 4, KC, BN, SW) &&
+              make_map_2d(&mc, F32, p.C, ccols, crows, (uint64_t)p.ldc * 4, 32, 32, SW);
+    if (!ok) { set_last_error("tgemm tensor maps", cudaErrorInvalidValue); return QT_ERR_CUDA; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { set_last_error("tgemm smem attr", e); return QT_ERR_CUDA; }
+        attr_set = true;
+    }
+    Args a;
+    a.m_tiles = (p.M + BM - 1) / BM;
+    a.n_tiles = (p.N + BN - 1) / BN;
+    a.batch = p.batch;
+    a.kchunks = p.Kd / KC;
+    a.M = p.M; a.N = p.N;
+    a.a_row0 = p.a_row0; a.a_col0 = p.a_col0; a.b_row0 = p.b_row0; a.b_col0 = p.b_col0;
+    a.c_row0 = p.c_row0; a.c_col0 = p.c_col0;
+    a.a_sr = p.a_sr; a.a_sc = p.a_sc; a.b_sr = p.b_sr; a.b_sc = p.b_sc; a.c_sr = p.c_sr; a.c_sc = p.c_sc;
+    a.accumulate = p.accumulate; a.lower_only = p.lower_tiles_only; a.a_tri = p.a_tri; a.b_tri = p.b_tri;
+    a.idesc = p.negate ? make_idesc(true) : make_idesc(false);
+    int dev = 0, nsm = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (long long)a.batch * a.m_tiles * a.n_tiles;
+    tgemm_kernel<<<(unsigned)(ntiles < nsm ? ntiles : nsm), NTHREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, a);
+    return check_launch("tgemm");
+}
+
+}  // namespace tgemm
+}  // namespace qt
+
+using namespace qt;
+
+extern "C" {
+
+// C (op)= +-A B^T with A = a_hi + a_lo [M,Kd], B = b_hi + b_lo [N,Kd] (tf32 splits, qt_split_tf32), all row-major
+// with leading dimensions lda/ldb/ldc.  flags: bit0 negate, bit1 accumulate (C +=), bit2 lower tiles only,
+// bits 4-5 a_tri, bits 6-7 b_tri (1 lower, 2 upper).  Kd % 32 == 0; pointers 16-byte aligned.
+int qt_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, float* C, int M, int N,
+                   int Kd, int lda, int ldb, int ldc, int flags, void* stream) {
+    if (!a_hi || !a_lo || !b_hi || !b_lo || !C || M < 0 || N < 0 || Kd <= 0) return QT_ERR_INVALID;
+    if (((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo | (uintptr_t)C) & 15) return QT_ERR_INVALID;
+    tgemm::Problem p;
+    p.A = {a_hi, a_lo, M, Kd, lda};
+    p.B = {b_hi, b_lo, N, Kd, ldb};
+    p.C = C; p.c_rows = M; p.c_cols = N; p.ldc = ldc;
+    p.M = M; p.N = N; p.Kd = Kd;
+    p.negate = flags & 1; p.accumulate = (flags >> 1) & 1; p.lower_tiles_only = (flags >> 2) & 1;
+    p.a_tri = (flags >> 4) & 3; p.b_tri = (flags >> 6) & 3;
+    return tgemm::launch(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

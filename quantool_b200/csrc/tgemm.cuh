@@ -1,0 +1,37 @@
+// fp32-faithful GEMM on the tensor cores ("3xTF32"), used by the inverse-Hessian chain.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace qt {
+namespace tgemm {
+
+// A row-major fp32 matrix given as its tf32 split x = hi + lo (hi tf32-exact; qt_split_tf32 family).
+// rows/cols are the extents used for TMA zero-fill (loads) and clipping (stores).
+struct Mat {
+    const float* hi;
+    const float* lo;
+    int rows, cols, ld;
+};
+
+struct Problem {
+    // C[c_row0 + m][c_col0 + n] (op)= sign * sum_k A[a_row0 + m][a_col0 + k] * B[b_row0 + n][b_col0 + k]
+    // for m < M, n < N, k < Kd: both operands K-major (contraction over their columns).
+    Mat A, B;
+    float* C;
+    int c_rows, c_cols, ldc;       // extents of the C array (stores are clipped to c_row0+M / c_col0+N)
+    int M, N, Kd;                  // Kd % 32 == 0
+    int a_row0 = 0, a_col0 = 0, b_row0 = 0, b_col0 = 0, c_row0 = 0, c_col0 = 0;
+    int batch = 1;                 // batch b adds b * (stride_r, stride_c) to every offset (M % 128 == 0 and
+    int a_sr = 0, a_sc = 0, b_sr = 0, b_sc = 0, c_sr = 0, c_sc = 0;   // N % 256 == 0 when batch > 1)
+    bool negate = false;           // sign = -1
+    bool accumulate = false;       // C += (TMA reduce-add in L2) instead of C =
+    bool lower_tiles_only = false; // skip 128x256 tiles entirely above the diagonal of C (SYRK)
+    int a_tri = 0;                 // 1: A[m][k] = 0 for k > m (lower), 2: = 0 for k < m (upper) - k range is trimmed
+    int b_tri = 0;                 // same for B[n][k]
+};
+
+// stream-ordered; returns QT_OK / negative error code
+int launch(const Problem& p, cudaStream_t st);
+
+}  // namespace tgemm
+}  // namespace qt
