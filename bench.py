@@ -370,10 +370,11 @@ def main():
                 acc = pipeline.HessianAccumulator(x.shape[-1], dev)
                 if record and x.shape[-1] == Kmax:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(); acc.add(x, n_local); e1.record()
+                    acc.add(x, n_local, syrk_events=(e0, e1))
                     hess_events.append((e0, e1))
                 else:
                     acc.add(x, n_local)
+                acc.sync_diagonal()
                 d.all_reduce_sum(acc.H)
                 hess[n] = acc.finalize(a.samples)
             res = lq.quantize_layer(weights[l], hess)

@@ -89,6 +89,12 @@ int qt_unpack_int32(const int32_t* packed, int N, int K, int num_bits, int8_t* c
 int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* stream);
 /* H <- factor * H (factor = 2 / n_samples) on the upper triangle, mirrored to the lower */
 int qt_hessian_finalize(float* H, int K, float factor, void* stream);
+/* Exact diagonal: the tensor-core accumulator truncates, which biases the sums of squares on the diagonal by
+ * ~-5e-6 and can reorder argsort(diag H) (the act_order permutation).  diag[c] += sum_t X[t][c]^2 in fp32
+ * round-to-nearest, deterministic; scratch = 32*K floats.  qt_hessian_set_diagonal writes the raw sums into H
+ * (before finalize / before a cross-rank reduction). */
+int qt_hessian_diag_accumulate(const void* X, int64_t T, int K, float* diag, float* scratch, void* stream);
+int qt_hessian_set_diagonal(float* H, int K, const float* diag, void* stream);
 int qt_hessian_set_splits(int splits);   /* tuning: force the token split count (0 = heuristic) */
 /* fp32 SIMT cross-check of qt_hessian_accumulate (tests / smoke only) */
 int qt_hessian_accumulate_reference(const void* X, int64_t T, int K, float* H, void* stream);
@@ -99,6 +105,11 @@ int qt_gptq_prepare_hessian(const float* H, const int* perm, int K, float percda
 /* in place: A = Hf -> U = cholesky(H^-1, upper); X, W: [K,K] fp32 scratch; info: device int32,
  * 0 = ok else 1-based failing pivot (upstream's LinAlgError path: caller sets U = I) */
 int qt_gptq_hinv_factor(float* A, float* X, float* W, int K, int* info, void* stream);
+/* Same contract with the big products on the tensor cores (3xTF32, fp32-faithful): four more K x K fp32
+ * workspaces (tf32 splits of L and of the inverse blocks); K % 256 == 0.  stages: bit 0 = Cholesky trailing updates,
+ * bit 1 = triangular-inverse merges on the tensor cores (3 = both). */
+int qt_gptq_hinv_factor_tc(float* A, float* X, float* W, float* Lh, float* Ll, float* Dh, float* Dl, int K, int* info,
+                           int stages, void* stream);
 int qt_set_identity(float* U, int K, void* stream);
 int qt_sgemm(int b_is_nk, const float* A, const float* B, float* C, int M, int N, int Kd, int lda, int ldb, int ldc,
              float alpha, float beta, int lower_tiles_only, int a_lower_tri, int b_lower_tri, void* stream);

@@ -36,9 +36,12 @@ _SIGS = {
     "qt_hessian_set_splits": [_i32],
     "qt_hessian_accumulate": [_vp, _i64, _i32, _vp, _vp],
     "qt_hessian_finalize": [_vp, _i32, _f32, _vp],
+    "qt_hessian_diag_accumulate": [_vp, _i64, _i32, _vp, _vp, _vp],
+    "qt_hessian_set_diagonal": [_vp, _i32, _vp, _vp],
     "qt_hessian_accumulate_reference": [_vp, _i64, _i32, _vp, _vp],
     "qt_gptq_prepare_hessian": [_vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp],
     "qt_gptq_hinv_factor": [_vp, _vp, _vp, _i32, _vp, _vp],
+    "qt_gptq_hinv_factor_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp],
     "qt_set_identity": [_vp, _i32, _vp],
     "qt_sgemm": [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _vp],
     "qt_sgemm_ex": [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _vp],
@@ -231,6 +234,22 @@ def hessian_accumulate(x: torch.Tensor, H: torch.Tensor) -> None:
         _check(lib().qt_hessian_accumulate(_p(x), T, K, _p(H), _stream()), "qt_hessian_accumulate")
 
 
+def hessian_diag_accumulate(x: torch.Tensor, diag: torch.Tensor, scratch: torch.Tensor) -> None:
+    """diag (fp32 [K], raw sums) += column sums of squares of x [T, K] bf16, fp32 round-to-nearest."""
+    _dev(x, "x"); _dev(diag, "diag"); _dev(scratch, "scratch")
+    T, K = x.shape
+    assert x.dtype == torch.bfloat16 and diag.dtype == torch.float32 and scratch.numel() >= 32 * K
+    with torch.cuda.device(x.device):
+        _check(lib().qt_hessian_diag_accumulate(_p(x), T, K, _p(diag), _p(scratch), _stream()),
+               "qt_hessian_diag_accumulate")
+
+
+def hessian_set_diagonal(H: torch.Tensor, diag: torch.Tensor) -> None:
+    with torch.cuda.device(H.device):
+        _check(lib().qt_hessian_set_diagonal(_p(_dev(H, "H")), H.shape[0], _p(_dev(diag, "diag")), _stream()),
+               "qt_hessian_set_diagonal")
+
+
 def hessian_accumulate_reference(x: torch.Tensor, H: torch.Tensor) -> None:
     T, K = x.shape
     with torch.cuda.device(x.device):
@@ -261,17 +280,31 @@ def gptq_prepare_hessian(H: torch.Tensor, perm: Optional[torch.Tensor], percdamp
     return Hf, dead
 
 
+def hinv_tensor_core_ok(K: int) -> bool:
+    """The tensor-core chain needs K to be a multiple of its 256-wide tiles; other K run the FFMA chain."""
+    return K % 256 == 0
+
+
 def gptq_hinv_factor(Hf: torch.Tensor, scratch_x: Optional[torch.Tensor] = None,
-                     scratch_w: Optional[torch.Tensor] = None):
+                     scratch_w: Optional[torch.Tensor] = None, tensor_core: Optional[bool] = None,
+                     workspace=None, info: Optional[torch.Tensor] = None, stages: int = 3):
     """In place: Hf (flipped damped H) -> U = cholesky(H^-1, upper).  Returns (U, info) where
-    info is a device int32 (0 = ok, else 1-based failing pivot; caller decides when to read it)."""
+    info is a device int32 (0 = ok, else 1-based failing pivot; caller decides when to read it).
+    tensor_core (default: whenever K allows) runs the big products as 3xTF32 tcgen05 GEMMs and needs four
+    more K x K fp32 workspaces (`workspace`, allocated here when not given)."""
     _dev(Hf, "Hf")
     K = Hf.shape[0]
     X = scratch_x if scratch_x is not None else torch.empty_like(Hf)
     W = scratch_w if scratch_w is not None else torch.empty_like(Hf)
-    info = torch.zeros((1,), dtype=torch.int32, device=Hf.device)
+    info = torch.zeros((1,), dtype=torch.int32, device=Hf.device) if info is None else info
+    tc = hinv_tensor_core_ok(K) if tensor_core is None else tensor_core
     with torch.cuda.device(Hf.device):
-        _check(lib().qt_gptq_hinv_factor(_p(Hf), _p(X), _p(W), K, _p(info), _stream()), "qt_gptq_hinv_factor")
+        if tc:
+            ws = workspace if workspace is not None else [torch.empty_like(Hf) for _ in range(4)]
+            _check(lib().qt_gptq_hinv_factor_tc(_p(Hf), _p(X), _p(W), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]), K,
+                                                _p(info), int(stages), _stream()), "qt_gptq_hinv_factor_tc")
+        else:
+            _check(lib().qt_gptq_hinv_factor(_p(Hf), _p(X), _p(W), K, _p(info), _stream()), "qt_gptq_hinv_factor")
     return Hf, info
 
 

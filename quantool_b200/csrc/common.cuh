@@ -59,6 +59,19 @@ QT_D void stg_stream(void* p, uint4 v) {
 QT_D float bf16_bits_to_float(uint32_t b16) { return __uint_as_float(b16 << 16); }
 QT_D float f16_bits_to_float(uint32_t h16) { return __half2float(__ushort_as_half((unsigned short)h16)); }
 
+// x ~= hi + lo with hi = tf32(x) and lo = tf32(x - hi), both rounded to nearest (low 13 mantissa bits cleared): the
+// operand form of the 3xTF32 tensor-core GEMMs (lazy_gemm.cu, tgemm.cu).  x - hi is exact in fp32; rounding it here
+// (instead of letting the tensor core truncate the low bits when it reads the operand) halves the operand error and
+// removes its bias: |x - hi - lo| <= 2^-22 |x|.
+QT_D float tf32_rn(float e) {
+    const uint32_t b = __float_as_uint(e);
+    return ((b & 0x7F800000u) == 0x7F800000u) ? e : __uint_as_float((b + 0x1000u) & 0xFFFFE000u);
+}
+QT_D void tf32_split(float e, float& h, float& l) {
+    h = tf32_rn(e);
+    l = tf32_rn(e - h);
+}
+
 // fp32 -> fp16 (RNE) -> fp32: the reference's f16-GGUF intermediate
 QT_HD float round_via_f16(float v) { return __half2float(__float2half_rn(v)); }
 

@@ -3,7 +3,7 @@
 // Replaces the `W[:, i2:] -= Err1.matmul(Hinv[i1:i2, i2:])` line of UPSTREAM llmcompressor
 // gptq_quantize.py `quantize_weight`.  Upstream runs it as an fp32
 // matmul; here it is a tcgen05 kind::tf32 GEMM made fp32-faithful by operand splitting
-// ("3xTF32"): x = hi + lo with hi = tf32(x) exact and lo = x - hi, and
+// ("3xTF32"): x ~= hi + lo with hi = tf32(x), lo = tf32(x - hi) (about 22 mantissa bits), and
 //     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (dropped term ~2^-22 relative)
 // accumulated in fp32 in TMEM, so the result matches an fp32 FFMA GEMM to ~1e-6 relative.
 //
@@ -178,13 +178,9 @@ lazy_gemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     }
 }
 
-QT_D void split1(float e, float& h, float& l) {
-    const uint32_t b = __float_as_uint(e);
-    h = ((b & 0x7F800000u) == 0x7F800000u) ? e : __uint_as_float((b + 0x1000u) & 0xFFFFE000u);
-    l = e - h;
-}
+QT_D void split1(float e, float& h, float& l) { tf32_split(e, h, l); }
 
-// hi = tf32(x) (round to nearest, low 13 mantissa bits cleared), lo = x - hi (exact in fp32)
+// hi = tf32(x), lo = tf32(x - hi), both round to nearest (low 13 mantissa bits cleared)
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                                          float* __restrict__ lo, long long n4) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
@@ -257,7 +253,7 @@ using namespace qt;
 
 extern "C" {
 
-// hi = tf32-rounded x, lo = x - hi; n % 4 == 0, 16-byte aligned pointers
+// hi = tf32(x), lo = tf32(x - hi); n % 4 == 0, 16-byte aligned pointers
 int qt_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
     if (!x || !hi || !lo || n < 0 || (n & 3)) return QT_ERR_INVALID;
     if (((uintptr_t)x & 15) || ((uintptr_t)hi & 15) || ((uintptr_t)lo & 15)) return QT_ERR_INVALID;

@@ -9,12 +9,17 @@
 // With J the index reversal, J H J = Lf Lf^T (ordinary lower Cholesky) and
 // U[i][j] = (Lf^-1)[K-1-i][K-1-j].  So: gather H flipped (fused with the act_order permutation
 // and damping), one blocked right-looking Cholesky, one recursive blocked triangular inverse,
-// one flip.  All trailing updates are fp32 FFMA GEMMs (sgemm.cuh); nothing leaves fp32.
+// one flip.  Two variants of the GEMM work: fp32 FFMA GEMMs (sgemm.cuh) everywhere, or - when K is a multiple
+// of 256 and the caller provides four more K x K workspaces - the big products on the tensor cores as
+// fp32-faithful 3xTF32 GEMMs (tgemm.cu): the Cholesky trailing update is deferred per 512-column outer block
+// (inner dimension 512 instead of 128: 4x less C traffic) and the block merges of the triangular inverse run as
+// S = X11^T-form products with triangular k trimming.  Panels, TRSMs and the 128-level merges stay FFMA.
 //
 // HBM layout: every matrix is K x K fp32 row-major, leading dimension K.  Three buffers:
 //   A  in: flipped damped H (lower triangle read)   out: U (upper triangle, zeros below)
 //   X  scratch: Lf^-1 (lower)                       W  scratch: GEMM temporaries
 #include "sgemm.cuh"
+#include "tgemm.cuh"
 
 namespace qt {
 namespace linalg {
@@ -451,6 +456,269 @@ static int trtri_lower(const float* L, float* X, float* W, int K, int ld, cudaSt
     return QT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// tensor-core variant
+// ---------------------------------------------------------------------------------------------------
+// tf32 split of a rows x cols block (optionally transposed), batched over diagonal blocks.
+//   TRANSPOSE = false: dst[r][c] = split(src[r][c]);  TRANSPOSE = true: dst[c][r] = split(src[r][c])
+//   tri (in the SOURCE block's coordinates): 1 keeps c <= r (lower), 0 keeps everything; the rest is written as 0
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(256) split_block_kernel(const float* __restrict__ src, int lds, float* __restrict__ hi,
+                                                          float* __restrict__ lo, int ldd, int rows, int cols, int tri,
+                                                          long long sstride, long long dstride) {
+    __shared__ float t[32][33];
+    src += blockIdx.z * sstride;
+    hi += blockIdx.z * dstride;
+    lo += blockIdx.z * dstride;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (!TRANSPOSE) {
+        for (int rr = ty; rr < 32; rr += 8) {
+            const int r = r0 + rr, c = c0 + tx;
+            if (r < rows && c < cols) {
+                float h = 0.f, l = 0.f;
+                if (!tri || c <= r) tf32_split(src[(long long)r * lds + c], h, l);
+                hi[(long long)r * ldd + c] = h;
+                lo[(long long)r * ldd + c] = l;
+            }
+        }
+    } else {
+        for (int rr = ty; rr < 32; rr += 8) {
+            const int r = r0 + rr, c = c0 + tx;
+            t[rr][tx] = (r < rows && c < cols && (!tri || c <= r)) ? src[(long long)r * lds + c] : 0.f;
+        }
+        __syncthreads();
+        for (int cc = ty; cc < 32; cc += 8) {
+            const int c = c0 + cc, r = r0 + tx;     // destination row c, column r
+            if (c < cols && r < rows) {
+                float h, l;
+                tf32_split(t[tx][cc], h, l);
+                hi[(long long)c * ldd + r] = h;
+                lo[(long long)c * ldd + r] = l;
+            }
+        }
+    }
+}
+
+static int split_block(bool transpose, const float* src, int lds, float* hi, float* lo, int ldd, int rows, int cols,
+                       int tri, int batch, long long sstride, long long dstride, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0 || batch <= 0) return QT_OK;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+    if (transpose) split_block_kernel<true><<<grid, 256, 0, st>>>(src, lds, hi, lo, ldd, rows, cols, tri, sstride, dstride);
+    else split_block_kernel<false><<<grid, 256, 0, st>>>(src, lds, hi, lo, ldd, rows, cols, tri, sstride, dstride);
+    return check_launch("split_block");
+}
+
+constexpr int OB = 512;   // outer block of the tensor-core Cholesky: trailing update deferred over 4 panels
+
+// The tensor cores accumulate in fp32 with truncation, which is harmless for sums of mixed sign but biases a
+// long sum of squares: the diagonal of a SYRK update (measured: ~2e-3 absolute on sums of ~500, i.e. ~1000 ulp).
+// The diagonal entries of the deferred update are therefore computed here with FFMA in round-to-nearest -
+// dfix[i] = A[i][i] - sum_k L[i][k]^2 before the tensor-core GEMM, written back after it.  One warp per row.
+__global__ void __launch_bounds__(256) diag_fix_pre_kernel(const float* __restrict__ A, int ld, int row0, int nrows,
+                                                           int col0, int ncols, float* __restrict__ dfix) {
+    const int r = row0 + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= row0 + nrows) return;
+    const int lane = threadIdx.x & 31;
+    const float* p = A + (long long)r * ld + col0;
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = lane * 4; c < ncols; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(p + c);
+        s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1);
+        s0 = fmaf(v.z, v.z, s0); s1 = fmaf(v.w, v.w, s1);
+    }
+    const float s = warp_sum(s0 + s1);
+    if (lane == 0) dfix[r] = A[(long long)r * ld + r] - s;
+}
+__global__ void __launch_bounds__(256) diag_fix_post_kernel(float* __restrict__ A, int ld, int row0, int nrows,
+                                                            const float* __restrict__ dfix) {
+    const int r = row0 + blockIdx.x * 256 + threadIdx.x;
+    if (r < row0 + nrows) A[(long long)r * ld + r] = dfix[r];
+}
+
+// Blocked Cholesky with the trailing update on the tensor cores.  Lh/Ll receive the tf32 split of every
+// sub-diagonal panel of L (what the deferred updates and, later, the triangular inverse read as operands).
+static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* dfix, int K, int ld, int* info,
+                             cudaStream_t st) {
+    const size_t smem = (2 * NB * LDS_ + 64 * 65 + NB) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_last_error("potrf smem attr", e); return QT_ERR_CUDA; }
+    LookAhead& la = lookahead(st);
+    bool potrf_ahead = false;
+    for (int ob = 0; ob < K; ob += OB) {
+        const int oe = (ob + OB) < K ? (ob + OB) : K;
+        for (int k = ob; k < oe; k += NB) {
+            const int nb = (K - k) < NB ? (K - k) : NB;
+            if (potrf_ahead) {
+                if (cudaStreamWaitEvent(st, la.potrf_done, 0) != cudaSuccess) return QT_ERR_CUDA;
+            } else {
+                potrf_inv_kernel<<<1, 256, smem, st>>>(A, X, ld, nb, k, info);
+                int rc = check_launch("potrf_inv");
+                if (rc) return rc;
+            }
+            potrf_ahead = false;
+            const int rem = K - k - nb;
+            if (rem <= 0) break;
+            float* P = A + (long long)(k + nb) * ld + k;
+            GemmArgs t{};  // TRSM as GEMM: P <- P * (L_kk^-1)^T, in place
+            t.A = P; t.B = X + (long long)k * ld + k; t.C = P;
+            t.M = rem; t.N = nb; t.Kd = nb; t.lda = t.ldb = t.ldc = ld;
+            t.alpha = 1.f; t.beta = 0.f;
+            int rc = sgemm(true, t, 1, st);
+            if (rc) return rc;
+            const long long poff = (long long)(k + nb) * ld + k;
+            rc = split_block(false, P, ld, Lh + poff, Ll + poff, ld, rem, nb, 0, 1, 0, 0, st);
+            if (rc) return rc;
+            // inner SYRK (FFMA): only the columns of this outer block, next panel column first
+            const int n_in = oe - (k + nb);
+            if (n_in <= 0) continue;
+            const int nb2 = n_in < NB ? n_in : NB;
+            GemmArgs s1{};
+            s1.A = P; s1.B = P; s1.C = A + (long long)(k + nb) * ld + (k + nb);
+            s1.M = rem; s1.N = nb2; s1.Kd = nb; s1.lda = s1.ldb = s1.ldc = ld;
+            s1.alpha = -1.f; s1.beta = 1.f; s1.lower_tiles_only = 1;
+            rc = sgemm(true, s1, 1, st);
+            if (rc) return rc;
+            if (la.ok) {
+                if (cudaEventRecord(la.panel_ready, st) != cudaSuccess) return QT_ERR_CUDA;
+                if (cudaStreamWaitEvent(la.side, la.panel_ready, 0) != cudaSuccess) return QT_ERR_CUDA;
+                potrf_inv_kernel<<<1, 256, smem, la.side>>>(A, X, ld, nb2, k + nb, info);
+                rc = check_launch("potrf_inv(look-ahead)");
+                if (rc) return rc;
+                if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
+                potrf_ahead = true;
+            }
+            const int n_in2 = n_in - nb2;
+            if (n_in2 > 0) {
+                float* P2 = P + (long long)nb2 * ld;
+                GemmArgs s2{};
+                s2.A = P2; s2.B = P2; s2.C = A + (long long)(k + nb + nb2) * ld + (k + nb + nb2);
+                s2.M = rem - nb2; s2.N = n_in2; s2.Kd = nb; s2.lda = s2.ldb = s2.ldc = ld;
+                s2.alpha = -1.f; s2.beta = 1.f; s2.lower_tiles_only = 1;
+                rc = sgemm(true, s2, 1, st);
+                if (rc) return rc;
+            }
+        }
+        // deferred update of everything right of this outer block: A[oe:, oe:] -= L[oe:, ob:oe] L[oe:, ob:oe]^T
+        const int remo = K - oe;
+        if (remo <= 0) break;
+        diag_fix_pre_kernel<<<(remo + 7) / 8, 256, 0, st>>>(A, ld, oe, remo, ob, oe - ob, dfix);
+        int rcd = check_launch("diag_fix_pre");
+        if (rcd) return rcd;
+        tgemm::Problem p;
+        p.A = {Lh, Ll, K, oe, ld};
+        p.B = p.A;
+        p.C = A; p.c_rows = K; p.c_cols = K; p.ldc = ld;
+        p.Kd = oe - ob;
+        p.a_col0 = p.b_col0 = ob;
+        p.negate = true; p.accumulate = true; p.lower_tiles_only = true;
+        // next panel column first, so that its diagonal block can be factored underneath the rest
+        const int nb2 = remo < NB ? remo : NB;
+        p.M = remo; p.N = nb2;
+        p.a_row0 = p.b_row0 = p.c_row0 = p.c_col0 = oe;
+        int rc = tgemm::launch(p, st);
+        if (rc) return rc;
+        diag_fix_post_kernel<<<1, 256, 0, st>>>(A, ld, oe, nb2, dfix);
+        rc = check_launch("diag_fix_post");
+        if (rc) return rc;
+        if (la.ok && remo > nb2) {
+            if (cudaEventRecord(la.panel_ready, st) != cudaSuccess) return QT_ERR_CUDA;
+            if (cudaStreamWaitEvent(la.side, la.panel_ready, 0) != cudaSuccess) return QT_ERR_CUDA;
+            potrf_inv_kernel<<<1, 256, smem, la.side>>>(A, X, ld, nb2, oe, info);
+            rc = check_launch("potrf_inv(look-ahead)");
+            if (rc) return rc;
+            if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
+            potrf_ahead = true;
+        }
+        if (remo > nb2) {
+            p.M = remo - nb2; p.N = remo - nb2;
+            p.a_row0 = p.b_row0 = p.c_row0 = p.c_col0 = oe + nb2;
+            rc = tgemm::launch(p, st);
+            if (rc) return rc;
+            diag_fix_post_kernel<<<(remo - nb2 + 255) / 256, 256, 0, st>>>(A, ld, oe + nb2, remo - nb2, dfix);
+            rc = check_launch("diag_fix_post");
+            if (rc) return rc;
+        }
+    }
+    return QT_OK;
+}
+
+// Triangular inverse with the block merges (levels >= 256) on the tensor cores.  Per pair [[A,0],[C,B]]:
+//   P = split(X11^T) (upper), S = P C^T, X21 = -X22 S^T - every product contracts over operand columns.
+// Dh/Dl hold the operand splits: diagonal positions = P / X22, the (a0, b0) off-diagonal position = S.
+static int trtri_lower_tc(const float* L, float* X, float* W, const float* Lh, const float* Ll, float* Dh, float* Dl,
+                          int K, int ld, cudaStream_t st) {
+    for (long long s = NB; s < K; s *= 2) {
+        const long long nblk = (K + s - 1) / s;
+        const long long npairs = nblk / 2;
+        if (npairs == 0) break;
+        const long long lastB0 = (2 * (npairs - 1) + 1) * s;
+        const long long lastSB = (K - lastB0) < s ? (K - lastB0) : s;
+        const long long nfull = (lastSB == s) ? npairs : npairs - 1;
+        for (int pass = 0; pass < 2; pass++) {
+            const long long batch = pass == 0 ? nfull : (npairs - nfull);
+            if (batch <= 0) continue;
+            const long long p0 = pass == 0 ? 0 : nfull;
+            const long long sB = pass == 0 ? s : lastSB;
+            const long long a0 = 2 * p0 * s, b0 = a0 + s;
+            const long long stride = 2 * s * ((long long)ld + 1);
+            int rc;
+            if (s < 256) {
+                GemmArgs g1{};  // T = C * A^-1
+                g1.A = L + b0 * ld + a0; g1.B = X + a0 * ld + a0; g1.C = W + b0 * ld + a0;
+                g1.M = (int)sB; g1.N = (int)s; g1.Kd = (int)s; g1.lda = g1.ldb = g1.ldc = ld;
+                g1.alpha = 1.f; g1.beta = 0.f; g1.b_lower_tri = 1;
+                g1.strideA = g1.strideB = g1.strideC = stride;
+                rc = sgemm(false, g1, (int)batch, st);
+                if (rc) return rc;
+                GemmArgs g2{};  // X[C] = -B^-1 * T
+                g2.A = X + b0 * ld + b0; g2.B = W + b0 * ld + a0; g2.C = X + b0 * ld + a0;
+                g2.M = (int)sB; g2.N = (int)s; g2.Kd = (int)sB; g2.lda = g2.ldb = g2.ldc = ld;
+                g2.alpha = -1.f; g2.beta = 0.f; g2.a_lower_tri = 1;
+                g2.strideA = g2.strideB = g2.strideC = stride;
+                rc = sgemm(false, g2, (int)batch, st);
+                if (rc) return rc;
+                continue;
+            }
+            const int is = (int)s, isB = (int)sB, ia0 = (int)a0, ib0 = (int)b0, step = (int)(2 * s);
+            // P = split(X11^T) at (a0, a0); X22 split at (b0, b0)
+            rc = split_block(true, X + a0 * ld + a0, ld, Dh + a0 * ld + a0, Dl + a0 * ld + a0, ld, is, is, 1, (int)batch,
+                             stride, stride, st);
+            if (rc) return rc;
+            rc = split_block(false, X + b0 * ld + b0, ld, Dh + b0 * ld + b0, Dl + b0 * ld + b0, ld, isB, isB, 1,
+                             (int)batch, stride, stride, st);
+            if (rc) return rc;
+            tgemm::Problem g;   // S[i][l] = sum_k P[i][k] C[l][k]   -> W at (a0, b0)
+            g.A = {Dh, Dl, K, K, ld};
+            g.B = {Lh, Ll, K, K, ld};
+            g.C = W; g.c_rows = K; g.c_cols = K; g.ldc = ld;
+            g.M = is; g.N = isB; g.Kd = is;
+            g.a_row0 = ia0; g.a_col0 = ia0; g.b_row0 = ib0; g.b_col0 = ia0; g.c_row0 = ia0; g.c_col0 = ib0;
+            g.batch = (int)batch;
+            g.a_sr = g.a_sc = g.b_sr = g.b_sc = g.c_sr = g.c_sc = step;
+            g.a_tri = 2;
+            rc = tgemm::launch(g, st);
+            if (rc) return rc;
+            rc = split_block(false, W + a0 * ld + b0, ld, Dh + a0 * ld + b0, Dl + a0 * ld + b0, ld, is, isB, 0, (int)batch,
+                             stride, stride, st);
+            if (rc) return rc;
+            tgemm::Problem h;   // X21[j][i] = -sum_l X22[j][l] S[i][l]   -> X at (b0, a0)
+            h.A = {Dh, Dl, K, K, ld};
+            h.B = {Dh, Dl, K, K, ld};
+            h.C = X; h.c_rows = K; h.c_cols = K; h.ldc = ld;
+            h.M = isB; h.N = is; h.Kd = isB;
+            h.a_row0 = ib0; h.a_col0 = ib0; h.b_row0 = ia0; h.b_col0 = ib0; h.c_row0 = ib0; h.c_col0 = ia0;
+            h.batch = (int)batch;
+            h.a_sr = h.a_sc = h.b_sr = h.b_sc = h.c_sr = h.c_sc = step;
+            h.a_tri = 1;
+            h.negate = true;
+            rc = tgemm::launch(h, st);
+            if (rc) return rc;
+        }
+    }
+    return QT_OK;
+}
+
 }  // namespace linalg
 }  // namespace qt
 
@@ -484,6 +752,32 @@ int qt_gptq_hinv_factor(float* A, float* X, float* W, int K, int* info, void* st
     int rc = cholesky_lower(A, X, K, K, info, st);
     if (rc) return rc;
     rc = trtri_lower(A, X, W, K, K, st);
+    if (rc) return rc;
+    dim3 grid((K + 255) / 256, K);
+    flip_upper_kernel<<<grid, 256, 0, st>>>(X, A, K);
+    return check_launch("flip_upper");
+}
+
+// Tensor-core variant of qt_gptq_hinv_factor: same contract plus four more K x K fp32 workspaces (tf32 splits of
+// L and of the inverse blocks).  K % 256 == 0.  stages: bit 0 = Cholesky trailing updates on the tensor cores,
+// bit 1 = triangular-inverse merges on the tensor cores (3 = both; the other stage runs the FFMA GEMMs).
+int qt_gptq_hinv_factor_tc(float* A, float* X, float* W, float* Lh, float* Ll, float* Dh, float* Dl, int K, int* info,
+                           int stages, void* stream) {
+    if (!A || !X || !W || !Lh || !Ll || !Dh || !Dl || !info || K <= 0 || (K & 255)) return QT_ERR_INVALID;
+    if (((uintptr_t)A | (uintptr_t)X | (uintptr_t)W | (uintptr_t)Lh | (uintptr_t)Ll | (uintptr_t)Dh | (uintptr_t)Dl) & 15)
+        return QT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+    if (e != cudaSuccess) { set_last_error("memset info", e); return QT_ERR_CUDA; }
+    int rc;
+    if (stages & 1) {
+        rc = cholesky_lower_tc(A, X, Lh, Ll, W, K, K, info, st);   // W's first row holds the diagonal fix-ups
+    } else {
+        rc = cholesky_lower(A, X, K, K, info, st);
+        if (!rc && (stages & 2)) rc = split_block(false, A, K, Lh, Ll, K, K, K, 1, 1, 0, 0, st);
+    }
+    if (rc) return rc;
+    rc = (stages & 2) ? trtri_lower_tc(A, X, W, Lh, Ll, Dh, Dl, K, K, st) : trtri_lower(A, X, W, K, K, st);
     if (rc) return rc;
     dim3 grid((K + 255) / 256, K);
     flip_upper_kernel<<<grid, 256, 0, st>>>(X, A, K);

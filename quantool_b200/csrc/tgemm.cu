@@ -5,12 +5,20 @@
 // llmcompressor gptq_quantize.py, i.e. the trailing SYRK updates of the blocked Cholesky and the
 // block merges of the triangular inverse, which were FFMA GEMMs at ~50 TFLOP/s in the first version.
 //
-// tcgen05 kind::tf32 with operand splitting ("3xTF32"): x = hi + lo, hi = tf32(x) exact, lo = x - hi, and
+// tcgen05 kind::tf32 with operand splitting ("3xTF32"): x ~= hi + lo, hi = tf32(x), lo = tf32(x - hi) (about 22 mantissa bits), and
 //     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi   (dropped lo*lo term ~2^-22 relative), fp32 accumulation in TMEM.
 // Callers hand in the split operands (they are produced once per panel / block by the split kernels and reused
 // by many tiles).  Same pipeline as the lazy-batch kernel (lazy_gemm.cu), generalised: arbitrary inner
 // dimension, batches of diagonal blocks, triangular operands (k range trimmed per tile), lower-tiles-only
 // SYRK, and two epilogues - TMA store (C =) or TMA reduce-add in L2 (C +=), so C is never read by the SM.
+//
+// Accuracy note (measured): the tensor cores add into the fp32 TMEM accumulator with truncation, so a long
+// accumulation chain drifts: with one 3 x Kd/8-instruction chain per tile the inverse factor at K = 14336 was
+// 2.8e-5 away from the FFMA result, and the error is linear in the chain length (8.1e-6 / 4.7e-6 / 2.4e-6 /
+// 1.3e-6 at 1024 / 512 / 256 / 128).  The chain is therefore cut every `max_chain` = 128 k: each partial sum goes
+// to C through the TMA (first one stored, the rest reduce-added in L2 with round-to-nearest, strictly in order, so
+// the result is deterministic).  At 128 the factor is within 2x of the FFMA chain's distance to fp64 (K = 4096:
+// 5.0e-7 vs 2.8e-7) for 9 % of the chain time.
 //
 // Tile 128 x 256, k chunks of 32 floats (one 128-byte swizzle row); stage = A_hi,A_lo (2 x 16 KB) + B_hi,B_lo
 // (2 x 32 KB) = 96 KB, 2 stages; 2 TMEM accumulators (2 x 256 columns); warp 0 = TMA producer, warp 1 = MMA
@@ -45,6 +53,7 @@ struct Args {
     int a_row0, a_col0, b_row0, b_col0, c_row0, c_col0;
     int a_sr, a_sc, b_sr, b_sc, c_sr, c_sc;
     int accumulate, lower_only, a_tri, b_tri;
+    int chain_kc;   // k chunks accumulated in TMEM before the partial sum is flushed to C (see Problem::max_chain)
     uint32_t idesc;
 };
 
@@ -114,7 +123,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
                 if (!decode(a, t, tl)) continue;
                 const int ra = a.a_row0 + tl.b * a.a_sr + tl.tm * BM, ca = a.a_col0 + tl.b * a.a_sc;
                 const int rb = a.b_row0 + tl.b * a.b_sr + tl.tn * BN, cb = a.b_col0 + tl.b * a.b_sc;
-                for (int kc = tl.kc0; kc < tl.kc1; kc++, it++) {
+                for (int kc = tl.kc0; kc < tl.kc1; kc++, it++) {   // sub-ranges need no special handling here
                     const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&empty[stage], ph ^ 1);
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -132,33 +141,36 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
             Tile tl;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 if (!decode(a, t, tl)) continue;
-                const uint32_t acc = li & 1, aph = (li >> 1) & 1;
-                li++;
-                mbar_wait(&tempty[acc], aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kc = tl.kc0; kc < tl.kc1; kc++, it++) {
-                    const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&full[stage], ph);
+                for (int k0 = tl.kc0; k0 < tl.kc1; k0 += a.chain_kc) {
+                    const int k1 = min(k0 + a.chain_kc, tl.kc1);
+                    const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+                    li++;
+                    mbar_wait(&tempty[acc], aph ^ 1);
                     tc_fence_after();
-                    const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sa_lo = sa_hi + A_BYTES;
-                    const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
-                    const uint32_t sb_lo = sb_hi + B_BYTES;
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kc = k0; kc < k1; kc++, it++) {
+                        const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
+                        mbar_wait(&full[stage], ph);
+                        tc_fence_after();
+                        const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t sa_lo = sa_hi + A_BYTES;
+                        const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+                        const uint32_t sb_lo = sb_hi + B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < KC / UMMA_K; k++) {
-                        // K-major SW128: rows of 128 B, 8-row groups 1 KB apart; k-step = 32 B inside the row
-                        const uint64_t ahi = make_desc_sw128(sa_hi + k * UMMA_K * 4, 16, 1024);
-                        const uint64_t alo = make_desc_sw128(sa_lo + k * UMMA_K * 4, 16, 1024);
-                        const uint64_t bhi = make_desc_sw128(sb_hi + k * UMMA_K * 4, 16, 1024);
-                        const uint64_t blo = make_desc_sw128(sb_lo + k * UMMA_K * 4, 16, 1024);
-                        tc_mma_tf32(d_tmem, ahi, bhi, a.idesc, (kc > tl.kc0 || k > 0) ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, ahi, blo, a.idesc, 1u);
-                        tc_mma_tf32(d_tmem, alo, bhi, a.idesc, 1u);
+                        for (int k = 0; k < KC / UMMA_K; k++) {
+                            // K-major SW128: rows of 128 B, 8-row groups 1 KB apart; k-step = 32 B inside the row
+                            const uint64_t ahi = make_desc_sw128(sa_hi + k * UMMA_K * 4, 16, 1024);
+                            const uint64_t alo = make_desc_sw128(sa_lo + k * UMMA_K * 4, 16, 1024);
+                            const uint64_t bhi = make_desc_sw128(sb_hi + k * UMMA_K * 4, 16, 1024);
+                            const uint64_t blo = make_desc_sw128(sb_lo + k * UMMA_K * 4, 16, 1024);
+                            tc_mma_tf32(d_tmem, ahi, bhi, a.idesc, (kc > k0 || k > 0) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, ahi, blo, a.idesc, 1u);
+                            tc_mma_tf32(d_tmem, alo, bhi, a.idesc, 1u);
+                        }
+                        tc_commit(&empty[stage]);
                     }
-                    tc_commit(&empty[stage]);
+                    tc_commit(&tfull[acc]);
                 }
-                tc_commit(&tfull[acc]);
             }
         }
     } else {
@@ -168,41 +180,47 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
         Tile tl;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             if (!decode(a, t, tl)) continue;
-            const uint32_t acc = li & 1, aph = (li >> 1) & 1;
-            li++;
-            mbar_wait(&tfull[acc], aph);
-            tc_fence_after();
             const int row_local = tl.tm * BM + lg * 32;
             const int crow = a.c_row0 + tl.b * a.c_sr + row_local;
             const int ccol0 = a.c_col0 + tl.b * a.c_sc + tl.tn * BN;
-            if (row_local < a.M) {
+            for (int k0 = tl.kc0; k0 < tl.kc1; k0 += a.chain_kc) {
+                const uint32_t acc = li & 1, aph = (li >> 1) & 1;
+                li++;
+                mbar_wait(&tfull[acc], aph);
+                tc_fence_after();
+                // partial sums of one tile are applied in order: the previous flush must have completed
+                const bool first = (k0 == tl.kc0);
+                if (!first && lane == 0) bulk_wait<0>();
+                const bool add = a.accumulate || !first;
+                if (row_local < a.M) {
 #pragma unroll 1
-                for (int cc = 0; cc < BN / 32; cc++) {
-                    if (tl.tn * BN + cc * 32 >= a.N) break;
-                    uint32_t r[32];
-                    tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + cc * 32, r);
-                    uint8_t* buf = my + (nstore & 1) * 4096;
-                    nstore++;
-                    // the buffer used two stores ago must have been read by the TMA engine
-                    if (lane == 0) bulk_wait_read<1>();
-                    __syncwarp();
-                    // row = lane (128 B), 16-byte chunk c stored at c ^ (lane & 7): SWIZZLE_128B, conflict-free
+                    for (int cc = 0; cc < BN / 32; cc++) {
+                        if (tl.tn * BN + cc * 32 >= a.N) break;
+                        uint32_t r[32];
+                        tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + cc * 32, r);
+                        uint8_t* buf = my + (nstore & 1) * 4096;
+                        nstore++;
+                        // the buffer used two stores ago must have been read by the TMA engine
+                        if (lane == 0) bulk_wait_read<1>();
+                        __syncwarp();
+                        // row = lane (128 B), 16-byte chunk c stored at c ^ (lane & 7): SWIZZLE_128B, conflict-free
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const uint4 v = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (a.accumulate) tma_reduce_add_2d(&map_c, buf, ccol0 + cc * 32, crow);
-                        else tma_store_2d(&map_c, buf, ccol0 + cc * 32, crow);
-                        bulk_commit();
+                        for (int c = 0; c < 8; c++) {
+                            const uint4 v = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                            *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (add) tma_reduce_add_2d(&map_c, buf, ccol0 + cc * 32, crow);
+                            else tma_store_2d(&map_c, buf, ccol0 + cc * 32, crow);
+                            bulk_commit();
+                        }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(&tempty[acc]);
             }
-            tc_fence_before();
-            mbar_arrive(&tempty[acc]);
         }
         if (lane == 0) bulk_wait<0>();
     }
@@ -245,6 +263,7 @@ int launch(const Problem& p, cudaStream_t st) {
     a.c_row0 = p.c_row0; a.c_col0 = p.c_col0;
     a.a_sr = p.a_sr; a.a_sc = p.a_sc; a.b_sr = p.b_sr; a.b_sc = p.b_sc; a.c_sr = p.c_sr; a.c_sc = p.c_sc;
     a.accumulate = p.accumulate; a.lower_only = p.lower_tiles_only; a.a_tri = p.a_tri; a.b_tri = p.b_tri;
+    a.chain_kc = p.max_chain >= KC ? p.max_chain / KC : 1;
     a.idesc = p.negate ? make_idesc(true) : make_idesc(false);
     int dev = 0, nsm = kNumSMs;
     cudaGetDevice(&dev);

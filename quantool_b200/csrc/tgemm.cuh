@@ -28,6 +28,7 @@ struct Problem {
     bool lower_tiles_only = false; // skip 128x256 tiles entirely above the diagonal of C (SYRK)
     int a_tri = 0;                 // 1: A[m][k] = 0 for k > m (lower), 2: = 0 for k < m (upper) - k range is trimmed
     int b_tri = 0;                 // same for B[n][k]
+    int max_chain = 128;           // longest k span accumulated in TMEM before the partial sum is flushed to C
 };
 
 // stream-ordered; returns QT_OK / negative error code

@@ -16,28 +16,47 @@ from .schemes import WeightArgs
 
 class HessianAccumulator:
     """H = (2 / n_samples) * sum_b X_b^T X_b  (SURVEY §A.1).  Raw fp32 sums are kept on the device
-    (upper-triangle tiles only) and scaled/mirrored once in `finalize`."""
+    (upper-triangle tiles only) and scaled/mirrored once in `finalize`.  The diagonal is accumulated separately
+    in fp32 round-to-nearest (the tensor-core accumulator truncates, which would reorder argsort(diag H));
+    `sync_diagonal` writes it into H - call it before reducing H across ranks."""
 
     def __init__(self, K: int, device):
         self.K = K
         self.H = torch.zeros((K, K), dtype=torch.float32, device=device)
+        self.diag = torch.zeros((K,), dtype=torch.float32, device=device)
+        self._scratch = torch.empty((32 * K,), dtype=torch.float32, device=device)
         self.n_samples = 0
         self._final = False
+        self._diag_synced = True
 
-    def add(self, x: torch.Tensor, n_samples: Optional[int] = None) -> None:
-        """x: [B, S, K] or [T, K]; n_samples defaults to B (a 2-D input counts as one sample)."""
+    def add(self, x: torch.Tensor, n_samples: Optional[int] = None, syrk_events=None) -> None:
+        """x: [B, S, K] or [T, K]; n_samples defaults to B (a 2-D input counts as one sample).
+        syrk_events = (start, end) CUDA events recorded around the tensor-core SYRK launch alone."""
         assert not self._final
         if n_samples is None:
             n_samples = x.shape[0] if x.dim() == 3 else 1
         x2 = x.reshape(-1, x.shape[-1])
         if x2.dtype != torch.bfloat16:
             x2 = x2.to(torch.bfloat16)
-        cabi.hessian_accumulate(x2.contiguous(), self.H)
+        x2 = x2.contiguous()
+        if syrk_events is not None:
+            syrk_events[0].record()
+        cabi.hessian_accumulate(x2, self.H)
+        if syrk_events is not None:
+            syrk_events[1].record()
+        cabi.hessian_diag_accumulate(x2, self.diag, self._scratch)
+        self._diag_synced = False
         self.n_samples += int(n_samples)
+
+    def sync_diagonal(self) -> None:
+        if not self._diag_synced:
+            cabi.hessian_set_diagonal(self.H, self.diag)
+            self._diag_synced = True
 
     def finalize(self, total_samples: Optional[int] = None) -> torch.Tensor:
         n = total_samples if total_samples is not None else self.n_samples
         if not self._final:
+            self.sync_diagonal()
             cabi.hessian_finalize(self.H, 2.0 / max(n, 1))
             self._final = True
         return self.H
@@ -54,8 +73,10 @@ class GPTQResult:
 
 
 def quantize_linear(weight: torch.Tensor, H: torch.Tensor, args: WeightArgs, blocksize: int = 128,
-                    percdamp: float = 0.01, check_info: bool = True, tensor_core_lazy: bool = True) -> GPTQResult:
-    """weight [N, K] (CUDA, model dtype), H finalized [K, K] fp32.  H is not modified."""
+                    percdamp: float = 0.01, check_info: bool = True, tensor_core_lazy: bool = True,
+                    tensor_core_chain: Optional[bool] = None) -> GPTQResult:
+    """weight [N, K] (CUDA, model dtype), H finalized [K, K] fp32.  H is not modified.
+    tensor_core_chain: None = tensor-core inverse-Hessian chain whenever K allows (K % 256 == 0)."""
     if blocksize != 128:
         raise ValueError("the sm_100a GPTQ kernel is specialised for block_size=128 (upstream default)")
     N, K = weight.shape
@@ -86,7 +107,7 @@ def quantize_linear(weight: torch.Tensor, H: torch.Tensor, args: WeightArgs, blo
             zp = torch.empty((N, K // gs), dtype=torch.float32, device=dev)
 
     Hf, dead = cabi.gptq_prepare_hessian(H, perm, percdamp)
-    U, info = cabi.gptq_hinv_factor(Hf)
+    U, info = cabi.gptq_hinv_factor(Hf, tensor_core=tensor_core_chain)
     if check_info and int(info.item()) != 0:
         cabi.set_identity(U)   # upstream: on LinAlgError, Hinv = eye(K)
     wp = cabi.gptq_permute_in(weight, perm, dead)

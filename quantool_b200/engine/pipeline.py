@@ -145,8 +145,9 @@ class GPTQLayerQuantizer:
                                                            cabi._stream()), "qt_gptq_prepare_hessian")
             X = self._buf("X" + slot, (K, K), torch.float32, dev)
             W = self._buf("W" + slot, (K, K), torch.float32, dev)
-            cabi._check(cabi.lib().qt_gptq_hinv_factor(cabi._p(U), cabi._p(X), cabi._p(W), K, cabi._p(info),
-                                                       cabi._stream()), "qt_gptq_hinv_factor")
+            tc = cabi.hinv_tensor_core_ok(K)
+            ws = [self._buf(f"chain{i}" + slot, (K, K), torch.float32, dev) for i in range(4)] if tc else None
+            cabi.gptq_hinv_factor(U, X, W, tensor_core=tc, workspace=ws, info=info)
             self.launches += 2
         if d.on:
             d.broadcast(U, owner % d.world)
@@ -344,7 +345,9 @@ class GPTQLayerQuantizer:
                 st = self._streams[idx] = torch.cuda.Stream(device=dev)
             st.wait_event(ready)
             with torch.cuda.stream(st):
-                if self.dist.on and hessians[inp].shape[0] >= self.DIST_CHAIN_MIN_K:
+                Kin = hessians[inp].shape[0]
+                # the tensor-core chain on one rank (+ broadcast of U) beats the 2x2 FFMA block chain over all ranks
+                if self.dist.on and Kin >= self.DIST_CHAIN_MIN_K and not cabi.hinv_tensor_core_ok(Kin):
                     ctx = self.prepare_input_distributed(hessians[inp], slot=f"#{idx}")
                 else:
                     ctx = self.prepare_input(hessians[inp], owner=idx, slot=f"#{idx}")
@@ -384,6 +387,7 @@ def accumulate_layer_hessians(inputs: Dict[str, torch.Tensor], n_samples_local: 
     for name, x in inputs.items():
         acc = HessianAccumulator(x.shape[-1], x.device)
         acc.add(x, n_samples_local)
+        acc.sync_diagonal()
         dist.all_reduce_sum(acc.H)
         out[name] = acc.finalize(n_samples_total)
     return out
@@ -521,6 +525,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
         del cap
         hess = {}
         for n in dims:
+            accs[n].sync_diagonal()
             dist.all_reduce_sum(accs[n].H)
             hess[n] = accs[n].finalize(n_total)
             lq.launches += 1

@@ -71,9 +71,11 @@ def test_sgemm(M, N, Kd, nk):
     assert (C.double() - ref).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("K", [128, 384, 576, 1024, 2048])
+@pytest.mark.parametrize("K,tc", [(128, False), (384, False), (576, False), (1024, False), (2048, False),
+                                  (256, True), (1024, True), (2048, True), (2560, True), (3072, True)])
 @pytest.mark.parametrize("act", [False, True])
-def test_hinv_factor_vs_fp64(K, act):
+def test_hinv_factor_vs_fp64(K, tc, act):
+    """tc = the tensor-core (3xTF32) chain; the FFMA chain serves K that are not multiples of 256."""
     from quantool_b200 import cabi
     T = 4 * K
     x = _acts(T, K, seed=K)
@@ -81,7 +83,7 @@ def test_hinv_factor_vs_fp64(K, act):
     Hc = H.float().cuda()
     perm = torch.argsort(torch.diagonal(Hc), descending=True, stable=True).to(torch.int32) if act else None
     Hf, dead = cabi.gptq_prepare_hessian(Hc, perm, 0.01)
-    U, info = cabi.gptq_hinv_factor(Hf)
+    U, info = cabi.gptq_hinv_factor(Hf, tensor_core=tc)
     assert int(info.item()) == 0
     Hd = H.clone()
     if act:
@@ -100,7 +102,10 @@ def test_hinv_not_pd_reports_info():
     K = 256
     H = -torch.eye(K, device="cuda")
     Hf, _ = cabi.gptq_prepare_hessian(H, None, 0.0)
-    _, info = cabi.gptq_hinv_factor(Hf)
+    _, info = cabi.gptq_hinv_factor(Hf, tensor_core=False)
+    assert int(info.item()) != 0
+    Hf, _ = cabi.gptq_prepare_hessian(H, None, 0.0)
+    _, info = cabi.gptq_hinv_factor(Hf, tensor_core=True)
     assert int(info.item()) != 0
 
 
@@ -222,7 +227,10 @@ def test_lazy_update_tensor_core_tf32x3(M, K, i1, i2):
     cabi.sgemm(err, U[i1:i1 + 128, i2:], W_simt[:, i2:], alpha=-1.0, beta=1.0)
     uh, ul = cabi.split_tf32_transpose(U)
     eh, el = cabi.split_tf32(err)
-    assert torch.equal(uh + ul, U.t()) and torch.equal((uh.view(torch.int32) & 0x1FFF), torch.zeros_like(uh, dtype=torch.int32))
+    # both halves are tf32 values (low 13 mantissa bits clear) and together carry x to 2^-22 relative
+    for part in (uh, ul, eh, el):
+        assert torch.equal((part.view(torch.int32) & 0x1FFF), torch.zeros_like(part, dtype=torch.int32))
+    assert ((uh + ul - U.t()).abs() <= 2.0 ** -22 * U.t().abs()).all()
     W_tc = W.clone()
     cabi.gptq_lazy_update_tf32x3(eh, el, uh, ul, W_tc, i1, i2)
     assert torch.equal(W_tc[:, :i2], W[:, :i2])                       # untouched columns
