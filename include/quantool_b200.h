@@ -126,8 +126,8 @@ int qt_gptq_permute_in(const void* W, int dtype, const int* perm, const uint8_t*
 int qt_gptq_permute_out(const float* Wp, const int* inv_perm, void* out, int dtype, int N, int K, void* stream);
 /* blocked column loop (block 128).  mode 0: re-fit group qparams at group starts (group_size 32/64/128),
  * 1: static scales looked up through g_idx (actorder=weight), 2: one scale per row.  W in/out.
- * U_hi/U_lo (qt_split_tf32_transpose of U) non-NULL: lazy update on the tensor cores, err_scratch [2,N,128];
- * NULL: fp32 FFMA GEMM, err_scratch [N,128]. */
+ * U_hi/U_lo (qt_split_tf32_transpose of U) non-NULL: lazy update on the tensor cores, batched over 512-column
+ * outer blocks, err_scratch [2,N,512]; NULL: fp32 FFMA GEMM per block, err_scratch [N,128]. */
 int qt_gptq_quantize_weight(float* W, const float* U, const float* U_hi, const float* U_lo, float* err_scratch,
                             float* scale, float* zp, const int* g_idx, float* losses, int N, int K, int G,
                             int group_size, int num_bits, int symmetric, int mode, void* stream);

@@ -404,9 +404,9 @@ def gptq_quantize_weight(wp: torch.Tensor, U: torch.Tensor, scale: torch.Tensor,
     N, K = wp.shape
     G = scale.shape[1]
     losses = torch.zeros((N,), dtype=torch.float32, device=wp.device)
-    nerr = 2 if U_split is not None else 1
-    err = err_scratch if err_scratch is not None else torch.empty((nerr, N, 128), dtype=torch.float32, device=wp.device)
-    assert err.numel() >= nerr * N * 128
+    nerr = 2 * 512 if U_split is not None else 128      # tensor-core path keeps Err of a 512-column outer block
+    err = err_scratch if err_scratch is not None else torch.empty((nerr * N,), dtype=torch.float32, device=wp.device)
+    assert err.numel() >= nerr * N
     if g_idx is not None:
         g_idx = _dev(g_idx.to(torch.int32), "g_idx")
     uh, ul = U_split if U_split is not None else (None, None)

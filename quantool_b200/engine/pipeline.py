@@ -296,7 +296,7 @@ class GPTQLayerQuantizer:
                 scale, zp = cabi.minmax_qparams(wl.float(), gs, a.num_bits, a.symmetric)
                 self.launches += 1
             wp = cabi.gptq_permute_in(wl, ctx.perm, ctx.dead)
-            err = self._buf("err" + getattr(ctx, "slot", ""), (2, nloc, 128), torch.float32, dev)
+            err = self._buf("err" + getattr(ctx, "slot", ""), (2, nloc, 512), torch.float32, dev)
             losses = cabi.gptq_quantize_weight(wp, ctx.U, scale, zp, g_idx_perm, gs, a.num_bits, a.symmetric, mode,
                                                err_scratch=err, U_split=ctx.U_split)
             wq = cabi.gptq_permute_out(wp, ctx.inv_perm, weight.dtype)

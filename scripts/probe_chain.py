@@ -30,4 +30,11 @@ for K in (4096, 14336):
     def loop_tc():
         wq = wp.clone(); cabi.gptq_quantize_weight(wq, U, scale, zp, None, 128, 4, True, 0, U_split=us)
     print(f"gptq loop (tcgen05 tf32x3 lazy) N={N} K={K}: {timeit(loop_tc):.2f} ms", flush=True)
+    if K == 4096:
+        N2 = 14336
+        w2 = (torch.randn((N2,K), device="cuda")*0.02).to(torch.bfloat16)
+        wp2 = cabi.gptq_permute_in(w2, perm, dead); scale2 = torch.empty((N2,K//128), device="cuda"); zp2 = torch.empty_like(scale2)
+        def loop_tc2():
+            wq = wp2.clone(); cabi.gptq_quantize_weight(wq, U, scale2, zp2, None, 128, 4, True, 0, U_split=us)
+        print(f"gptq loop (tcgen05 tf32x3 lazy) N={N2} K={K}: {timeit(loop_tc2):.2f} ms", flush=True)
     del H, X, W, Hf, U; torch.cuda.empty_cache()
