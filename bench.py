@@ -481,5 +481,26 @@ def main():
         d.dist.destroy_process_group()
 
 
+def _run_with_clean_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is
+    written to the saved descriptor at the end."""
+    import io
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    py_stdout, sys.stdout = sys.stdout, buf
+    try:
+        main()
+    finally:
+        sys.stdout = py_stdout
+        os.dup2(real, 1)
+        os.close(real)
+        out = buf.getvalue()
+        if out:
+            os.write(1, out.encode())
+
+
 if __name__ == "__main__":
-    main()
+    _run_with_clean_stdout()
