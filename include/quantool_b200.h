@@ -59,6 +59,12 @@ int qt_gguf_block_bytes(int ggml_type);
  * HF -> model.f16.gguf -> llama-quantize chain does (llama_cpp.py:207,238). */
 int qt_gguf_quantize(int ggml_type, const void* src, int src_dtype, int round_via_f16, int64_t nrows,
                      int64_t ncols, void* dst, void* stream);
+/* Many tensors of one type in ONE launch (a model is hundreds of small tensors; llama-quantize walks them in a
+ * loop, llama_cpp.py:165-178).  src[i]/dst[i]: device pointers, nelems[i]: elements of tensor i; table_dev: device
+ * scratch of qt_gguf_batch_table_bytes(n) bytes. */
+int64_t qt_gguf_batch_table_bytes(int n);
+int qt_gguf_quantize_batch(int ggml_type, int n, const void* const* src, const int64_t* nelems, void* const* dst,
+                           int src_dtype, int round_via_f16, void* table_dev, void* stream);
 int qt_gguf_dequantize(int ggml_type, const void* src, int64_t nrows, int64_t ncols, float* dst, void* stream);
 
 unsigned long long qt_launch_count(void);   /* kernel launches issued through this library since load */

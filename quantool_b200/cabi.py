@@ -28,6 +28,8 @@ _SIGS = {
     "qt_gguf_block_elems": [_i32],
     "qt_gguf_block_bytes": [_i32],
     "qt_gguf_quantize": [_i32, _vp, _i32, _i32, _i64, _i64, _vp, _vp],
+    "qt_gguf_batch_table_bytes": [_i32],
+    "qt_gguf_quantize_batch": [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp],
     "qt_gguf_dequantize": [_i32, _vp, _i64, _i64, _vp, _vp],
     "qt_minmax_qparams": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "qt_quantize_codes": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
@@ -66,7 +68,8 @@ _SIGS = {
     "qt_split_tf32_transpose": [_vp, _vp, _vp, _i32, _vp],
     "qt_gptq_lazy_update_tf32x3": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
 }
-_RESTYPE = {"qt_last_error": ctypes.c_char_p, "qt_launch_count": ctypes.c_ulonglong}
+_RESTYPE = {"qt_last_error": ctypes.c_char_p, "qt_launch_count": ctypes.c_ulonglong,
+            "qt_gguf_batch_table_bytes": ctypes.c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -148,6 +151,58 @@ def gguf_quantize(x: torch.Tensor, qtype: str, round_via_f16: bool = True,
     with torch.cuda.device(x.device):
         _check(lib().qt_gguf_quantize(GGML[qtype], _p(x), _DT[x.dtype], int(round_via_f16), nrows, ncols,
                                       _p(out), _stream()), "qt_gguf_quantize")
+    return out
+
+
+def gguf_quantize_batch(xs, qtype: str, round_via_f16: bool = True, outs=None):
+    """Many 2-D tensors (same dtype, same device) -> packed blocks of one type in ONE kernel launch."""
+    if not xs:
+        return []
+    be, bb = gguf_block_elems(qtype), gguf_block_bytes(qtype)
+    dev, dt = xs[0].device, xs[0].dtype
+    for x in xs:
+        _dev(x, "x")
+        if x.dim() != 2 or x.device != dev or x.dtype != dt:
+            raise QtError("gguf_quantize_batch takes 2-D tensors of one dtype on one device")
+        if x.shape[1] % be:
+            raise QtError(f"ncols={x.shape[1]} is not a multiple of the {qtype} block size {be}")
+    n = len(xs)
+    sizes = [x.numel() // be * bb for x in xs]
+    if outs is None:
+        # one allocation for the whole group; the per-tensor views are made after the launch, while it runs
+        offs, total = [], 0
+        for sz in sizes:
+            offs.append(total)
+            total += (sz + 15) & ~15
+        buf = torch.empty((max(total, 1),), dtype=torch.uint8, device=dev)
+        base = buf.data_ptr()
+        dst = (ctypes.c_void_p * n)(*[base + o for o in offs])
+    else:
+        buf = None
+        dst = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    src = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+    nel = (ctypes.c_int64 * n)(*[x.numel() for x in xs])
+    table = torch.empty((int(lib().qt_gguf_batch_table_bytes(n)),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().qt_gguf_quantize_batch(GGML[qtype], n, src, nel, dst, _DT[dt], int(round_via_f16), _p(table),
+                                            _stream()), "qt_gguf_quantize_batch")
+    if buf is not None:
+        outs = [buf[o:o + sz].view(x.shape[0], -1) if sz else torch.empty((x.shape[0], x.shape[1] // be * bb),
+                                                                           dtype=torch.uint8, device=dev)
+                for x, o, sz in zip(xs, offs, sizes)]
+    return outs
+
+
+def gguf_quantize_many(plan, round_via_f16: bool = True):
+    """plan: list of (tensor, qtype).  One launch per (qtype, dtype, device) group; results in plan order."""
+    groups = {}
+    for i, (x, qt) in enumerate(plan):
+        groups.setdefault((qt, x.dtype, x.device), []).append(i)
+    out = [None] * len(plan)
+    for (qt, _, _), idx in groups.items():
+        ys = gguf_quantize_batch([plan[i][0] for i in idx], qt, round_via_f16)
+        for i, y in zip(idx, ys):
+            out[i] = y
     return out
 
 

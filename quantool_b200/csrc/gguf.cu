@@ -18,6 +18,8 @@
 // K-quants (256-element super-blocks) run a 19-21 candidate scale search per sub-block with
 //   strictly ordered fp32 sums: ~500 ALU ops per element, so they are fp32-ALU-bound, not
 //   HBM-bound; one thread owns one sub-block, input/output staged through shared memory.
+#include <vector>
+
 #include "gguf_kquant.cuh"
 
 namespace qt {
@@ -61,6 +63,27 @@ QT_D void copy_out(uint8_t* __restrict__ gdst, const uint8_t* sout, int bytes) {
 // slow path), and float->int truncation of the non-negative codes uses a round-down magic add
 // instead of the quarter-rate F2I.
 // ---------------------------------------------------------------------------------------
+// One launch can pack many tensors of the same type ("segments"): a model is hundreds of small tensors and a
+// launch per tensor made BASELINE config 1 (SmolLM2-135M, 211 tensors) launch-bound (3.2 ms for 0.4 GB).
+// A tile = the work of one CTA iteration; tile_start[] is the exclusive prefix sum of tiles per segment.
+struct Seg { const void* src; uint8_t* dst; long long n; };   // n = blocks (32-element types) or super-blocks
+struct Segs {
+    int nseg, total_tiles;
+    const int* tile_start;   // device [nseg + 1]; unused when nseg == 1
+    const Seg* table;        // device [nseg];     unused when nseg == 1
+    Seg one;
+};
+QT_D Seg seg_of(const Segs& s, int tile, int& local_tile) {
+    if (s.nseg == 1) { local_tile = tile; return s.one; }
+    int lo = 0, hi = s.nseg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(s.tile_start + mid) <= tile) lo = mid; else hi = mid - 1;
+    }
+    local_tile = tile - __ldg(s.tile_start + lo);
+    return s.table[lo];
+}
+
 constexpr int kSimpleU = 4;
 constexpr int kSimpleBlocksPerCta = 64 * kSimpleU;  // 256 blocks: 256*BB is a multiple of 16
 
@@ -202,8 +225,7 @@ QT_D void pack_simple_block(const float (&v)[8], int q, uint8_t* o) {
 }
 
 template <int TYPE, int DT, bool VIA_F16>
-__global__ void __launch_bounds__(256) pack_simple_kernel(const void* __restrict__ src,
-                                                          uint8_t* __restrict__ dst, int64_t nblocks) {
+__global__ void __launch_bounds__(256) pack_simple_kernel(const Segs segs) {
     // Each warp owns 32 consecutive blocks per iteration (8 blocks x kSimpleU passes): 32*BB bytes
     // of output is a multiple of 16 for every type, so the warp stages and stores its own slice
     // and the CTA never synchronises - warps drift apart and cover each other's load latency.
@@ -213,8 +235,14 @@ __global__ void __launch_bounds__(256) pack_simple_kernel(const void* __restrict
     __shared__ __align__(16) uint8_t sout[kSimpleBlocksPerCta * BB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3, bl = lane >> 2;
     uint8_t* wout = sout + warp * kWarpBlocks * BB;
-    for (int64_t base = (int64_t)blockIdx.x * kSimpleBlocksPerCta + warp * kWarpBlocks; base < nblocks;
-         base += (int64_t)gridDim.x * kSimpleBlocksPerCta) {
+    for (int tile = blockIdx.x; tile < segs.total_tiles; tile += gridDim.x) {
+        int lt;
+        const Seg sg = seg_of(segs, tile, lt);
+        const void* __restrict__ src = sg.src;
+        uint8_t* __restrict__ dst = sg.dst;
+        const int64_t nblocks = sg.n;
+        const int64_t base = (int64_t)lt * kSimpleBlocksPerCta + warp * kWarpBlocks;
+        if (base >= nblocks) continue;     // warp-uniform; this kernel has no CTA-wide barrier
         float v[kSimpleU][8];
         const bool full = base + kWarpBlocks <= nblocks;
         if (full) {
@@ -289,15 +317,19 @@ constexpr int kK45Nsb = 32;  // 256 threads, 32 super-blocks (8192 elements) per
 constexpr int kK6Nsb = 16;   // 256 threads, 16 super-blocks (4096 elements)
 
 template <int TYPE, int DT, bool VIA_F16>
-__global__ void __launch_bounds__(256) pack_k45_kernel(const void* __restrict__ src, uint8_t* __restrict__ dst,
-                                                       int64_t nsuper) {
+__global__ void __launch_bounds__(256) pack_k45_kernel(const Segs segs) {
     constexpr int BB = block_bytes(TYPE);
     using S = kq::K45Shared<kK45Nsb, BB>;
     __shared__ S s;
     const int t = threadIdx.x;
     constexpr int nmax = TYPE == T_Q4_K ? 15 : 31;
-    for (int64_t base = (int64_t)blockIdx.x * kK45Nsb; base < nsuper; base += (int64_t)gridDim.x * kK45Nsb) {
-        const int64_t left = nsuper - base;
+    for (int tile = blockIdx.x; tile < segs.total_tiles; tile += gridDim.x) {
+        int lt;
+        const Seg sg = seg_of(segs, tile, lt);
+        const void* __restrict__ src = sg.src;
+        uint8_t* __restrict__ dst = sg.dst;
+        const int64_t base = (int64_t)lt * kK45Nsb;
+        const int64_t left = sg.n - base;
         const int nvalid = left < kK45Nsb ? (int)left : kK45Nsb;
         stage_in<DT, VIA_F16, 32, 33, kK45Nsb * 256>(src, base * 256, (int64_t)nvalid * 256, s.u.x);
         __syncthreads();
@@ -315,13 +347,17 @@ __global__ void __launch_bounds__(256) pack_k45_kernel(const void* __restrict__ 
 }
 
 template <int DT, bool VIA_F16>
-__global__ void __launch_bounds__(256) pack_q6k_kernel(const void* __restrict__ src, uint8_t* __restrict__ dst,
-                                                       int64_t nsuper) {
+__global__ void __launch_bounds__(256) pack_q6k_kernel(const Segs segs) {
     using S = kq::K6Shared<kK6Nsb>;
     __shared__ S s;
     const int t = threadIdx.x;
-    for (int64_t base = (int64_t)blockIdx.x * kK6Nsb; base < nsuper; base += (int64_t)gridDim.x * kK6Nsb) {
-        const int64_t left = nsuper - base;
+    for (int tile = blockIdx.x; tile < segs.total_tiles; tile += gridDim.x) {
+        int lt;
+        const Seg sg = seg_of(segs, tile, lt);
+        const void* __restrict__ src = sg.src;
+        uint8_t* __restrict__ dst = sg.dst;
+        const int64_t base = (int64_t)lt * kK6Nsb;
+        const int64_t left = sg.n - base;
         const int nvalid = left < kK6Nsb ? (int)left : kK6Nsb;
         stage_in<DT, VIA_F16, 16, 17, kK6Nsb * 256>(src, base * 256, (int64_t)nvalid * 256, s.x);
         __syncthreads();
@@ -338,14 +374,18 @@ __global__ void __launch_bounds__(256) pack_q6k_kernel(const void* __restrict__ 
 }
 
 template <int TYPE, int DT, bool VIA_F16>
-__global__ void __launch_bounds__(256) pack_k23_kernel(const void* __restrict__ src, uint8_t* __restrict__ dst,
-                                                       int64_t nsuper) {
+__global__ void __launch_bounds__(256) pack_k23_kernel(const Segs segs) {
     constexpr int BB = block_bytes(TYPE);
     using S = kq::K23Shared<kK6Nsb, BB>;
     __shared__ S s;
     const int t = threadIdx.x;
-    for (int64_t base = (int64_t)blockIdx.x * kK6Nsb; base < nsuper; base += (int64_t)gridDim.x * kK6Nsb) {
-        const int64_t left = nsuper - base;
+    for (int tile = blockIdx.x; tile < segs.total_tiles; tile += gridDim.x) {
+        int lt;
+        const Seg sg = seg_of(segs, tile, lt);
+        const void* __restrict__ src = sg.src;
+        uint8_t* __restrict__ dst = sg.dst;
+        const int64_t base = (int64_t)lt * kK6Nsb;
+        const int64_t left = sg.n - base;
         const int nvalid = left < kK6Nsb ? (int)left : kK6Nsb;
         stage_in<DT, VIA_F16, 16, 17, kK6Nsb * 256>(src, base * 256, (int64_t)nvalid * 256, s.x);
         __syncthreads();
@@ -501,32 +541,57 @@ static int grid_for(int64_t units_per_cta_iter_total, int ctas_per_sm) {
     return (int)(units_per_cta_iter_total < cap ? (units_per_cta_iter_total > 0 ? units_per_cta_iter_total : 1) : cap);
 }
 
+template <int TYPE>
+constexpr int tile_units() {
+    return block_elems(TYPE) == 32 ? kSimpleBlocksPerCta : (TYPE == T_Q4_K || TYPE == T_Q5_K) ? kK45Nsb : kK6Nsb;
+}
+
 template <int TYPE, int DT, bool VIA>
-static void launch_pack(const void* src, uint8_t* dst, int64_t nblk, cudaStream_t st) {
+static void launch_pack(const Segs& segs, cudaStream_t st) {
     if constexpr (block_elems(TYPE) == 32) {
-        const int64_t iters = (nblk + kSimpleBlocksPerCta - 1) / kSimpleBlocksPerCta;
-        pack_simple_kernel<TYPE, DT, VIA><<<grid_for(iters, 8), 256, 0, st>>>(src, dst, nblk);
+        pack_simple_kernel<TYPE, DT, VIA><<<grid_for(segs.total_tiles, 8), 256, 0, st>>>(segs);
     } else if constexpr (TYPE == T_Q6_K) {
-        const int64_t iters = (nblk + kK6Nsb - 1) / kK6Nsb;
-        pack_q6k_kernel<DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
+        pack_q6k_kernel<DT, VIA><<<grid_for(segs.total_tiles, 4), 256, 0, st>>>(segs);
     } else if constexpr (TYPE == T_Q2_K || TYPE == T_Q3_K) {
-        const int64_t iters = (nblk + kK6Nsb - 1) / kK6Nsb;
-        pack_k23_kernel<TYPE, DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
+        pack_k23_kernel<TYPE, DT, VIA><<<grid_for(segs.total_tiles, 4), 256, 0, st>>>(segs);
     } else {
-        const int64_t iters = (nblk + kK45Nsb - 1) / kK45Nsb;
-        pack_k45_kernel<TYPE, DT, VIA><<<grid_for(iters, 4), 256, 0, st>>>(src, dst, nblk);
+        pack_k45_kernel<TYPE, DT, VIA><<<grid_for(segs.total_tiles, 4), 256, 0, st>>>(segs);
     }
 }
 
 template <int TYPE>
-static int dispatch_dt(const void* src, int dt, int via, uint8_t* dst, int64_t nblk, cudaStream_t st) {
+static int dispatch_dt(const Segs& segs, int dt, int via, cudaStream_t st) {
     switch (dt) {
-        case QT_F32: via ? launch_pack<TYPE, QT_F32, true>(src, dst, nblk, st) : launch_pack<TYPE, QT_F32, false>(src, dst, nblk, st); break;
-        case QT_F16: launch_pack<TYPE, QT_F16, false>(src, dst, nblk, st); break;
-        case QT_BF16: via ? launch_pack<TYPE, QT_BF16, true>(src, dst, nblk, st) : launch_pack<TYPE, QT_BF16, false>(src, dst, nblk, st); break;
+        case QT_F32: via ? launch_pack<TYPE, QT_F32, true>(segs, st) : launch_pack<TYPE, QT_F32, false>(segs, st); break;
+        case QT_F16: launch_pack<TYPE, QT_F16, false>(segs, st); break;
+        case QT_BF16: via ? launch_pack<TYPE, QT_BF16, true>(segs, st) : launch_pack<TYPE, QT_BF16, false>(segs, st); break;
         default: return QT_ERR_INVALID;
     }
     return check_launch("qt_gguf_quantize");
+}
+
+static int tile_units_of(int t) {
+    switch (t) {
+        case T_Q4_K: case T_Q5_K: return kK45Nsb;
+        case T_Q2_K: case T_Q3_K: case T_Q6_K: return kK6Nsb;
+        default: return kSimpleBlocksPerCta;
+    }
+}
+
+static int dispatch_type(int ggml_type, const Segs& segs, int dt, int via, cudaStream_t st) {
+    switch (ggml_type) {
+        case T_Q4_0: return dispatch_dt<T_Q4_0>(segs, dt, via, st);
+        case T_Q4_1: return dispatch_dt<T_Q4_1>(segs, dt, via, st);
+        case T_Q5_0: return dispatch_dt<T_Q5_0>(segs, dt, via, st);
+        case T_Q5_1: return dispatch_dt<T_Q5_1>(segs, dt, via, st);
+        case T_Q8_0: return dispatch_dt<T_Q8_0>(segs, dt, via, st);
+        case T_Q2_K: return dispatch_dt<T_Q2_K>(segs, dt, via, st);
+        case T_Q3_K: return dispatch_dt<T_Q3_K>(segs, dt, via, st);
+        case T_Q4_K: return dispatch_dt<T_Q4_K>(segs, dt, via, st);
+        case T_Q5_K: return dispatch_dt<T_Q5_K>(segs, dt, via, st);
+        case T_Q6_K: return dispatch_dt<T_Q6_K>(segs, dt, via, st);
+    }
+    return QT_ERR_UNSUPPORTED;
 }
 
 }  // namespace gguf
@@ -547,21 +612,61 @@ int qt_gguf_quantize(int ggml_type, const void* src, int src_dtype, int round_vi
     if (nrows == 0 || ncols == 0) return QT_OK;
     if (!src || !dst || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return QT_ERR_INVALID;
     const int64_t nblk = nrows * (ncols / be);
-    cudaStream_t st = (cudaStream_t)stream;
-    uint8_t* d = (uint8_t*)dst;
-    switch (ggml_type) {
-        case T_Q4_0: return dispatch_dt<T_Q4_0>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q4_1: return dispatch_dt<T_Q4_1>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q5_0: return dispatch_dt<T_Q5_0>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q5_1: return dispatch_dt<T_Q5_1>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q8_0: return dispatch_dt<T_Q8_0>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q2_K: return dispatch_dt<T_Q2_K>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q3_K: return dispatch_dt<T_Q3_K>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q4_K: return dispatch_dt<T_Q4_K>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q5_K: return dispatch_dt<T_Q5_K>(src, src_dtype, round_via_f16, d, nblk, st);
-        case T_Q6_K: return dispatch_dt<T_Q6_K>(src, src_dtype, round_via_f16, d, nblk, st);
+    const int tu = tile_units_of(ggml_type);
+    const int64_t tiles = (nblk + tu - 1) / tu;
+    if (tiles > 2147483647LL) return QT_ERR_INVALID;
+    Segs segs{};
+    segs.nseg = 1;
+    segs.total_tiles = (int)tiles;
+    segs.one = Seg{src, (uint8_t*)dst, (long long)nblk};
+    return dispatch_type(ggml_type, segs, src_dtype, round_via_f16, (cudaStream_t)stream);
+}
+
+// Many tensors of one type in ONE launch.  src[i] / dst[i]: device pointers (16-byte aligned), nelems[i]: element
+// count of tensor i (rows are multiples of the block size, so a tensor is a flat array of blocks).
+// table_dev: device scratch of at least qt_gguf_batch_table_bytes(n) bytes (the segment table is copied there).
+int64_t qt_gguf_batch_table_bytes(int n) { return n <= 0 ? 0 : (int64_t)(((4 * (n + 1) + 15) / 16) * 16) + (int64_t)sizeof(Seg) * n; }
+
+int qt_gguf_quantize_batch(int ggml_type, int n, const void* const* src, const int64_t* nelems, void* const* dst,
+                           int src_dtype, int round_via_f16, void* table_dev, void* stream) {
+    const int be = block_elems(ggml_type);
+    if (be < 0) return QT_ERR_UNSUPPORTED;
+    if (n < 0 || (n > 0 && (!src || !nelems || !dst || !table_dev))) return QT_ERR_INVALID;
+    if (n == 0) return QT_OK;
+    const int tu = tile_units_of(ggml_type);
+    const size_t ts_bytes = (size_t)(((4 * (n + 1) + 15) / 16) * 16);
+    std::vector<uint8_t> host(ts_bytes + sizeof(Seg) * n);
+    int* tile_start = reinterpret_cast<int*>(host.data());
+    Seg* table = reinterpret_cast<Seg*>(host.data() + ts_bytes);
+    long long tiles = 0;
+    int m = 0;                                  // empty tensors are dropped from the table
+    for (int i = 0; i < n; i++) {
+        if (nelems[i] < 0 || nelems[i] % be) return QT_ERR_INVALID;
+        if (nelems[i] == 0) continue;
+        if (!src[i] || !dst[i] || ((uintptr_t)src[i] & 15) || ((uintptr_t)dst[i] & 15)) return QT_ERR_INVALID;
+        const long long units = nelems[i] / be;
+        tile_start[m] = (int)tiles;
+        table[m] = Seg{src[i], (uint8_t*)dst[i], units};
+        tiles += (units + tu - 1) / tu;
+        if (tiles > 2147483647LL) return QT_ERR_INVALID;
+        m++;
     }
-    return QT_ERR_UNSUPPORTED;
+    if (m == 0) return QT_OK;
+    tile_start[m] = (int)tiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    Segs segs{};
+    segs.nseg = m;
+    segs.total_tiles = (int)tiles;
+    if (m == 1) {
+        segs.one = table[0];
+    } else {
+        // pageable source: the copy is staged before the call returns, so `host` may go out of scope
+        cudaError_t e = cudaMemcpyAsync(table_dev, host.data(), host.size(), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { qt::set_last_error("gguf batch table copy", e); return QT_ERR_CUDA; }
+        segs.tile_start = reinterpret_cast<const int*>(table_dev);
+        segs.table = reinterpret_cast<const Seg*>((const uint8_t*)table_dev + ts_bytes);
+    }
+    return dispatch_type(ggml_type, segs, src_dtype, round_via_f16, st);
 }
 
 int qt_gguf_dequantize(int ggml_type, const void* src, int64_t nrows, int64_t ncols, float* dst, void* stream) {

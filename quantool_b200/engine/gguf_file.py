@@ -204,20 +204,25 @@ def quantize_gguf(input_gguf: str, out_file: str, ftype: str, devices: Optional[
         plan.append((t, shape, tensor_type(t.name, shape, ftype, n_layers, has_output, n_head, n_kv)))
     sizes = [int(np.prod(s)) for _, s, _ in plan]
     place = assign_devices(sizes, len(devices))
-    pending = []
-    for (t, shape, qt), d in zip(plan, place):
+    pending = [None] * len(plan)
+    groups: Dict[tuple, list] = {}            # (device, type, dtype) -> [(index, device tensor)]: one launch per group
+    for i, ((t, shape, qt), d) in enumerate(zip(plan, place)):
         data = np.asarray(t.data)
         if qt == "F32":
             out = data.astype(np.float32) if data.dtype != np.float32 else data
-            pending.append((t.name, out.reshape(shape), None, None))
+            pending[i] = (t.name, out.reshape(shape), None, None)
         elif qt == "F16":
-            pending.append((t.name, data.astype(np.float16).reshape(shape), None, None))
+            pending[i] = (t.name, data.astype(np.float16).reshape(shape), None, None)
         else:
             dev = torch.device("cuda", devices[d])
-            src = torch.from_numpy(np.ascontiguousarray(data.reshape(-1, shape[-1])))
-            with torch.cuda.device(dev):
-                y = cabi.gguf_quantize(src.to(dev, non_blocking=True), qt, round_via_f16=(src.dtype != torch.float16))
-            pending.append((t.name, y, shape, getattr(gguf.GGMLQuantizationType, qt)))
+            src = torch.from_numpy(np.ascontiguousarray(data.reshape(-1, shape[-1]))).to(dev, non_blocking=True)
+            groups.setdefault((dev, qt, src.dtype), []).append((i, src))
+    for (dev, qt, dt), items in groups.items():
+        with torch.cuda.device(dev):
+            ys = cabi.gguf_quantize_batch([x for _, x in items], qt, round_via_f16=(dt != torch.float16))
+        for (i, _), y in zip(items, ys):
+            t, shape, _ = plan[i]
+            pending[i] = (t.name, y, shape, getattr(gguf.GGMLQuantizationType, qt))
     for name, arr, shape, raw in pending:
         if raw is None:
             w.add_tensor(name, np.ascontiguousarray(arr))

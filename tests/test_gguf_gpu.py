@@ -104,3 +104,21 @@ def test_full_size_roundtrip_property(qtype):
         a = y1.view(-1, 34)[:, 2:]
         b = y3.view(-1, 34)[:, 2:]
         assert (a != b).float().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q5_1", "Q3_K", "Q4_K", "Q6_K"])
+def test_batch_launch_equals_per_tensor(qtype):
+    """Many tensors in one launch (segment table) == one launch per tensor, including an empty tensor, tensors
+    smaller than a CTA tile and tensors that end in the middle of one."""
+    from quantool_b200 import cabi
+    be = cabi.gguf_block_elems(qtype)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    shapes = [(3, be), (0, 2 * be), (17, 5 * be), (1, be), (300, 9 * be), (64, 4 * be)]
+    xs = [(torch.randn(s, generator=g, device="cuda") * 0.05).half() for s in shapes]
+    ys = cabi.gguf_quantize_batch(xs, qtype)
+    for x, y in zip(xs, ys):
+        assert torch.equal(y, cabi.gguf_quantize(x, qtype))
+    many = cabi.gguf_quantize_many([(x, qtype) for x in xs] + [(xs[2].float(), "Q8_0")])
+    assert torch.equal(many[2], ys[2]) and torch.equal(many[-1], cabi.gguf_quantize(xs[2].float(), "Q8_0"))
+    with pytest.raises(cabi.QtError):
+        cabi.gguf_quantize_batch([xs[0], xs[2].float()], qtype)      # mixed dtypes
