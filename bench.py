@@ -278,10 +278,10 @@ def side_workload(a, shape, dev):
     def step():
         for l in range(L if not a.layers else a.layers):
             w = llama.random_layer_weights(shape, l % 2, dev)
-            eawq.awq_layer(shape, w, h, cos, sin, args, 8)
+            eawq.awq_layer(shape, w, h, cos, sin, args, 32)
     for _ in range(min(a.warmup, 1)):
         w = llama.random_layer_weights(shape, 0, dev)
-        eawq.awq_layer(shape, w, h, cos, sin, args, 8)
+        eawq.awq_layer(shape, w, h, cos, sin, args, 32)
     ms = sum(ev_time(step) for _ in range(a.steps)) / a.steps
     wt = llama.random_layer_weights(shape, 0, dev)["mlp.gate_proj.weight"]
     s = torch.rand((wt.shape[1],), device=dev) + 0.5

@@ -112,7 +112,7 @@ def apply_mapping(w: Dict[str, torch.Tensor], mp: Mapping, s: torch.Tensor) -> N
 
 
 def awq_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor, cos, sin, args: WeightArgs,
-              chunk_samples: int = 8, dist=None, n_grid: int = N_GRID, duo_scaling: bool = True):
+              chunk_samples: int = 32, dist=None, n_grid: int = N_GRID, duo_scaling: bool = True):
     """Calibrate + smooth one decoder layer in place.  Returns {smooth-name: (scales, ratio, losses)}."""
     dev = h.device
     n_local, seq, _ = h.shape

@@ -562,7 +562,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
 
 
 def quantize_model_awq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor], token_ids: torch.Tensor,
-                       args: WeightArgs, device, fmt: str = "pack-quantized", chunk_samples: int = 8,
+                       args: WeightArgs, device, fmt: str = "pack-quantized", chunk_samples: int = 32,
                        n_grid: int = 20, duo_scaling: bool = True, dist: Optional[Dist] = None,
                        progress=None) -> ModelQuantResult:
     """AWQ over the whole model: per layer calibrate -> 20-point scale search per mapping -> smooth ->
