@@ -335,6 +335,9 @@ __global__ void __launch_bounds__(256) set_identity_kernel(float* __restrict__ U
 struct LookAhead {
     cudaStream_t side = nullptr;
     cudaEvent_t panel_ready = nullptr, potrf_done = nullptr;
+    // tensor-core Cholesky: the far part of a deferred update runs here, underneath the next outer block's panels
+    cudaStream_t far = nullptr;
+    cudaEvent_t far_ready = nullptr, far_done = nullptr;
     bool ok = false;
 };
 // one side stream per caller stream: chains that the host runs concurrently on different streams
@@ -352,7 +355,10 @@ static LookAhead& lookahead(cudaStream_t st) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         la.ok = cudaStreamCreateWithPriority(&la.side, cudaStreamNonBlocking, hi) == cudaSuccess &&
                 cudaEventCreateWithFlags(&la.panel_ready, cudaEventDisableTiming) == cudaSuccess &&
-                cudaEventCreateWithFlags(&la.potrf_done, cudaEventDisableTiming) == cudaSuccess;
+                cudaEventCreateWithFlags(&la.potrf_done, cudaEventDisableTiming) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&la.far, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.far_ready, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.far_done, cudaEventDisableTiming) == cudaSuccess;
     }
     return la;
 }
@@ -544,7 +550,7 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
     cudaError_t e = cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error("potrf smem attr", e); return QT_ERR_CUDA; }
     LookAhead& la = lookahead(st);
-    bool potrf_ahead = false;
+    bool potrf_ahead = false, far_pending = false;
     for (int ob = 0; ob < K; ob += OB) {
         const int oe = (ob + OB) < K ? (ob + OB) : K;
         for (int k = ob; k < oe; k += NB) {
@@ -560,33 +566,55 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
             const int rem = K - k - nb;
             if (rem <= 0) break;
             float* P = A + (long long)(k + nb) * ld + k;
-            GemmArgs t{};  // TRSM as GEMM: P <- P * (L_kk^-1)^T, in place
-            t.A = P; t.B = X + (long long)k * ld + k; t.C = P;
-            t.M = rem; t.N = nb; t.Kd = nb; t.lda = t.ldb = t.ldc = ld;
+            const int n_in = oe - (k + nb);            // columns of this outer block still to the right
+            const int nb2 = n_in > 0 ? (n_in < NB ? n_in : NB) : 0;
+            // Critical path first: the next diagonal block only needs the top nb2 rows of the panel.  Solve those,
+            // update that one block, and hand it to the look-ahead factorisation; everything else of this panel
+            // (the rest of the TRSM, the split, the other updates) then runs underneath the next potrf.
+            GemmArgs t{};  // TRSM as GEMM: P <- P * (L_kk^-1)^T, in place; row ranges are independent
+            t.B = X + (long long)k * ld + k;
+            t.N = nb; t.Kd = nb; t.lda = t.ldb = t.ldc = ld;
             t.alpha = 1.f; t.beta = 0.f;
-            int rc = sgemm(true, t, 1, st);
-            if (rc) return rc;
+            int rc;
+            if (nb2 > 0) {
+                t.A = P; t.C = P; t.M = nb2;
+                rc = sgemm(true, t, 1, st);
+                if (rc) return rc;
+                GemmArgs sd{};   // next diagonal block -= P_top P_top^T
+                sd.A = P; sd.B = P; sd.C = A + (long long)(k + nb) * ld + (k + nb);
+                sd.M = nb2; sd.N = nb2; sd.Kd = nb; sd.lda = sd.ldb = sd.ldc = ld;
+                sd.alpha = -1.f; sd.beta = 1.f;
+                rc = sgemm(true, sd, 1, st);
+                if (rc) return rc;
+                if (la.ok) {
+                    if (cudaEventRecord(la.panel_ready, st) != cudaSuccess) return QT_ERR_CUDA;
+                    if (cudaStreamWaitEvent(la.side, la.panel_ready, 0) != cudaSuccess) return QT_ERR_CUDA;
+                    potrf_inv_kernel<<<1, 256, smem, la.side>>>(A, X, ld, nb2, k + nb, info);
+                    rc = check_launch("potrf_inv(look-ahead)");
+                    if (rc) return rc;
+                    if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
+                    potrf_ahead = true;
+                }
+            }
+            if (rem > nb2) {     // rest of the TRSM
+                float* Pr = P + (long long)nb2 * ld;
+                t.A = Pr; t.C = Pr; t.M = rem - nb2;
+                rc = sgemm(true, t, 1, st);
+                if (rc) return rc;
+            }
             const long long poff = (long long)(k + nb) * ld + k;
             rc = split_block(false, P, ld, Lh + poff, Ll + poff, ld, rem, nb, 0, 1, 0, 0, st);
             if (rc) return rc;
-            // inner SYRK (FFMA): only the columns of this outer block, next panel column first
-            const int n_in = oe - (k + nb);
             if (n_in <= 0) continue;
-            const int nb2 = n_in < NB ? n_in : NB;
-            GemmArgs s1{};
-            s1.A = P; s1.B = P; s1.C = A + (long long)(k + nb) * ld + (k + nb);
-            s1.M = rem; s1.N = nb2; s1.Kd = nb; s1.lda = s1.ldb = s1.ldc = ld;
-            s1.alpha = -1.f; s1.beta = 1.f; s1.lower_tiles_only = 1;
-            rc = sgemm(true, s1, 1, st);
-            if (rc) return rc;
-            if (la.ok) {
-                if (cudaEventRecord(la.panel_ready, st) != cudaSuccess) return QT_ERR_CUDA;
-                if (cudaStreamWaitEvent(la.side, la.panel_ready, 0) != cudaSuccess) return QT_ERR_CUDA;
-                potrf_inv_kernel<<<1, 256, smem, la.side>>>(A, X, ld, nb2, k + nb, info);
-                rc = check_launch("potrf_inv(look-ahead)");
+            // inner updates (FFMA): only the columns of this outer block
+            if (rem > nb2) {     // rows below the next diagonal block, its column:  -= P_rest P_top^T
+                float* Pr = P + (long long)nb2 * ld;
+                GemmArgs s1{};
+                s1.A = Pr; s1.B = P; s1.C = A + (long long)(k + nb + nb2) * ld + (k + nb);
+                s1.M = rem - nb2; s1.N = nb2; s1.Kd = nb; s1.lda = s1.ldb = s1.ldc = ld;
+                s1.alpha = -1.f; s1.beta = 1.f;
+                rc = sgemm(true, s1, 1, st);
                 if (rc) return rc;
-                if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
-                potrf_ahead = true;
             }
             const int n_in2 = n_in - nb2;
             if (n_in2 > 0) {
@@ -599,12 +627,20 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
                 if (rc) return rc;
             }
         }
-        // deferred update of everything right of this outer block: A[oe:, oe:] -= L[oe:, ob:oe] L[oe:, ob:oe]^T
+        // deferred update of everything right of this outer block: A[oe:, oe:] -= L[oe:, ob:oe] L[oe:, ob:oe]^T,
+        // in three parts: (a) the next panel column - its diagonal block goes to the look-ahead factorisation;
+        // (b) the other columns of the NEXT outer block; (c) everything beyond it, on the `far` stream, underneath
+        // the next outer block's latency-bound panel loop.  Each element still receives its updates in outer-block
+        // order (the far stream is ordered, and the next (a)/(b) wait for it), so the result is deterministic.
         const int remo = K - oe;
         if (remo <= 0) break;
+        if (far_pending) {
+            if (cudaStreamWaitEvent(st, la.far_done, 0) != cudaSuccess) return QT_ERR_CUDA;
+            far_pending = false;
+        }
         diag_fix_pre_kernel<<<(remo + 7) / 8, 256, 0, st>>>(A, ld, oe, remo, ob, oe - ob, dfix);
-        int rcd = check_launch("diag_fix_pre");
-        if (rcd) return rcd;
+        int rc = check_launch("diag_fix_pre");
+        if (rc) return rc;
         tgemm::Problem p;
         p.A = {Lh, Ll, K, oe, ld};
         p.B = p.A;
@@ -612,11 +648,10 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
         p.Kd = oe - ob;
         p.a_col0 = p.b_col0 = ob;
         p.negate = true; p.accumulate = true; p.lower_tiles_only = true;
-        // next panel column first, so that its diagonal block can be factored underneath the rest
         const int nb2 = remo < NB ? remo : NB;
-        p.M = remo; p.N = nb2;
+        p.M = remo; p.N = nb2;                                           // (a)
         p.a_row0 = p.b_row0 = p.c_row0 = p.c_col0 = oe;
-        int rc = tgemm::launch(p, st);
+        rc = tgemm::launch(p, st);
         if (rc) return rc;
         diag_fix_post_kernel<<<1, 256, 0, st>>>(A, ld, oe, nb2, dfix);
         rc = check_launch("diag_fix_post");
@@ -630,16 +665,36 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
             if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
             potrf_ahead = true;
         }
-        if (remo > nb2) {
-            p.M = remo - nb2; p.N = remo - nb2;
+        const int nextw = remo < OB ? remo : OB;                         // width of the next outer block
+        if (nextw > nb2) {                                               // (b)
+            p.M = remo - nb2; p.N = nextw - nb2;
             p.a_row0 = p.b_row0 = p.c_row0 = p.c_col0 = oe + nb2;
             rc = tgemm::launch(p, st);
             if (rc) return rc;
-            diag_fix_post_kernel<<<(remo - nb2 + 255) / 256, 256, 0, st>>>(A, ld, oe + nb2, remo - nb2, dfix);
+            diag_fix_post_kernel<<<(nextw - nb2 + 255) / 256, 256, 0, st>>>(A, ld, oe + nb2, nextw - nb2, dfix);
             rc = check_launch("diag_fix_post");
             if (rc) return rc;
         }
+        if (remo > nextw) {                                              // (c)
+            cudaStream_t fs = la.ok ? la.far : st;
+            if (la.ok) {
+                if (cudaEventRecord(la.far_ready, st) != cudaSuccess) return QT_ERR_CUDA;
+                if (cudaStreamWaitEvent(fs, la.far_ready, 0) != cudaSuccess) return QT_ERR_CUDA;
+            }
+            p.M = remo - nextw; p.N = remo - nextw;
+            p.a_row0 = p.b_row0 = p.c_row0 = p.c_col0 = oe + nextw;
+            rc = tgemm::launch(p, fs);
+            if (rc) return rc;
+            diag_fix_post_kernel<<<(remo - nextw + 255) / 256, 256, 0, fs>>>(A, ld, oe + nextw, remo - nextw, dfix);
+            rc = check_launch("diag_fix_post");
+            if (rc) return rc;
+            if (la.ok) {
+                if (cudaEventRecord(la.far_done, fs) != cudaSuccess) return QT_ERR_CUDA;
+                far_pending = true;
+            }
+        }
     }
+    if (far_pending && cudaStreamWaitEvent(st, la.far_done, 0) != cudaSuccess) return QT_ERR_CUDA;
     return QT_OK;
 }
 
