@@ -318,3 +318,73 @@ def test_hessian_empty_and_unaligned_errors():
                                 torch.zeros((60, 60), device="cuda"))                        # K % 8 != 0
     with pytest.raises(cabi.QtError):
         cabi.hessian_accumulate(torch.zeros((8, 64), device="cuda"), H)                      # fp32 activations
+
+
+def test_hessian_exact_diagonal():
+    """Row a1: the tensor-core accumulator truncates; the diagonal (which decides the act_order permutation) is
+    accumulated separately in fp32 round-to-nearest and written into H."""
+    from quantool_b200 import cabi
+    from quantool_b200.engine import gptq as eg
+    K, T = 1024, 16384
+    x = _acts(T, K, seed=3)
+    acc = eg.HessianAccumulator(K, "cuda")
+    for xb in x.reshape(4, T // 4, K):
+        acc.add(xb.cuda(), 2)
+    raw_tc = torch.diagonal(acc.H).clone()                   # tensor-core sums, before the exact diagonal is written
+    H = acc.finalize()
+    d64 = (2.0 / 8) * (x.double() ** 2).sum(0)
+    got = torch.diagonal(H).cpu().double()
+    assert ((got - d64).abs() / d64).max().item() < 5e-7
+    tc = (2.0 / 8) * raw_tc.cpu().double()
+    assert ((tc - d64) / d64).mean().item() < 0            # the bias this pass removes: truncation -> too small
+    assert torch.equal(H, H.t())
+    # direct C-ABI use: accumulate twice = double
+    diag = torch.zeros((K,), device="cuda")
+    scr = torch.empty((32 * K,), device="cuda")
+    xb = x[:4096].cuda().contiguous()
+    cabi.hessian_diag_accumulate(xb, diag, scr)
+    one = diag.clone()
+    cabi.hessian_diag_accumulate(xb, diag, scr)
+    assert torch.allclose(diag, 2 * one, rtol=1e-6)
+    with pytest.raises(cabi.QtError):
+        cabi.hessian_diag_accumulate(xb.cpu(), diag, scr)
+
+
+@pytest.mark.parametrize("actorder,own_h,floor", [(None, True, 0.9999), ("group", False, 0.999)])
+def test_gptq_larger_k_vs_oracle(actorder, own_h, floor):
+    """K = 2048 (tensor-core chain + two-level lazy update).  Without act_order the codes match the oracle to the
+    last entry with the GPU's own Hessian.  With act_order the comparison is made on the oracle's H: argsort(diag H)
+    breaks near-ties differently for two fp32 evaluations of the same diagonal, which moves group boundaries
+    (DESIGN.md §6 "Parity at larger K")."""
+    from quantool_b200.engine import gptq as eg, schemes
+    from oracle import gptq as og
+    from compressed_tensors.quantization import ActivationOrdering
+    N, K = 48, 2048
+    g = torch.Generator().manual_seed(77)
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    T = 4 * K
+    x = _acts(T, K, seed=K + 9)
+    oargs = og.scheme_weight_args("W4A16")
+    if actorder:
+        oargs.actorder = ActivationOrdering.GROUP
+    Ho, n = og.make_empty_hessian(K), 0
+    for xb in x.reshape(8, T // 8, K):
+        Ho, n = og.accumulate_hessian(xb.unsqueeze(0), Ho, n)
+    loss_o, Wq_o, s_o, z_o, gi_o = og.quantize_weight(W, Ho.clone(), oargs)
+    codes_o, _, _ = og.compress_packed(Wq_o, s_o, None, gi_o, oargs)
+    args = schemes.resolve("W4A16", actorder)
+    if own_h:
+        acc = eg.HessianAccumulator(K, "cuda")
+        for xb in x.reshape(8, T // 8, K):
+            acc.add(xb.unsqueeze(0).cuda())
+        H = acc.finalize()
+    else:
+        H = Ho.cuda()
+    res = eg.quantize_linear(W.cuda(), H, args)
+    assert int(res.info.item()) == 0
+    _, codes = eg.compress_linear(res.weight, res.scale, res.zero_point, res.g_idx, args)
+    agree = (codes.cpu() == codes_o).float().mean().item()
+    assert agree >= floor, agree
+    e_o = og.layer_error(W, Wq_o, x.float())
+    e_c = og.layer_error(W, res.weight.cpu(), x.float())
+    assert abs(e_c - e_o) <= 0.01 * e_o
