@@ -421,8 +421,17 @@ def main():
     ntiles = sum(min(2 * j + 2, NI) for j in range(NJ))
     exec_flops = 2.0 * T_local * ntiles * 128 * 256
     ref_flops = 2.0 * T_local * Kmax * Kmax
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this exact shape
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "hessian_syrk_traffic.json")))
+        if tj.get("T") == T_local and tj.get("K") == Kmax:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"kernel": "hessian_syrk_kernel", "bound": "tensor", "achieved": exec_flops / hess_ms / 1e9,
-                "peak": peak, "unit": "TFLOP/s", "frac": exec_flops / hess_ms / 1e9 / peak, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": exec_flops / hess_ms / 1e9 / peak, "traffic": traffic,
+                "traffic_unit": "bytes/launch (dram read + write)", "traffic_source": traffic_src,
                 "peak_source": peak_src, "ms_per_launch": hess_ms, "shape": f"X[{T_local},{Kmax}] bf16 -> H[{Kmax},{Kmax}] fp32",
                 "algorithmic": "executed upper-triangle tile FLOPs 2*T*ntiles*128*256",
                 "reference_equivalent_tflops": ref_flops / hess_ms / 1e9}
