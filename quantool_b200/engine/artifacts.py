@@ -87,3 +87,35 @@ def autogptq_view(weight_packed: torch.Tensor, weight_scale: torch.Tensor, weigh
     if g_idx is None:
         g_idx = (torch.arange(K, dtype=torch.int32, device=u.device) // (group_size or K))
     return {"qweight": qweight, "qzeros": qzeros, "scales": scales, "g_idx": g_idx.to(torch.int32)}
+
+
+AWQ_ORDER = (0, 2, 4, 6, 1, 3, 5, 7)   # AutoAWQ nibble order inside one int32 (vLLM reverses it with 0,4,1,5,2,6,3,7)
+
+
+def autoawq_view(weight_packed: torch.Tensor, weight_scale: torch.Tensor, weight_zero_point: Optional[torch.Tensor],
+                 K: int) -> Dict[str, torch.Tensor]:
+    """AutoAWQ GEMM layout of a 4-bit group-quantized Linear: qweight [K, N/8] packed along N (output channels)
+    with the interleave AWQ_ORDER, qzeros [G, N/8] packed the same way, scales [G, N].  Pure index shuffling of
+    the compressed-tensors codes (consumer: vLLM quant_utils awq_pack)."""
+    from .. import cabi
+    N = weight_packed.shape[0]
+    dev = weight_packed.device
+    if N % 8:
+        raise ValueError("AutoAWQ packing needs the number of output channels to be a multiple of 8")
+    if dev.type == "cuda":
+        codes = cabi.unpack_int32(weight_packed.contiguous(), 4, K)
+    else:
+        shifts = torch.arange(8, dtype=torch.int32) * 4
+        u = (weight_packed.unsqueeze(-1) >> shifts) & 0xF
+        codes = (u.reshape(N, -1)[:, :K] - 8).to(torch.int8)
+    u = (codes.to(torch.int32) + 8).t().contiguous()                       # [K, N] unsigned codes
+    order = torch.tensor(AWQ_ORDER, dtype=torch.long, device=u.device)
+    shifts = (torch.arange(8, dtype=torch.int32, device=u.device) * 4).view(1, 1, 8)
+    qweight = (u.view(K, N // 8, 8)[:, :, order] << shifts).sum(dim=2, dtype=torch.int32)
+    G = weight_scale.shape[1]
+    if weight_zero_point is None:
+        zeros = torch.full((G, N), 8, dtype=torch.int32, device=u.device)
+    else:
+        zeros = (weight_zero_point.to(torch.int32) + 8).t().contiguous()
+    qzeros = (zeros.view(G, N // 8, 8)[:, :, order] << shifts).sum(dim=2, dtype=torch.int32)
+    return {"qweight": qweight, "qzeros": qzeros, "scales": weight_scale.t().contiguous()}

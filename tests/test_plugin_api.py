@@ -184,3 +184,29 @@ def test_gguf_tensor_type_table_low_bit_levels():
     assert t("blk.9.attn_v.weight", (1024, 8192), "Q3_K_S", L=80, h=64) == "Q5_K"    # 70B: shared attn_v
     with pytest.raises(NotImplementedError):                                   # 576 % 256 != 0 -> IQ4_NL
         t("blk.0.attn_q.weight", (576, 576), "Q3_K_S", L=30, kv=3)
+
+
+def test_autogptq_and_autoawq_views_are_pure_repacks_cpu():
+    """the AutoGPTQ / AutoAWQ key layouts are index shuffles of the compressed-tensors codes."""
+    import torch
+    from compressed_tensors.compressors.pack_quantized.helpers import pack_to_int32
+    from quantool_b200.engine import artifacts
+    N, K, gs = 32, 256, 128
+    g = torch.Generator().manual_seed(0)
+    codes = torch.randint(-8, 8, (N, K), generator=g, dtype=torch.int8)
+    packed = pack_to_int32(codes, 4)
+    scale = torch.rand((N, K // gs), generator=g).to(torch.bfloat16)
+    zp = torch.randint(-8, 8, (N, K // gs), generator=g, dtype=torch.int8)
+    u = codes.to(torch.int32) + 8
+    v = artifacts.autogptq_view(packed, scale, zp, None, 4, K, gs)
+    qw = v["qweight"]
+    assert qw.shape == (K // 8, N)
+    back = torch.stack([(qw >> (4 * i)) & 0xF for i in range(8)], dim=1).reshape(K, N).t()
+    assert torch.equal(back, u)
+    a = artifacts.autoawq_view(packed, scale, zp, K)
+    assert a["qweight"].shape == (K, N // 8) and a["qzeros"].shape == (K // gs, N // 8) and a["scales"].shape == (K // gs, N)
+    rev = [0, 4, 1, 5, 2, 6, 3, 7]                     # vLLM's AWQ unpack order
+    nib = torch.stack([(a["qweight"] >> (4 * i)) & 0xF for i in range(8)], dim=2)      # [K, N/8, 8] in packed order
+    assert torch.equal(nib[:, :, rev].reshape(K, N).t(), u)
+    znib = torch.stack([(a["qzeros"] >> (4 * i)) & 0xF for i in range(8)], dim=2)
+    assert torch.equal(znib[:, :, rev].reshape(K // gs, N).t(), zp.to(torch.int32) + 8)
