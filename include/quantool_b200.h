@@ -43,6 +43,7 @@ extern "C" {
 #define QT_GGML_Q4_K 12
 #define QT_GGML_Q5_K 13
 #define QT_GGML_Q6_K 14
+#define QT_GGML_IQ4_NL 20
 
 const char* qt_last_error(void);
 int qt_abi_version(void);

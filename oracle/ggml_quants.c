@@ -17,7 +17,7 @@
  *   - Q8_0 / Q4_0 / Q4_1 / Q5_0 / Q5_1 packed bytes == gguf-py `gguf.quants.quantize`
  *     (GGUFPY/quants.py:220-239, 291-311, 378-393; "bit-exact same results as reference
  *     implementation in ggml-quants.c") and the sha256 KATs in SURVEY.md §8c.
- *   - Q2_K / Q3_K / Q4_K / Q5_K / Q6_K: PARITY UNPINNED against llama.cpp itself (no quantize twin on
+ *   - IQ4_NL / Q2_K / Q3_K / Q4_K / Q5_K / Q6_K: PARITY UNPINNED against llama.cpp itself (no quantize twin on
  *     disk); pinned only by (a) an independent numpy restatement (oracle/ggml_quants_np.py)
  *     agreeing byte-for-byte and (b) gguf-py's dequantizers (GGUFPY/quants.py:475-572)
  *     reading the packed layout back to within the format's error.
@@ -108,6 +108,7 @@ typedef struct { uint16_t d; uint16_t dmin; uint8_t scales[12]; uint8_t qh[32]; 
 typedef struct { uint8_t ql[128]; uint8_t qh[64]; int8_t scales[16]; uint16_t d; } block_q6_K; /* 210 B */
 typedef struct { uint8_t scales[16]; uint8_t qs[64]; uint16_t d; uint16_t dmin; } block_q2_K; /* 84 B */
 typedef struct { uint8_t hmask[32]; uint8_t qs[64]; uint8_t scales[12]; uint16_t d; } block_q3_K; /* 110 B */
+typedef struct { uint16_t d; uint8_t qs[16]; } block_iq4_nl;               /* 18 B */
 #pragma pack(pop)
 
 /* ---- D.1 Q8_0 ------------------------------------------------------------------- */
@@ -586,6 +587,79 @@ static void row_q3_K(const float *x, block_q3_K *y, int64_t k) {
     }
 }
 
+/* ---- IQ4_NL: 32-element blocks, 4-bit indices into a fixed non-linear table ------------------------
+ * llama.cpp falls back to it for Q2_K / Q3_K tensors whose rows are not a multiple of 256.  llama-quantize
+ * reaches it through quantize_iq4_nl -> quantize_row_iq4_nl_impl(super_block = block = 32, quant_weights = NULL,
+ * ntry = 7): weights x^2, first guess d = -max/values[0], then 15 candidate inverse scales (itry + values[0])/max,
+ * keep the one maximising (sum w q x)^2 / (sum w q^2); indices are re-derived from the final fp32 scale. */
+static const int8_t kvalues_iq4nl[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
+
+static inline int best_index_int8(int n, const int8_t *val, float x) {
+    if (x <= val[0]) return 0;
+    if (x >= val[n - 1]) return n - 1;
+    int ml = 0, mu = n - 1;
+    while (mu - ml > 1) {
+        int mav = (ml + mu) / 2;
+        if (x < val[mav]) mu = mav; else ml = mav;
+    }
+    return x - val[mu - 1] < val[mu] - x ? mu - 1 : mu;
+}
+
+static void row_iq4_nl(const float *x, block_iq4_nl *y, int64_t k) {
+    const int64_t nb = k / QK;
+    const int8_t *values = kvalues_iq4nl;
+    const int ntry = 7;
+    for (int64_t ib = 0; ib < nb; ib++) {
+        const float *xb = x + QK * ib;
+        uint8_t L[QK];
+        float weight[QK];
+        memset(y[ib].qs, 0, QK / 2);
+        y[ib].d = f32_to_f16(0.f);
+        for (int j = 0; j < QK; ++j) weight[j] = xb[j] * xb[j];
+        float amax = 0, max = 0;
+        for (int j = 0; j < QK; ++j) {
+            float ax = fabsf(xb[j]);
+            if (ax > amax) { amax = ax; max = xb[j]; }
+        }
+        float scale = 0;
+        if (!(amax < GROUP_MAX_EPS)) {
+            float d = ntry > 0 ? -max / values[0] : max / values[0];
+            float id = 1 / d;
+            float sumqx = 0, sumq2 = 0;
+            for (int j = 0; j < QK; ++j) {
+                float al = id * xb[j];
+                int l = best_index_int8(16, values, al);
+                float q = values[l];
+                float w = weight[j];
+                sumqx += w * q * xb[j];
+                sumq2 += w * q * q;
+            }
+            d = sumqx / sumq2;
+            float best = d * sumqx;
+            for (int itry = -ntry; itry <= ntry; ++itry) {
+                id = (itry + values[0]) / max;
+                sumqx = sumq2 = 0;
+                for (int j = 0; j < QK; ++j) {
+                    float al = id * xb[j];
+                    int l = best_index_int8(16, values, al);
+                    float q = values[l];
+                    float w = weight[j];
+                    sumqx += w * q * xb[j];
+                    sumq2 += w * q * q;
+                }
+                if (sumq2 > 0 && sumqx * sumqx > best * sumq2) {
+                    d = sumqx / sumq2; best = d * sumqx;
+                }
+            }
+            scale = d;
+        }
+        y[ib].d = f32_to_f16(scale);
+        float id = scale ? 1 / scale : 0;
+        for (int j = 0; j < QK; ++j) L[j] = (uint8_t)best_index_int8(16, values, id * xb[j]);
+        for (int j = 0; j < 16; ++j) y[ib].qs[j] = (uint8_t)(L[j] | (L[16 + j] << 4));
+    }
+}
+
 /* ---- D.5 Q6_K ------------------------------------------------------------------- */
 static float make_qx_quants_rmse1(int n, int nmax, const float *x, int8_t *L) {
     float max = 0;
@@ -746,6 +820,17 @@ static void deq_q5_1(const block_q5_1 *x, float *y, int64_t k) {
         }
     }
 }
+static void deq_iq4_nl(const block_iq4_nl *x, float *y, int64_t k) {
+    const int64_t nb = k / QK;
+    for (int64_t i = 0; i < nb; i++) {
+        const float d = f16_to_f32(x[i].d);
+        for (int j = 0; j < 16; ++j) {
+            y[i * QK + j] = d * kvalues_iq4nl[x[i].qs[j] & 0xF];
+            y[i * QK + j + 16] = d * kvalues_iq4nl[x[i].qs[j] >> 4];
+        }
+    }
+}
+
 static void deq_q2_K(const block_q2_K *x, float *y, int64_t k) {
     const int64_t nb = k / QK_K;
     for (int64_t i = 0; i < nb; i++) {
@@ -868,18 +953,18 @@ static void deq_q6_K(const block_q6_K *x, float *y, int64_t k) {
 
 /* ---- exported entry points --------------------------------------------------------- */
 /* ggml_type ids (GGUFPY/constants.py GGMLQuantizationType) */
-enum { T_Q2_K = 10, T_Q3_K = 11, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
+enum { T_IQ4_NL = 20, T_Q2_K = 10, T_Q3_K = 11, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
 
 int oracle_block_elems(int t) {
     switch (t) {
-        case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: return QK;
+        case T_Q4_0: case T_Q4_1: case T_Q5_0: case T_Q5_1: case T_Q8_0: case T_IQ4_NL: return QK;
         case T_Q2_K: case T_Q3_K: case T_Q4_K: case T_Q5_K: case T_Q6_K: return QK_K;
         default: return -1;
     }
 }
 int oracle_block_bytes(int t) {
     switch (t) {
-        case T_Q4_0: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24;
+        case T_Q4_0: case T_IQ4_NL: return 18; case T_Q4_1: return 20; case T_Q5_0: return 22; case T_Q5_1: return 24;
         case T_Q8_0: return 34; case T_Q2_K: return 84; case T_Q3_K: return 110; case T_Q4_K: return 144; case T_Q5_K: return 176; case T_Q6_K: return 210;
         default: return -1;
     }
@@ -935,6 +1020,7 @@ static void quant_rows(int64_t lo, int64_t hi, void *p) {
             case T_Q5_0: row_q5_0(xr, (block_q5_0 *)yr, c->ncols); break;
             case T_Q5_1: row_q5_1(xr, (block_q5_1 *)yr, c->ncols); break;
             case T_Q8_0: row_q8_0(xr, (block_q8_0 *)yr, c->ncols); break;
+            case T_IQ4_NL: row_iq4_nl(xr, (block_iq4_nl *)yr, c->ncols); break;
             case T_Q2_K: row_q2_K(xr, (block_q2_K *)yr, c->ncols); break;
             case T_Q3_K: row_q3_K(xr, (block_q3_K *)yr, c->ncols); break;
             case T_Q4_K: row_q4_K(xr, (block_q4_K *)yr, c->ncols); break;
@@ -954,6 +1040,7 @@ static void deq_rows(int64_t lo, int64_t hi, void *p) {
             case T_Q5_0: deq_q5_0((const block_q5_0 *)xr, yr, c->ncols); break;
             case T_Q5_1: deq_q5_1((const block_q5_1 *)xr, yr, c->ncols); break;
             case T_Q8_0: deq_q8_0((const block_q8_0 *)xr, yr, c->ncols); break;
+            case T_IQ4_NL: deq_iq4_nl((const block_iq4_nl *)xr, yr, c->ncols); break;
             case T_Q2_K: deq_q2_K((const block_q2_K *)xr, yr, c->ncols); break;
             case T_Q3_K: deq_q3_K((const block_q3_K *)xr, yr, c->ncols); break;
             case T_Q4_K: deq_q4_K((const block_q4_K *)xr, yr, c->ncols); break;

@@ -419,4 +419,67 @@ def quantize_q3_K(x):
     return out.reshape(nrows, -1)
 
 
-QUANTIZE = {"Q2_K": quantize_q2_K, "Q3_K": quantize_q3_K, "Q4_K": quantize_q4_K, "Q5_K": quantize_q5_K, "Q6_K": quantize_q6_K}
+KVALUES_IQ4NL = np.array([-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113], dtype=f32)
+
+
+def _best_index(x):
+    """llama.cpp best_index_int8 over KVALUES_IQ4NL: nearest table value, ties to the upper one."""
+    v = KVALUES_IQ4NL
+    mu = np.clip(np.searchsorted(v, x, side="right"), 1, 15)      # first index with v[mu] > x (binary search result)
+    lower = (x - v[mu - 1]).astype(f32) < (v[mu] - x).astype(f32)
+    idx = np.where(lower, mu - 1, mu)
+    idx = np.where(x <= v[0], 0, idx)
+    return np.where(x >= v[15], 15, idx)
+
+
+def quantize_iq4_nl(x):
+    """quantize_row_iq4_nl_impl(32, 32, quant_weights=NULL, ntry=7), vectorised over blocks."""
+    x = np.ascontiguousarray(x, dtype=f32)
+    nrows, ncols = x.shape
+    xb = x.reshape(-1, 32)
+    B = xb.shape[0]
+    w = (xb * xb).astype(f32)
+    amax = np.zeros(B, dtype=f32)
+    mx = np.zeros(B, dtype=f32)
+    for j in range(32):
+        ax = np.abs(xb[:, j])
+        upd = ax > amax
+        amax = np.where(upd, ax, amax)
+        mx = np.where(upd, xb[:, j], mx)
+    tiny = amax < f32(1e-15)
+    mxs = np.where(tiny, f32(1), mx).astype(f32)
+
+    def sums(idv):
+        sumqx = np.zeros(B, dtype=f32)
+        sumq2 = np.zeros(B, dtype=f32)
+        for j in range(32):
+            q = KVALUES_IQ4NL[_best_index((idv * xb[:, j]).astype(f32))]
+            wq = (w[:, j] * q).astype(f32)
+            sumqx = (sumqx + (wq * xb[:, j]).astype(f32)).astype(f32)
+            sumq2 = (sumq2 + (wq * q).astype(f32)).astype(f32)
+        return sumqx, sumq2
+
+    with np.errstate(all="ignore"):
+        d = (-mxs / f32(-127)).astype(f32)
+        sumqx, sumq2 = sums((f32(1) / d).astype(f32))
+        d = (sumqx / sumq2).astype(f32)
+        best = (d * sumqx).astype(f32)
+        for itry in range(-7, 8):
+            idv = (f32(itry - 127) / mxs).astype(f32)
+            sumqx, sumq2 = sums(idv)
+            adopt = (sumq2 > 0) & ((sumqx * sumqx).astype(f32) > (best * sumq2).astype(f32))
+            nd = (sumqx / np.where(sumq2 != 0, sumq2, f32(1))).astype(f32)
+            d = np.where(adopt, nd, d).astype(f32)
+            best = np.where(adopt, (nd * sumqx).astype(f32), best).astype(f32)
+        scale = np.where(tiny, f32(0), d).astype(f32)
+        idv = np.where(scale != 0, f32(1) / np.where(scale != 0, scale, f32(1)), f32(0)).astype(f32)
+    L = np.empty((B, 32), dtype=np.int32)
+    for j in range(32):
+        L[:, j] = _best_index((idv * xb[:, j]).astype(f32))
+    out = np.zeros((B, 18), dtype=np.uint8)
+    out[:, 0:2] = scale.astype(np.float16).view(np.uint8).reshape(B, 2)
+    out[:, 2:18] = (L[:, :16] | (L[:, 16:] << 4)).astype(np.uint8)
+    return out.reshape(nrows, -1)
+
+
+QUANTIZE = {"IQ4_NL": quantize_iq4_nl, "Q2_K": quantize_q2_K, "Q3_K": quantize_q3_K, "Q4_K": quantize_q4_K, "Q5_K": quantize_q5_K, "Q6_K": quantize_q6_K}

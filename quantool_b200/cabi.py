@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libquantool_b200.so")
 QT_F32, QT_F16, QT_BF16 = 0, 1, 2
 _DT = {torch.float32: QT_F32, torch.float16: QT_F16, torch.bfloat16: QT_BF16}
 
-GGML = {"Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q8_0": 8, "Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}
+GGML = {"Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q8_0": 8, "Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14, "IQ4_NL": 20}
 
 _i64, _i32, _vp, _f32 = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_float
 

@@ -4,7 +4,7 @@
 //
 // Replaces: the `llama-quantize` child process of the reference,
 //   ref/src/quantool/methods/llama_cpp/llama_cpp.py:165-178 (`GGUF._quantize_gguf`)
-// i.e. llama.cpp ggml-quants.c quantize_row_{q8_0,q4_0,q4_1,q5_0,q5_1,q2_K,q3_K,q4_K,q5_K,q6_K}_ref
+// i.e. llama.cpp ggml-quants.c quantize_row_{q8_0,q4_0,q4_1,q5_0,q5_1,q2_K,q3_K,q4_K,q5_K,q6_K}_ref, quantize_iq4_nl
 // and dequantize_row_* (§D.1-§D.5).
 //
 // Data layout in HBM: src is the tensor as a flat row-major array (rows are a multiple of the
@@ -27,15 +27,15 @@ namespace gguf {
 
 enum : int {
     T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
-    T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14
+    T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14, T_IQ4_NL = 20
 };
 
 __host__ __device__ constexpr int block_elems(int t) {
     return (t == T_Q2_K || t == T_Q3_K || t == T_Q4_K || t == T_Q5_K || t == T_Q6_K) ? 256
-         : (t == T_Q4_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_Q8_0) ? 32 : -1;
+         : (t == T_Q4_0 || t == T_Q4_1 || t == T_Q5_0 || t == T_Q5_1 || t == T_Q8_0 || t == T_IQ4_NL) ? 32 : -1;
 }
 __host__ __device__ constexpr int block_bytes(int t) {
-    return t == T_Q4_0 ? 18 : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q8_0 ? 34
+    return (t == T_Q4_0 || t == T_IQ4_NL) ? 18 : t == T_Q4_1 ? 20 : t == T_Q5_0 ? 22 : t == T_Q5_1 ? 24 : t == T_Q8_0 ? 34
          : t == T_Q2_K ? 84 : t == T_Q3_K ? 110 : t == T_Q4_K ? 144 : t == T_Q5_K ? 176 : t == T_Q6_K ? 210 : -1;
 }
 
@@ -410,6 +410,32 @@ __global__ void __launch_bounds__(256) pack_k23_kernel(const Segs segs) {
     }
 }
 
+// IQ4_NL: one thread per 32-element block (16 candidate scales x 32 table look-ups: ALU-bound like the K-quants)
+template <int DT, bool VIA_F16>
+__global__ void __launch_bounds__(256) pack_iq4nl_kernel(const Segs segs) {
+    __shared__ float sx[kSimpleBlocksPerCta][33];
+    __shared__ __align__(16) uint8_t sout[kSimpleBlocksPerCta * 18];
+    const int t = threadIdx.x;
+    for (int tile = blockIdx.x; tile < segs.total_tiles; tile += gridDim.x) {
+        int lt;
+        const Seg sg = seg_of(segs, tile, lt);
+        const void* __restrict__ src = sg.src;
+        uint8_t* __restrict__ dst = sg.dst;
+        const int64_t base = (int64_t)lt * kSimpleBlocksPerCta;
+        const int64_t left = sg.n - base;
+        const int nvalid = left < kSimpleBlocksPerCta ? (int)left : kSimpleBlocksPerCta;
+        stage_in<DT, VIA_F16, 32, 33, kSimpleBlocksPerCta * 32>(src, base * 32, (int64_t)nvalid * 32, sx);
+        __syncthreads();
+        float v[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l) v[l] = sx[t][l];
+        kq::iq4nl_block(v, sout + t * 18);
+        __syncthreads();
+        copy_out(dst + base * 18, sout, nvalid * 18);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // dequantize: one thread per 16 (simple) / 32 (K) output elements; packed blocks are read
 // byte-wise through the read-only path (they are 2-byte aligned at best), outputs are
@@ -438,6 +464,10 @@ __global__ void __launch_bounds__(256) dequant_simple_kernel(const uint8_t* __re
         const float d = ld_f16(b);
 #pragma unroll
         for (int j = 0; j < 16; j++) out[j] = (float)(int)(signed char)b[2 + 16 * h + j] * d;
+    } else if (TYPE == T_IQ4_NL) {
+        const float d = ld_f16(b);
+#pragma unroll
+        for (int j = 0; j < 16; j++) out[j] = d * kq::iq4nl_value(h ? (b[2 + j] >> 4) : (b[2 + j] & 0xF));
     } else {
         constexpr bool kSym = (TYPE == T_Q4_0 || TYPE == T_Q5_0);
         constexpr bool k5 = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
@@ -548,7 +578,9 @@ constexpr int tile_units() {
 
 template <int TYPE, int DT, bool VIA>
 static void launch_pack(const Segs& segs, cudaStream_t st) {
-    if constexpr (block_elems(TYPE) == 32) {
+    if constexpr (TYPE == T_IQ4_NL) {
+        pack_iq4nl_kernel<DT, VIA><<<grid_for(segs.total_tiles, 4), 256, 0, st>>>(segs);
+    } else if constexpr (block_elems(TYPE) == 32) {
         pack_simple_kernel<TYPE, DT, VIA><<<grid_for(segs.total_tiles, 8), 256, 0, st>>>(segs);
     } else if constexpr (TYPE == T_Q6_K) {
         pack_q6k_kernel<DT, VIA><<<grid_for(segs.total_tiles, 4), 256, 0, st>>>(segs);
@@ -585,6 +617,7 @@ static int dispatch_type(int ggml_type, const Segs& segs, int dt, int via, cudaS
         case T_Q5_0: return dispatch_dt<T_Q5_0>(segs, dt, via, st);
         case T_Q5_1: return dispatch_dt<T_Q5_1>(segs, dt, via, st);
         case T_Q8_0: return dispatch_dt<T_Q8_0>(segs, dt, via, st);
+        case T_IQ4_NL: return dispatch_dt<T_IQ4_NL>(segs, dt, via, st);
         case T_Q2_K: return dispatch_dt<T_Q2_K>(segs, dt, via, st);
         case T_Q3_K: return dispatch_dt<T_Q3_K>(segs, dt, via, st);
         case T_Q4_K: return dispatch_dt<T_Q4_K>(segs, dt, via, st);
@@ -687,6 +720,7 @@ int qt_gguf_dequantize(int ggml_type, const void* src, int64_t nrows, int64_t nc
             case T_Q5_0: dequant_simple_kernel<T_Q5_0><<<grid, 256, 0, st>>>(s, dst, nblk); break;
             case T_Q5_1: dequant_simple_kernel<T_Q5_1><<<grid, 256, 0, st>>>(s, dst, nblk); break;
             case T_Q8_0: dequant_simple_kernel<T_Q8_0><<<grid, 256, 0, st>>>(s, dst, nblk); break;
+            case T_IQ4_NL: dequant_simple_kernel<T_IQ4_NL><<<grid, 256, 0, st>>>(s, dst, nblk); break;
         }
     } else {
         const int64_t nthreads = nblk * 8;

@@ -1,4 +1,4 @@
-// K-quant (Q2_K / Q3_K / Q4_K / Q5_K / Q6_K) block math, written as phase functions that run once per
+// K-quant (Q2_K / Q3_K / Q4_K / Q5_K / Q6_K) and IQ4_NL block math, written as phase functions that run once per
 // thread with every cross-thread exchange going through a plain "shared" struct.  On the
 // GPU the struct lives in shared memory and phases are separated by __syncthreads(); the
 // host test harness (tests/host_emul.cu) runs the same phase functions in a loop over
@@ -682,6 +682,79 @@ QT_HD void q3k_phase_c(int t, S& s) {
         const int k = j - 8;
         o[96 + j] = (uint8_t)((l6[k] >> 4) | ((l6[k + 4] >> 4) << 2) | ((l6[k + 8] >> 4) << 4) | ((l6[k + 12] >> 4) << 6));
     }
+}
+
+// ------------------------------------------------------------------------------------
+// IQ4_NL (llama.cpp's fallback for Q2_K / Q3_K rows that are not a multiple of 256): one thread per 32-element
+// block.  quantize_row_iq4_nl_impl(32, 32, quant_weights = NULL, ntry = 7): weights x^2, 1 + 15 candidate scales.
+// ------------------------------------------------------------------------------------
+QT_HD float iq4nl_value(int i) {
+    // kvalues_iq4nl; a switch keeps it in immediates on both host and device
+    switch (i) {
+        case 0: return -127.f; case 1: return -104.f; case 2: return -83.f; case 3: return -65.f;
+        case 4: return -49.f; case 5: return -35.f; case 6: return -22.f; case 7: return -10.f;
+        case 8: return 1.f; case 9: return 13.f; case 10: return 25.f; case 11: return 38.f;
+        case 12: return 53.f; case 13: return 69.f; case 14: return 89.f; default: return 113.f;
+    }
+}
+
+// best_index_int8(16, kvalues_iq4nl, x): nearest table value, ties to the upper one
+QT_HD int iq4nl_best_index(float x) {
+    if (x <= -127.f) return 0;
+    if (x >= 113.f) return 15;
+    int ml = 0, mu = 15;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {          // 16 entries: the bisection ends after at most 4 halvings
+        if (mu - ml > 1) {
+            const int mav = (ml + mu) / 2;
+            if (x < iq4nl_value(mav)) mu = mav; else ml = mav;
+        }
+    }
+    return x - iq4nl_value(mu - 1) < iq4nl_value(mu) - x ? mu - 1 : mu;
+}
+
+QT_HD void iq4nl_sums(const float (&x)[32], float id, float& sumqx, float& sumq2) {
+    sumqx = 0.f; sumq2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float q = iq4nl_value(iq4nl_best_index(id * x[j]));
+        const float w = x[j] * x[j];
+        sumqx += w * q * x[j];
+        sumq2 += w * q * q;
+    }
+}
+
+// out: 18 bytes (fp16 d, 16 bytes of nibbles: element j low, j + 16 high)
+QT_HD void iq4nl_block(const float (&x)[32], uint8_t* out) {
+    float amax = 0.f, mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float ax = fabsf(x[j]);
+        if (ax > amax) { amax = ax; mx = x[j]; }
+    }
+    float scale = 0.f;
+    if (!(amax < 1e-15f)) {
+        float d = -mx / -127.f;
+        float sumqx, sumq2;
+        iq4nl_sums(x, 1 / d, sumqx, sumq2);
+        d = sumqx / sumq2;
+        float best = d * sumqx;
+#pragma unroll 1
+        for (int itry = -7; itry <= 7; ++itry) {
+            const float id = (itry + -127.f) / mx;
+            iq4nl_sums(x, id, sumqx, sumq2);
+            if (sumq2 > 0 && sumqx * sumqx > best * sumq2) {
+                d = sumqx / sumq2; best = d * sumqx;
+            }
+        }
+        scale = d;
+    }
+    const unsigned short db = __half_as_ushort(__float2half_rn(scale));
+    out[0] = (uint8_t)(db & 0xff); out[1] = (uint8_t)(db >> 8);
+    const float id = scale ? 1 / scale : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        out[2 + j] = (uint8_t)(iq4nl_best_index(id * x[j]) | (iq4nl_best_index(id * x[16 + j]) << 4));
 }
 
 }  // namespace kq

@@ -22,8 +22,7 @@ from .. import cabi
 BASE_TYPE = {"Q4_0": "Q4_0", "Q4_1": "Q4_1", "Q5_0": "Q5_0", "Q5_1": "Q5_1", "Q8_0": "Q8_0",
              "Q2_K": "Q2_K", "Q3_K_S": "Q3_K", "Q3_K_M": "Q3_K", "Q3_K_L": "Q3_K",
              "Q4_K_S": "Q4_K", "Q4_K_M": "Q4_K", "Q5_K_S": "Q5_K", "Q5_K_M": "Q5_K", "Q6_K": "Q6_K"}
-# row length not a multiple of 256 (llama.cpp falls back per tensor).  Q2_K / Q3_K fall back to IQ4_NL,
-# whose quantizer is not implemented by the sm_100a packers: such a tensor raises NotImplementedError.
+# row length not a multiple of 256: llama.cpp falls back per tensor (Q2_K / Q3_K -> IQ4_NL)
 FALLBACK = {"Q4_K": "Q5_0", "Q5_K": "Q5_1", "Q6_K": "Q8_0", "Q2_K": "IQ4_NL", "Q3_K": "IQ4_NL"}
 
 
@@ -78,9 +77,6 @@ def tensor_type(name: str, shape: Tuple[int, ...], ftype: str, n_layers: int, ha
         new = FALLBACK.get(new, new)
         if ncols % 32 != 0:
             new = "F16"
-        elif new == "IQ4_NL":
-            raise NotImplementedError(f"{name}: row length {ncols} is not a multiple of 256, llama.cpp falls back to "
-                                      f"IQ4_NL for {ftype}, which the sm_100a packers do not implement")
     return new
 
 

@@ -31,7 +31,7 @@ def main():
 
     from oracle import ggml_quants as oq
     kq = {"x": x}
-    for name in ("Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"):
+    for name in ("IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"):
         packed = oq.quantize(x, name)                  # oracle bytes (parity unpinned vs llama.cpp)
         kq[f"packed_{name}"] = packed
         kq[f"dequant_{name}"] = gq.dequantize(packed, getattr(T, name)).astype(np.float32)   # gguf-py reading them

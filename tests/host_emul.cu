@@ -50,6 +50,13 @@ static void emul_k23(const float* x, uint8_t* out, int64_t nsuper) {
 }
 
 extern "C" {
+void emul_iq4_nl(const float* x, uint8_t* out, int64_t nblocks) {
+    for (int64_t b = 0; b < nblocks; b++) {
+        float v[32];
+        for (int j = 0; j < 32; j++) v[j] = x[b * 32 + j];
+        iq4nl_block(v, out + b * 18);
+    }
+}
 void emul_q2_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k23<84, false>(x, out, nsuper); }
 void emul_q3_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k23<110, true>(x, out, nsuper); }
 void emul_q4_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k45<144, false>(x, out, nsuper); }

@@ -7,7 +7,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-ALL = ["Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"]
+ALL = ["Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"]
 KAT = {"Q8_0": "d8b3256c9fd9ae4c", "Q4_0": "d153bbca62836335", "Q5_0": "c9154c30f4008bbe",
        "Q4_1": "f1844724bdbc3ca3", "Q5_1": "2cce57372f71162a"}
 
@@ -106,7 +106,7 @@ def test_full_size_roundtrip_property(qtype):
         assert (a != b).float().mean().item() < 1e-3
 
 
-@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q5_1", "Q3_K", "Q4_K", "Q6_K"])
+@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q5_1", "IQ4_NL", "Q3_K", "Q4_K", "Q6_K"])
 def test_batch_launch_equals_per_tensor(qtype):
     """Many tensors in one launch (segment table) == one launch per tensor, including an empty tensor, tensors
     smaller than a CTA tile and tensors that end in the middle of one."""

@@ -54,13 +54,13 @@ def test_golden_fixtures():
     for q in ("Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1"):
         assert np.array_equal(oq.quantize(s["x"], q), s[f"packed_{q}"]), q
     k = np.load(os.path.join(GOLD, "gguf_k_quants.npz"))
-    for q in ("Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"):
+    for q in ("IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"):
         packed = oq.quantize(k["x"], q)
         assert np.array_equal(packed, k[f"packed_{q}"]), q
         assert np.array_equal(oq.dequantize(packed, q, 512).view(np.uint32), k[f"dequant_{q}"].view(np.uint32)), q
 
 
-@pytest.mark.parametrize("qtype", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+@pytest.mark.parametrize("qtype", ["IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
 def test_k_quants_two_independent_restatements_agree(qtype):
     from gguf import GGMLQuantizationType as T
     from gguf import quants as gq
@@ -71,10 +71,10 @@ def test_k_quants_two_independent_restatements_agree(qtype):
     d = gq.dequantize(a, getattr(T, qtype)).astype(np.float32)
     assert np.array_equal(d.view(np.uint32), oq.dequantize(a, qtype, 1024).view(np.uint32))
     rmse = float(np.sqrt(np.mean((d[7:] - x[7:]) ** 2)))
-    assert rmse < {"Q2_K": 0.40, "Q3_K": 0.20, "Q4_K": 0.09, "Q5_K": 0.045, "Q6_K": 0.025}[qtype]
+    assert rmse < {"IQ4_NL": 0.10, "Q2_K": 0.40, "Q3_K": 0.20, "Q4_K": 0.09, "Q5_K": 0.045, "Q6_K": 0.025}[qtype]
 
 
-@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+@pytest.mark.parametrize("qtype", ["Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1", "IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
 def test_dequant_equals_gguf_py(qtype):
     from gguf import GGMLQuantizationType as T
     from gguf import quants as gq
@@ -95,7 +95,7 @@ def test_threads_do_not_change_bytes():
 
 
 @pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
-@pytest.mark.parametrize("qtype", ["Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
+@pytest.mark.parametrize("qtype", ["IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"])
 def test_cuda_kquant_device_math_on_host_equals_oracle(qtype):
     """The __host__ __device__ phase functions the CUDA kernels run, executed on the CPU."""
     from oracle import ggml_quants as oq
@@ -113,8 +113,9 @@ def test_cuda_kquant_device_math_on_host_equals_oracle(qtype):
     x = _edge(np.random.default_rng(2), 40, 1024)
     ref = oq.quantize(x, qtype)
     out = np.zeros_like(ref)
+    units = x.size // (32 if qtype == "IQ4_NL" else 256)
     getattr(L, "emul_" + qtype.lower().replace("_k", "_K"))(ctypes.c_void_p(x.ctypes.data),
-                                                          ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(x.size // 256))
+                                                          ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(units))
     assert np.array_equal(out, ref)
 
 

@@ -182,8 +182,8 @@ def test_gguf_tensor_type_table_low_bit_levels():
     assert t("blk.9.ffn_down.weight", (4096, 14336), "Q3_K_L") == "Q5_K"
     assert t("blk.9.attn_output.weight", (4096, 4096), "Q3_K_L") == "Q5_K"
     assert t("blk.9.attn_v.weight", (1024, 8192), "Q3_K_S", L=80, h=64) == "Q5_K"    # 70B: shared attn_v
-    with pytest.raises(NotImplementedError):                                   # 576 % 256 != 0 -> IQ4_NL
-        t("blk.0.attn_q.weight", (576, 576), "Q3_K_S", L=30, kv=3)
+    assert t("blk.0.attn_q.weight", (576, 576), "Q3_K_S", L=30, kv=3) == "IQ4_NL"    # 576 % 256 != 0
+    assert t("blk.0.ffn_down.weight", (576, 1536), "Q2_K", L=30, kv=3) == "Q3_K"
 
 
 def test_autogptq_and_autoawq_views_are_pure_repacks_cpu():

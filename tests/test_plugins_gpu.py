@@ -112,8 +112,15 @@ def test_gguf_plugin_end_to_end_bit_exact_vs_oracle(tmp_path):
             assert {"Q5_0", "Q8_0", "Q4_K", "Q6_K", "F32"} <= seen_types
     q.save_pretrained(str(tmp_path / "saved"))
     assert sorted(os.listdir(tmp_path / "saved")) == ["tiny-llama-Q4_K_M.gguf", "tiny-llama-Q8_0.gguf"]
-    with pytest.raises(NotImplementedError):
-        q.quantize(model=path, level="Q3_K_S", output_dir=str(tmp_path / "gg2"))
+    # 576-wide rows cannot hold K-quants: Q3_K_S falls back to IQ4_NL there (llama.cpp's rule), bit-exact vs the oracle
+    out = q.quantize(model=path, level="Q3_K_S", output_dir=str(tmp_path / "gg2"))
+    r = gguf.GGUFReader(out)
+    types = {t.name: t for t in r.tensors}
+    tq = types["blk.0.attn_q.weight"]
+    assert tq.tensor_type.name == "IQ4_NL" and types["blk.0.ffn_down.weight"].tensor_type.name == "Q3_K"
+    wq = gguf_file._permute_qk(sd["model.layers.0.self_attn.q_proj.weight"], shape.num_attention_heads)
+    ref = oq.quantize(oq.round_f16(wq.float().numpy()), "IQ4_NL")
+    assert np.array_equal(np.asarray(tq.data).reshape(ref.shape), ref)
 
 
 def test_gguf_low_bit_levels_bit_exact_vs_oracle(tmp_path):
