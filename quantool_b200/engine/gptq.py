@@ -48,6 +48,14 @@ class HessianAccumulator:
         self._diag_synced = False
         self.n_samples += int(n_samples)
 
+    def reset(self) -> None:
+        """Reuse the buffers for the next decoder layer (stream-ordered after the previous consumers)."""
+        self.H.zero_()
+        self.diag.zero_()
+        self.n_samples = 0
+        self._final = False
+        self._diag_synced = True
+
     def sync_diagonal(self) -> None:
         if not self._diag_synced:
             cabi.hessian_set_diagonal(self.H, self.diag)

@@ -14,6 +14,8 @@ Single node, one process per GPU:
     independent given U), and the fake-quantized rows / scales are all-gathered.
 """
 from dataclasses import dataclass, field
+import queue
+import threading
 from typing import Dict, List, Optional
 
 import torch
@@ -416,31 +418,90 @@ def _layer_weights(host_sd, pre: str, dev, res) -> Dict[str, torch.Tensor]:
     return w
 
 
+class _PinnedRing:
+    """A few page-locked staging buffers per device, created once and kept: page-locking is slow (~1 GB/s), so
+    pinning a fresh host tensor per artifact made the D2H side of a run cost seconds."""
+    SLOT_BYTES = 64 << 20
+    NSLOTS = 4
+    _cache: Dict[str, "_PinnedRing"] = {}
+
+    def __init__(self):
+        self.slots = [torch.empty((self.SLOT_BYTES,), dtype=torch.uint8, pin_memory=True) for _ in range(self.NSLOTS)]
+        self.free = [threading.Event() for _ in range(self.NSLOTS)]
+        for e in self.free:
+            e.set()
+        self.next = 0
+
+    @classmethod
+    def get(cls, dev) -> "_PinnedRing":
+        key = str(dev)
+        if key not in cls._cache:
+            cls._cache[key] = cls()
+        return cls._cache[key]
+
+
 class _HostSink:
-    """Asynchronous D2H of artifact tensors into pinned host memory on a copy stream."""
+    """Asynchronous D2H of artifact tensors: device -> pinned staging ring on a copy stream, then a worker thread
+    moves each piece into its (pageable) result tensor as soon as its copy event has fired."""
 
     def __init__(self, dev, res: "ModelQuantResult"):
         self.dev = dev
         self.res = res
         self.stream = torch.cuda.Stream(device=dev)
+        self.ring = _PinnedRing.get(dev)
+        self.q: "queue.Queue" = queue.Queue()
+        self.err: Optional[BaseException] = None
+        self.worker = threading.Thread(target=self._drain, daemon=True)
+        self.worker.start()
+
+    def _drain(self) -> None:
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            ev, slot, out_flat, off, n = item
+            try:
+                ev.synchronize()
+                out_flat[off: off + n].copy_(self.ring.slots[slot][:n])
+            except BaseException as e:      # surfaced by finish()
+                self.err = e
+            finally:
+                self.ring.free[slot].set()
 
     def put(self, key: str, t: torch.Tensor) -> None:
+        self.res.d2h_bytes += t.numel() * t.element_size()
         if not t.is_cuda:
             self.res.tensors[key] = t
-            self.res.d2h_bytes += t.numel() * t.element_size()
             return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.dev))
-        self.stream.wait_event(ev)
-        with torch.cuda.stream(self.stream):
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-        t.record_stream(self.stream)
-        self.res.tensors[key] = h
-        self.res.d2h_bytes += h.numel() * h.element_size()
+        out = torch.empty(t.shape, dtype=t.dtype)
+        self.res.tensors[key] = out
+        if t.numel() == 0:
+            return
+        src = t.contiguous().reshape(-1).view(torch.uint8)
+        out_flat = out.reshape(-1).view(torch.uint8)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.dev))
+        self.stream.wait_event(ready)
+        ring = self.ring
+        for off in range(0, src.numel(), ring.SLOT_BYTES):
+            n = min(ring.SLOT_BYTES, src.numel() - off)
+            slot = ring.next
+            ring.next = (slot + 1) % ring.NSLOTS
+            ring.free[slot].wait()
+            ring.free[slot].clear()
+            with torch.cuda.stream(self.stream):
+                ring.slots[slot][:n].copy_(src[off: off + n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self.q.put((ev, slot, out_flat, off, n))
+        src.record_stream(self.stream)
 
     def finish(self) -> None:
+        self.q.put(None)
+        self.worker.join()
         self.stream.synchronize()
+        if self.err is not None:
+            raise self.err
 
 
 class _WeightPrefetcher:
@@ -506,15 +567,20 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
     losses = {}
     L = shape.num_hidden_layers
     chunk_samples = max(1, min(chunk_samples, n_local)) if n_local else 1
+    accs = cap = None
     for l in range(L):
         pre = f"model.layers.{l}."
         w = fetch.get(pre, f"model.layers.{l + 1}." if l + 1 < L else None)
         if smooth_strength is not None:
             from .smoothquant import smooth_layer
             smooth_layer(shape, w, h, cos, sin, smooth_strength, chunk_samples, dist)
-        # pass 1: statistics with the layer's original weights
-        accs = {n: HessianAccumulator(k, dev) for n, k in dims.items()}
-        cap = {n: torch.empty((chunk_samples * seq, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
+        # pass 1: statistics with the layer's original weights (accumulators and capture buffers are reused)
+        if accs is None:
+            accs = {n: HessianAccumulator(k, dev) for n, k in dims.items()}
+            cap = {n: torch.empty((chunk_samples * seq, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
+        else:
+            for acc in accs.values():
+                acc.reset()
         for c0 in range(0, n_local, chunk_samples):
             hb = h[c0: c0 + chunk_samples]
             rows = hb.shape[0] * seq
@@ -522,7 +588,6 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
             for n in dims:
                 accs[n].add(cap[n][:rows], hb.shape[0])
                 lq.launches += 1
-        del cap
         hess = {}
         for n in dims:
             accs[n].sync_diagonal()
@@ -530,7 +595,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
             hess[n] = accs[n].finalize(n_total)
             lq.launches += 1
         results = lq.quantize_layer(w, hess)
-        del hess, accs
+        del hess
         for lin, r in results.items():
             w[f"{lin}.weight"] = r.weight
             art, _codes = compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args, fmt=fmt)
