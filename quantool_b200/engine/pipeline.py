@@ -421,8 +421,8 @@ def _layer_weights(host_sd, pre: str, dev, res) -> Dict[str, torch.Tensor]:
 class _PinnedRing:
     """A few page-locked staging buffers per device, created once and kept: page-locking is slow (~1 GB/s), so
     pinning a fresh host tensor per artifact made the D2H side of a run cost seconds."""
-    SLOT_BYTES = 64 << 20
-    NSLOTS = 4
+    SLOT_BYTES = 32 << 20
+    NSLOTS = 16        # a decoder layer's ~30 artifact tensors (most of them tiny) must not make the host wait
     _cache: Dict[str, "_PinnedRing"] = {}
 
     def __init__(self):
