@@ -92,19 +92,18 @@ int qt_unpack_int32(const int32_t* packed, int N, int K, int num_bits, int8_t* c
  * quantize_weight), which the reference reaches by building GPTQModifier at
  * ref/src/quantool/methods/llm_compressor/gptq/gptq.py:86 and running llmcompressor.oneshot at
  * ref/src/quantool/methods/llm_compressor/base.py:159-161. */
-/* H fp32 [K,K] (raw sums, caller zeroes it first) += X^T X on upper-triangle tiles; X bf16 [T,K]; tcgen05 */
-int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* stream);
+/* H fp32 [K,K] (raw sums, caller zeroes it first) += X^T X on upper-triangle tiles; X [T,K] of `dtype` = QT_BF16 or
+ * QT_F16 (the model's activation dtype goes to the tensor cores unchanged; QT_F32 -> QT_ERR_UNSUPPORTED); tcgen05 */
+int qt_hessian_accumulate(const void* X, int dtype, int64_t T, int K, float* H, void* stream);
 /* H <- factor * H (factor = 2 / n_samples) on the upper triangle, mirrored to the lower */
 int qt_hessian_finalize(float* H, int K, float factor, void* stream);
 /* Exact diagonal: the tensor-core accumulator truncates, which biases the sums of squares on the diagonal by
  * ~-5e-6 and can reorder argsort(diag H) (the act_order permutation).  diag[c] += sum_t X[t][c]^2 in fp32
  * round-to-nearest, deterministic; scratch = 32*K floats.  qt_hessian_set_diagonal writes the raw sums into H
  * (before finalize / before a cross-rank reduction). */
-int qt_hessian_diag_accumulate(const void* X, int64_t T, int K, float* diag, float* scratch, void* stream);
+int qt_hessian_diag_accumulate(const void* X, int dtype, int64_t T, int K, float* diag, float* scratch, void* stream);
 int qt_hessian_set_diagonal(float* H, int K, const float* diag, void* stream);
 int qt_hessian_set_splits(int splits);   /* tuning: force the token split count (0 = heuristic) */
-/* fp32 SIMT cross-check of qt_hessian_accumulate (tests / smoke only) */
-int qt_hessian_accumulate_reference(const void* X, int64_t T, int K, float* H, void* stream);
 /* dead[i] = (H[i][i]==0); damp = percdamp*mean(diag); Hf = J P^T (H' + damp I) P J (lower triangle),
  * perm int32 [K] or NULL, dead uint8 [K], damp_scratch fp32 [1] */
 int qt_gptq_prepare_hessian(const float* H, const int* perm, int K, float percdamp, float* Hf, uint8_t* dead,
@@ -138,13 +137,10 @@ int qt_gptq_permute_out(const float* Wp, const int* inv_perm, void* out, int dty
 int qt_gptq_quantize_weight(float* W, const float* U, const float* U_hi, const float* U_lo, float* err_scratch,
                             float* scale, float* zp, const int* g_idx, float* losses, int N, int K, int G,
                             int group_size, int num_bits, int symmetric, int mode, void* stream);
-/* tensor-core lazy-batch update (tcgen05 kind::tf32, 3-product split for fp32 fidelity):
- * x -> hi (tf32-exact) + lo ; W[:, i2:] -= (err_hi+err_lo)[M,128] * U[i1:i1+128, i2:], U^T = u_hi+u_lo */
+/* tf32 operand splits of the 3xTF32 tensor-core GEMMs (qt_gemm_tf32x3): x -> hi (tf32-exact) + lo */
 int qt_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
-/* ut_hi + ut_lo = U^T (the K-major B operand of the lazy update) */
+/* ut_hi + ut_lo = U^T (the K-major B operand of the lazy-batch update W[:, i2:] -= Err * U[i1:i2, i2:]) */
 int qt_split_tf32_transpose(const float* U, float* ut_hi, float* ut_lo, int K, void* stream);
-int qt_gptq_lazy_update_tf32x3(const float* err_hi, const float* err_lo, const float* u_hi, const float* u_lo,
-                               float* W, int M, int K, int i1, int i2, void* stream);
 
 /* ---- SmoothQuant / AWQ --------------------------------------------------------------------------
  * Replaces UPSTREAM llmcompressor SmoothQuantModifier built at

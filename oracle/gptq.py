@@ -76,8 +76,11 @@ def _channel_args(args: QuantizationArgs) -> QuantizationArgs:
 
 # ---- §A.2 - §A.5 -----------------------------------------------------------------------------
 def quantize_weight(weight: torch.Tensor, H: torch.Tensor, args: QuantizationArgs, blocksize: int = 128,
-                    percdamp: float = 0.01, return_hinv: bool = False):
-    """Returns (loss, W_q [model dtype], scale [model dtype], zero_point int8, g_idx or None)."""
+                    percdamp: float = 0.01, return_hinv: bool = False, perm_override: Optional[torch.Tensor] = None):
+    """Returns (loss, W_q [model dtype], scale [model dtype], zero_point int8, g_idx or None).
+    `perm_override` (test hook, not in upstream): use this act_order permutation instead of argsort(diag H) -
+    lets a test separate "the two fp32 diagonals order near-ties differently" from every other source of
+    disagreement (tests/test_gptq_gpu.py::test_gptq_baseline_widths_own_hessian)."""
     final_dtype = weight.dtype
     W = weight.clone().to(GPTQ_PRECISION)
     H = H.clone()
@@ -89,11 +92,11 @@ def quantize_weight(weight: torch.Tensor, H: torch.Tensor, args: QuantizationArg
         gs = args.group_size
         g_idx = torch.arange(K, dtype=torch.int) // gs
         if actorder == ActivationOrdering.GROUP:
-            W, H, perm = _apply_activation_ordering(W, H)
+            W, H, perm = _apply_activation_ordering(W, H, perm_override)
             scale, zero_point = minmax_qparams(W, args)
         elif actorder == ActivationOrdering.WEIGHT:
             scale, zero_point = minmax_qparams(W, args)
-            W, H, perm = _apply_activation_ordering(W, H)
+            W, H, perm = _apply_activation_ordering(W, H, perm_override)
             g_idx = g_idx[perm]
         else:
             scale, zero_point = minmax_qparams(W, args)
@@ -169,8 +172,9 @@ def quantize_weight(weight: torch.Tensor, H: torch.Tensor, args: QuantizationArg
     return out
 
 
-def _apply_activation_ordering(W: torch.Tensor, H: torch.Tensor):
-    perm = torch.argsort(torch.diag(H), descending=True, stable=True)
+def _apply_activation_ordering(W: torch.Tensor, H: torch.Tensor, perm_override: Optional[torch.Tensor] = None):
+    perm = torch.argsort(torch.diag(H), descending=True, stable=True) if perm_override is None \
+        else perm_override.to(torch.int64)
     return W[:, perm], H[perm][:, perm], perm
 
 

@@ -36,11 +36,10 @@ _SIGS = {
     "qt_pack_int32": [_vp, _i32, _i32, _i32, _vp, _vp],
     "qt_unpack_int32": [_vp, _i32, _i32, _i32, _vp, _vp],
     "qt_hessian_set_splits": [_i32],
-    "qt_hessian_accumulate": [_vp, _i64, _i32, _vp, _vp],
+    "qt_hessian_accumulate": [_vp, _i32, _i64, _i32, _vp, _vp],
     "qt_hessian_finalize": [_vp, _i32, _f32, _vp],
-    "qt_hessian_diag_accumulate": [_vp, _i64, _i32, _vp, _vp, _vp],
+    "qt_hessian_diag_accumulate": [_vp, _i32, _i64, _i32, _vp, _vp, _vp],
     "qt_hessian_set_diagonal": [_vp, _i32, _vp, _vp],
-    "qt_hessian_accumulate_reference": [_vp, _i64, _i32, _vp, _vp],
     "qt_gptq_prepare_hessian": [_vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp],
     "qt_gptq_hinv_factor": [_vp, _vp, _vp, _i32, _vp, _vp],
     "qt_gptq_hinv_factor_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp],
@@ -66,7 +65,6 @@ _SIGS = {
     "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "qt_split_tf32": [_vp, _vp, _vp, _i64, _vp],
     "qt_split_tf32_transpose": [_vp, _vp, _vp, _i32, _vp],
-    "qt_gptq_lazy_update_tf32x3": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
 }
 _RESTYPE = {"qt_last_error": ctypes.c_char_p, "qt_launch_count": ctypes.c_ulonglong,
             "qt_gguf_batch_table_bytes": ctypes.c_int64}
@@ -279,23 +277,24 @@ def unpack_int32(packed: torch.Tensor, num_bits: int, K: int) -> torch.Tensor:
 # GPTQ
 # ---------------------------------------------------------------------------------------
 def hessian_accumulate(x: torch.Tensor, H: torch.Tensor) -> None:
-    """H (fp32 [K,K], raw sums, upper tiles) += x^T x.  x: [T, K] bf16."""
+    """H (fp32 [K,K], raw sums, upper tiles) += x^T x.  x: [T, K] bf16 or fp16 (fed to the tensor cores as is)."""
     _dev(x, "x"); _dev(H, "H")
-    if x.dtype != torch.bfloat16:
-        raise QtError("hessian_accumulate takes bf16 activations")
+    if x.dtype not in (torch.bfloat16, torch.float16):
+        raise QtError(f"hessian_accumulate takes bf16 or fp16 activations, got {x.dtype} (load the model in its "
+                      "16-bit dtype; there is no fp32 tensor-core Hessian and no silent down-cast)")
     T, K = x.shape
     assert H.shape == (K, K) and H.dtype == torch.float32
     with torch.cuda.device(x.device):
-        _check(lib().qt_hessian_accumulate(_p(x), T, K, _p(H), _stream()), "qt_hessian_accumulate")
+        _check(lib().qt_hessian_accumulate(_p(x), _DT[x.dtype], T, K, _p(H), _stream()), "qt_hessian_accumulate")
 
 
 def hessian_diag_accumulate(x: torch.Tensor, diag: torch.Tensor, scratch: torch.Tensor) -> None:
-    """diag (fp32 [K], raw sums) += column sums of squares of x [T, K] bf16, fp32 round-to-nearest."""
+    """diag (fp32 [K], raw sums) += column sums of squares of x [T, K] bf16/fp16, fp32 round-to-nearest."""
     _dev(x, "x"); _dev(diag, "diag"); _dev(scratch, "scratch")
     T, K = x.shape
-    assert x.dtype == torch.bfloat16 and diag.dtype == torch.float32 and scratch.numel() >= 32 * K
+    assert x.dtype in (torch.bfloat16, torch.float16) and diag.dtype == torch.float32 and scratch.numel() >= 32 * K
     with torch.cuda.device(x.device):
-        _check(lib().qt_hessian_diag_accumulate(_p(x), T, K, _p(diag), _p(scratch), _stream()),
+        _check(lib().qt_hessian_diag_accumulate(_p(x), _DT[x.dtype], T, K, _p(diag), _p(scratch), _stream()),
                "qt_hessian_diag_accumulate")
 
 
@@ -303,13 +302,6 @@ def hessian_set_diagonal(H: torch.Tensor, diag: torch.Tensor) -> None:
     with torch.cuda.device(H.device):
         _check(lib().qt_hessian_set_diagonal(_p(_dev(H, "H")), H.shape[0], _p(_dev(diag, "diag")), _stream()),
                "qt_hessian_set_diagonal")
-
-
-def hessian_accumulate_reference(x: torch.Tensor, H: torch.Tensor) -> None:
-    T, K = x.shape
-    with torch.cuda.device(x.device):
-        _check(lib().qt_hessian_accumulate_reference(_p(_dev(x, "x")), T, K, _p(_dev(H, "H")), _stream()),
-               "qt_hessian_accumulate_reference")
 
 
 def hessian_finalize(H: torch.Tensor, factor: float) -> None:
@@ -440,13 +432,6 @@ def split_tf32_transpose(U: torch.Tensor, hi: Optional[torch.Tensor] = None, lo:
     with torch.cuda.device(U.device):
         _check(lib().qt_split_tf32_transpose(_p(U), _p(hi), _p(lo), K, _stream()), "qt_split_tf32_transpose")
     return hi, lo
-
-
-def gptq_lazy_update_tf32x3(err_hi, err_lo, u_hi, u_lo, W, i1: int, i2: int) -> None:
-    M, K = W.shape
-    with torch.cuda.device(W.device):
-        _check(lib().qt_gptq_lazy_update_tf32x3(_p(err_hi), _p(err_lo), _p(u_hi), _p(u_lo), _p(W), M, K, i1, i2,
-                                                _stream()), "qt_gptq_lazy_update_tf32x3")
 
 
 def gptq_quantize_weight(wp: torch.Tensor, U: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor,

@@ -28,7 +28,7 @@ SOURCES = {
     "linalg.cu": [],
     "gptq.cu": [],
     "hessian.cu": [],
-    "lazy_gemm.cu": [],
+    "split.cu": [],
     "smooth.cu": [],
     "awq.cu": [],
     "forward.cu": [],

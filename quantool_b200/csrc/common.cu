@@ -25,7 +25,7 @@ const char* last_error() { return g_err; }
 
 extern "C" {
 const char* qt_last_error(void) { return qt::last_error(); }
-int qt_abi_version(void) { return 1; }
+int qt_abi_version(void) { return 2; }
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 unsigned long long qt_launch_count(void) { return qt::launch_count(); }
 int qt_device_sm_count(void) {

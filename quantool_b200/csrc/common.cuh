@@ -60,7 +60,7 @@ QT_D float bf16_bits_to_float(uint32_t b16) { return __uint_as_float(b16 << 16);
 QT_D float f16_bits_to_float(uint32_t h16) { return __half2float(__ushort_as_half((unsigned short)h16)); }
 
 // x ~= hi + lo with hi = tf32(x) and lo = tf32(x - hi), both rounded to nearest (low 13 mantissa bits cleared): the
-// operand form of the 3xTF32 tensor-core GEMMs (lazy_gemm.cu, tgemm.cu).  x - hi is exact in fp32; rounding it here
+// operand form of the 3xTF32 tensor-core GEMMs (tgemm.cu; splits in split.cu).  x - hi is exact in fp32; rounding it here
 // (instead of letting the tensor core truncate the low bits when it reads the operand) halves the operand error and
 // removes its bias: |x - hi - lo| <= 2^-22 |x|.
 QT_D float tf32_rn(float e) {

@@ -54,15 +54,16 @@ QT_D uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) 
     return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both MN-major, N=256, M=128
-constexpr uint32_t make_idesc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
-           ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both MN-major, N=256, M=128
+constexpr uint32_t make_idesc(bool bf16) {
+    return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct Sched {
     int K, NI, NJ, ntiles, S, nkb;  // nkb = ceil(T / BKT)
     int nunits;
+    uint32_t idesc;                 // operand format (bf16 / fp16) is a run-time property of the activations
 };
 
 // tile index -> (im, jn).  The upper-triangle tile set {im <= 2 jn + 1} is walked in compact
@@ -144,7 +145,7 @@ hessian_syrk_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc();
+            const uint32_t idesc = s.idesc;
             uint32_t it = 0, li = 0;
             for (int u = blockIdx.x; u < s.nunits; u += gridDim.x, li++) {
                 const int split = u / s.ntiles;
@@ -243,19 +244,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(float* __restrict__ H, in
     }
 }
 
-// plain fp32 SIMT reference (no tensor cores): used by tests and smoke to cross-check the
-// tcgen05 path at sizes where the CPU oracle is too slow.  One thread per upper-triangle entry.
-__global__ void __launch_bounds__(256) syrk_reference_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ H,
-                                                             long long T, int K) {
-    const int j = blockIdx.x * 16 + (threadIdx.x & 15);
-    const int i = blockIdx.y * 16 + (threadIdx.x >> 4);
-    if (i >= K || j >= K || j < i) return;
-    float acc = 0.f;
-    for (long long t = 0; t < T; t++)
-        acc = fmaf(__bfloat162float(X[t * K + i]), __bfloat162float(X[t * K + j]), acc);
-    H[(long long)i * K + j] += acc;
-}
-
 // ---- exact diagonal -------------------------------------------------------------------------------
 // The tensor cores add into the fp32 TMEM accumulator with truncation; over the ~1000-instruction chain of one
 // work unit that biases a sum of squares by about -5e-6 relative (measured), enough to reorder near-equal
@@ -263,7 +251,8 @@ __global__ void __launch_bounds__(256) syrk_reference_kernel(const __nv_bfloat16
 // separately with FFMA in round-to-nearest: a deterministic two-stage column reduction (row slabs -> partial
 // sums -> fixed-order total), one extra streaming pass over X (~3 % of the SYRK time).
 constexpr int DIAG_SLABS = 32;
-__global__ void __launch_bounds__(256) diag_partial_kernel(const __nv_bfloat16* __restrict__ X, long long T, int K,
+template <int DT>
+__global__ void __launch_bounds__(256) diag_partial_kernel(const void* __restrict__ X, long long T, int K,
                                                            float* __restrict__ partial) {
     __shared__ float sa[8][256 + 8];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -275,7 +264,7 @@ __global__ void __launch_bounds__(256) diag_partial_kernel(const __nv_bfloat16* 
         const long long r0 = T * blockIdx.y / gridDim.y, r1 = T * (blockIdx.y + 1) / gridDim.y;
         for (long long r = r0 + ty; r < r1; r += 8) {
             float v[8];
-            load8<QT_BF16>(X, (r * K + c0) / 8, v);
+            load8<DT>(X, (r * K + c0) / 8, v);
 #pragma unroll
             for (int i = 0; i < 8; i++) a[i] = fmaf(v[i], v[i], a[i]);
         }
@@ -318,8 +307,15 @@ extern "C" {
 int qt_hessian_set_splits(int s) { g_force_splits = s; return QT_OK; }
 
 // H[K,K] (fp32, zero-initialised by the caller before the first batch) += X^T X over the upper
-// triangle tiles.  X: [T, K] bf16 row-major.  K % 8 == 0.
-int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* stream) {
+// triangle tiles.  X: [T, K] bf16 or fp16 row-major (the model's activation dtype, fed to the tensor cores as it
+// is: upstream casts the same values to fp32, so no precision is dropped on the way in).  K % 8 == 0.
+int qt_hessian_accumulate(const void* X, int dtype, int64_t T, int K, float* H, void* stream) {
+    if (dtype == QT_F32) {
+        set_last_error("qt_hessian_accumulate: fp32 activations are not supported (bf16 / fp16 tensor-core operands)",
+                       cudaSuccess);
+        return QT_ERR_UNSUPPORTED;
+    }
+    if (dtype != QT_BF16 && dtype != QT_F16) return QT_ERR_INVALID;
     if (T < 0 || K <= 0 || (K & 7) || !H) return QT_ERR_INVALID;
     if (T == 0) return QT_OK;     // an empty batch adds nothing (X may be a null pointer then)
     if (!X) return QT_ERR_INVALID;
@@ -332,12 +328,13 @@ int qt_hessian_accumulate(const void* X, int64_t T, int K, float* H, void* strea
     const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)BKT};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(X), gdim, gstride, box, estr,
+    CUresult cr = enc(&tmap, dtype == QT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(X), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue); return QT_ERR_CUDA; }
 
     Sched s;
+    s.idesc = make_idesc(dtype == QT_BF16);
     s.K = K;
     s.NI = (K + BM - 1) / BM;
     s.NJ = (K + BN - 1) / BN;
@@ -392,14 +389,16 @@ int qt_hessian_finalize(float* H, int K, float factor, void* stream) {
 }
 
 // diag[c] += sum_t X[t][c]^2 in fp32 round-to-nearest (deterministic); scratch: 32 * K floats
-int qt_hessian_diag_accumulate(const void* X, int64_t T, int K, float* diag, float* scratch, void* stream) {
+int qt_hessian_diag_accumulate(const void* X, int dtype, int64_t T, int K, float* diag, float* scratch, void* stream) {
+    if (dtype != QT_BF16 && dtype != QT_F16) return QT_ERR_INVALID;
     if (T < 0 || K <= 0 || (K & 7) || !diag || !scratch) return QT_ERR_INVALID;
     if (T == 0) return QT_OK;
     if (!X || ((uintptr_t)X & 15)) return QT_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const int slabs = T < DIAG_SLABS ? (int)T : DIAG_SLABS;
     dim3 grid((K + 255) / 256, slabs);
-    diag_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)X, T, K, scratch);
+    if (dtype == QT_BF16) diag_partial_kernel<QT_BF16><<<grid, 256, 0, st>>>(X, T, K, scratch);
+    else diag_partial_kernel<QT_F16><<<grid, 256, 0, st>>>(X, T, K, scratch);
     int rc = check_launch("hessian_diag_partial");
     if (rc) return rc;
     diag_total_kernel<<<(K + 255) / 256, 256, 0, st>>>(scratch, K, slabs, diag);
@@ -411,14 +410,6 @@ int qt_hessian_set_diagonal(float* H, int K, const float* diag, void* stream) {
     if (!H || !diag || K <= 0) return QT_ERR_INVALID;
     set_diag_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(H, K, diag);
     return check_launch("hessian_set_diagonal");
-}
-
-// fp32 SIMT cross-check (test infrastructure on the device; never on the product path)
-int qt_hessian_accumulate_reference(const void* X, int64_t T, int K, float* H, void* stream) {
-    if (!X || !H || T < 0 || K <= 0) return QT_ERR_INVALID;
-    dim3 grid((K + 15) / 16, (K + 15) / 16);
-    syrk_reference_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, H, T, K);
-    return check_launch("syrk_reference");
 }
 
 }  // extern "C"

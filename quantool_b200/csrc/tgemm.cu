@@ -8,7 +8,7 @@
 // tcgen05 kind::tf32 with operand splitting ("3xTF32"): x ~= hi + lo, hi = tf32(x), lo = tf32(x - hi) (about 22 mantissa bits), and
 //     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi   (dropped lo*lo term ~2^-22 relative), fp32 accumulation in TMEM.
 // Callers hand in the split operands (they are produced once per panel / block by the split kernels and reused
-// by many tiles).  Same pipeline as the lazy-batch kernel (lazy_gemm.cu), generalised: arbitrary inner
+// by many tiles).  Pipeline: TMA-staged operand ring -> one-thread tcgen05.mma issue -> TMEM epilogue; arbitrary inner
 // dimension, batches of diagonal blocks, triangular operands (k range trimmed per tile), lower-tiles-only
 // SYRK, and two epilogues - TMA store (C =) or TMA reduce-add in L2 (C +=), so C is never read by the SM.
 //

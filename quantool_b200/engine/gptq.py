@@ -35,10 +35,7 @@ class HessianAccumulator:
         assert not self._final
         if n_samples is None:
             n_samples = x.shape[0] if x.dim() == 3 else 1
-        x2 = x.reshape(-1, x.shape[-1])
-        if x2.dtype != torch.bfloat16:
-            x2 = x2.to(torch.bfloat16)
-        x2 = x2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()      # bf16 or fp16, as the model produces it (no cast)
         if syrk_events is not None:
             syrk_events[0].record()
         cabi.hessian_accumulate(x2, self.H)
@@ -78,6 +75,7 @@ class GPTQResult:
     g_idx: Optional[torch.Tensor]    # [K] int32 (actorder="group" only)
     losses: torch.Tensor             # [N] fp32 per-row GPTQ loss (device)
     info: torch.Tensor               # device int32: 0 ok, else failing Cholesky pivot (identity fallback used)
+    perm: Optional[torch.Tensor] = None   # [K] int32 act_order permutation that was applied (None without act_order)
 
 
 def quantize_linear(weight: torch.Tensor, H: torch.Tensor, args: WeightArgs, blocksize: int = 128,
@@ -126,7 +124,7 @@ def quantize_linear(weight: torch.Tensor, H: torch.Tensor, args: WeightArgs, blo
     g_idx = None
     if args.strategy == "group" and args.actorder == "group":
         g_idx = (torch.arange(K, device=dev, dtype=torch.int32) // gs)[inv_perm.long()].contiguous()
-    return GPTQResult(wq, scale.to(final_dtype), zp.to(torch.int8), g_idx, losses, info)
+    return GPTQResult(wq, scale.to(final_dtype), zp.to(torch.int8), g_idx, losses, info, perm)
 
 
 def compress_linear(wq: torch.Tensor, scale: torch.Tensor, zero_point: Optional[torch.Tensor],

@@ -29,10 +29,12 @@ from .schemes import WeightArgs
 class Dist:
     """Thin view of torch.distributed (NCCL on GPUs, gloo in CPU tests); world_size 1 = no-op."""
 
-    def __init__(self):
+    def __init__(self, enabled: bool = True):
+        """enabled=False: a single-rank view even inside an initialised process group (used by the sharded-vs-
+        unsharded parity checks, which run both forms in one process)."""
         import torch.distributed as dist
         self.dist = dist
-        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.on = enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.rank = dist.get_rank() if self.on else 0
         self.world = dist.get_world_size() if self.on else 1
 

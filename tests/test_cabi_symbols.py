@@ -30,7 +30,7 @@ def test_binding_covers_the_header():
 def test_pure_host_entry_points_work_without_gpu():
     from quantool_b200 import cabi
     L = cabi.lib()
-    assert L.qt_abi_version() == 1
+    assert L.qt_abi_version() == 2
     assert L.qt_gguf_block_bytes(cabi.GGML["Q4_K"]) == 144 and L.qt_gguf_block_elems(cabi.GGML["Q4_K"]) == 256
     assert L.qt_gguf_block_bytes(cabi.GGML["Q8_0"]) == 34 and L.qt_gguf_block_bytes(99) == -1
 
