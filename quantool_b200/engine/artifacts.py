@@ -30,21 +30,35 @@ def quantization_config(level: str, actorder: Optional[str], fmt: str, ignore=("
 
 
 def artifact_format(num_bits: int, level: str) -> str:
-    """pack-quantized for 4-bit weight-only schemes, int-quantized for int8 weights (rows a6/a7)."""
-    return "pack-quantized" if num_bits == 4 else "int-quantized"
+    """The per-module format compressed-tensors infers (CT/compressors/format.py infer_module_format ->
+    PackedQuantizationCompressor.can_compress / IntQuantizationCompressor.can_compress), restated for integer
+    Linear schemes: weight-only INT with 4 or 8 bits -> "pack-quantized" (W4A16, W4A16_ASYM, W8A16: `weight_packed`
+    int32); INT weights WITH quantized input activations -> "int-quantized" (W8A8/INT8, W4A8: int8 `weight`).
+    tests/test_plugin_api.py checks this table against the installed compressed-tensors."""
+    from compressed_tensors.quantization import preset_name_to_scheme
+    scheme = preset_name_to_scheme(level, ["Linear"])
+    if scheme.input_activations is None and num_bits in (4, 8):
+        return "pack-quantized"
+    if scheme.input_activations is not None:
+        return "int-quantized"
+    raise ValueError(f"no compressed-tensors integer format for scheme {level!r} ({num_bits}-bit weight-only)")
 
 
 class QuantizedModel:
     """Holder returned as `plugin.last_model`: host tensors in artifact key names + HF config."""
 
-    def __init__(self, hf_config: dict, tensors: Dict[str, torch.Tensor], qconfig: dict, source_dir: Optional[str] = None):
+    def __init__(self, hf_config: dict, tensors: Dict[str, torch.Tensor], qconfig: dict, source_dir: Optional[str] = None,
+                 writer: bool = True):
         self.hf_config = dict(hf_config)
         self.tensors = tensors
         self.qconfig = qconfig
         self.source_dir = source_dir
+        self.writer = writer        # multi-process runs: rank 0 holds the tensors and is the only one that writes
 
     def save_pretrained(self, dest: str, save_compressed: bool = True, **_):
         from safetensors.torch import save_file
+        if not self.writer:
+            return
         os.makedirs(dest, exist_ok=True)
         cfg = dict(self.hf_config)
         cfg["quantization_config"] = self.qconfig

@@ -59,18 +59,20 @@ def _parent_forward(shape, kind: str, w: Dict[str, torch.Tensor], lin: Optional[
 
 
 def search_mapping(shape, w: Dict[str, torch.Tensor], mp: Mapping, x_all: torch.Tensor, x_mean: torch.Tensor,
-                   args: WeightArgs, cos, sin, seq: int, chunk_samples: int, dist=None, n_grid: int = N_GRID,
-                   duo_scaling: bool = True):
-    """x_all: [n_local*seq, K] cached inputs of the parent.  Returns (best_scales, best_ratio, losses)."""
+                   args: WeightArgs, chunks, dist=None, n_grid: int = N_GRID, duo_scaling: bool = True):
+    """x_all: [T_local, K] cached inputs of the parent; chunks: [(row0, B, S, cos, sin)] views into it (samples of
+    one chunk share a length).  Returns (best_scales, best_ratio, losses)."""
     dev = x_all.device
     gs = args.group_size if args.strategy == "group" else 0
     bw = [w[f"{b}.weight"] for b in mp.balance]
     w_mean = cabi.awq_wmean(bw, gs)
     lin = mp.balance[0] if mp.parent == "linear" else None
-    n_local = x_all.shape[0] // seq
-    chunks = [(c0, min(c0 + chunk_samples, n_local)) for c0 in range(0, n_local, chunk_samples)]
-    xin = x_all.view(n_local, seq, -1)
-    ref_out = [_parent_forward(shape, mp.parent, w, lin, xin[a:b], cos, sin) for a, b in chunks]
+
+    def xin(c):
+        r0, B, S, _, _ = c
+        return x_all[r0: r0 + B * S].view(B, S, -1)
+
+    ref_out = [_parent_forward(shape, mp.parent, w, lin, xin(c), c[3], c[4]) for c in chunks]
     numel = sum(o.numel() for o in ref_out)
     losses_dev = torch.zeros((n_grid,), dtype=torch.float64, device=dev)
     patched = dict(w)
@@ -83,8 +85,8 @@ def search_mapping(shape, w: Dict[str, torch.Tensor], mp: Mapping, x_all: torch.
         for name, t, buf in zip(mp.balance, bw, bufs):
             cabi.awq_scale_qdq(t, s, gs, args.num_bits, args.symmetric, out=buf)
             patched[f"{name}.weight"] = buf
-        for (a, b), ro in zip(chunks, ref_out):
-            out = _parent_forward(shape, mp.parent, patched, lin, xin[a:b], cos, sin)
+        for c, ro in zip(chunks, ref_out):
+            out = _parent_forward(shape, mp.parent, patched, lin, xin(c), c[3], c[4])
             cabi.sq_err_sum(ro, out, losses_dev[gi:gi + 1])
     tot = torch.tensor([float(numel)], dtype=torch.float64, device=dev)
     if dist is not None and dist.on:
@@ -111,17 +113,25 @@ def apply_mapping(w: Dict[str, torch.Tensor], mp: Mapping, s: torch.Tensor) -> N
         cabi.scale_matrix_(tail, s, divide=True, by_row=True)         # weight[-len(s):] /= s[:, None]
 
 
-def awq_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor, cos, sin, args: WeightArgs,
+def awq_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], calib, cos=None, sin=None, args: WeightArgs = None,
               chunk_samples: int = 32, dist=None, n_grid: int = N_GRID, duo_scaling: bool = True):
-    """Calibrate + smooth one decoder layer in place.  Returns {smooth-name: (scales, ratio, losses)}."""
-    dev = h.device
-    n_local, seq, _ = h.shape
+    """Calibrate + smooth one decoder layer in place.  `calib`: a pipeline.CalibSet, or hidden states
+    [n, seq, hidden] with `cos`/`sin`.  Returns {smooth-name: (scales, ratio, losses)}."""
+    from .pipeline import CalibSet
+    if isinstance(calib, torch.Tensor):
+        calib = CalibSet.from_hidden(calib, cos, sin)
+    dev = next(iter(w.values())).device
+    dtype = w["input_layernorm.weight"].dtype
     dims = shape.input_dims()
-    T = n_local * seq
-    cache = {n: torch.empty((T, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
-    for c0 in range(0, n_local, chunk_samples):
-        hb = h[c0: c0 + chunk_samples]
-        llama.layer_forward(shape, w, hb, cos, sin, capture=cache, row0=c0 * seq, stop_after="down_in")
+    T = calib.tokens_local
+    cache = {n: torch.empty((T, k), dtype=dtype, device=dev) for n, k in dims.items()}
+    chunks, row0 = [], 0
+    for gi, a, b in calib.chunks(max(1, chunk_samples) * max(calib.max_len, 1)):
+        hb = calib.groups[gi][a:b]
+        c, s_ = calib.ropes[gi]
+        llama.layer_forward(shape, w, hb, c, s_, capture=cache, row0=row0, stop_after="down_in")
+        chunks.append((row0, hb.shape[0], hb.shape[1], c, s_))
+        row0 += hb.shape[0] * hb.shape[1]
     out = {}
     for mp in llama_mappings(shape):
         x_all = cache[mp.inp]
@@ -132,8 +142,7 @@ def awq_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tens
             dist.all_reduce_sum(acc)
             dist.all_reduce_sum(cnt)
         x_mean = acc / cnt
-        s, ratio, losses = search_mapping(shape, w, mp, x_all, x_mean, args, cos, sin, seq, chunk_samples, dist,
-                                          n_grid, duo_scaling)
+        s, ratio, losses = search_mapping(shape, w, mp, x_all, x_mean, args, chunks, dist, n_grid, duo_scaling)
         apply_mapping(w, mp, s)
         out[mp.smooth] = (s, ratio, losses)
     return out

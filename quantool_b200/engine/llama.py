@@ -39,6 +39,7 @@ class LlamaShape:
     rope_theta: float = 500000.0
     tie_word_embeddings: bool = False
     max_position_embeddings: int = 8192
+    rope_scaling: Optional[dict] = None      # None or {"rope_type": "llama3", factor, low_freq_factor, ...}
 
     def __post_init__(self):
         if self.head_dim is None:
@@ -69,13 +70,43 @@ class LlamaShape:
                 "head_dim": self.head_dim, "vocab_size": self.vocab_size, "rms_norm_eps": self.rms_norm_eps,
                 "rope_theta": self.rope_theta, "tie_word_embeddings": self.tie_word_embeddings,
                 "max_position_embeddings": self.max_position_embeddings, "hidden_act": "silu",
-                "torch_dtype": "bfloat16", "attention_bias": False, "mlp_bias": False}
+                "torch_dtype": "bfloat16", "attention_bias": False, "mlp_bias": False,
+                **({"rope_scaling": dict(self.rope_scaling)} if self.rope_scaling else {})}
 
     @staticmethod
     def from_hf_config(cfg: dict) -> "LlamaShape":
+        """Raises on anything the calibration forward below would compute wrongly (the reference runs the real
+        HF module, so a silently different forward would change every Hessian)."""
+        mt = cfg.get("model_type")
+        archs = cfg.get("architectures") or []
+        if mt != "llama" or any(a != "LlamaForCausalLM" for a in archs):
+            raise ValueError(f"the sm_100a calibration driver implements the Llama decoder layer only "
+                             f"(model_type={mt!r}, architectures={archs})")
+        if cfg.get("attention_bias") or cfg.get("mlp_bias"):
+            raise ValueError("Llama variants with attention_bias / mlp_bias are not supported (bias tensors would be "
+                             "dropped from the forward and from the artifact)")
+        if cfg.get("sliding_window") or cfg.get("use_sliding_window"):
+            raise ValueError("sliding-window attention is not supported by the calibration forward")
+        if cfg.get("hidden_act", "silu") != "silu":
+            raise ValueError(f"hidden_act={cfg.get('hidden_act')!r} is not supported (silu only)")
         rope = cfg.get("rope_theta")
-        if rope is None and isinstance(cfg.get("rope_parameters"), dict):
-            rope = cfg["rope_parameters"].get("rope_theta")
+        rp = cfg.get("rope_parameters") if isinstance(cfg.get("rope_parameters"), dict) else None
+        if rope is None and rp:
+            rope = rp.get("rope_theta")
+        scaling = cfg.get("rope_scaling")
+        if scaling is None and rp and rp.get("rope_type", "default") != "default":
+            scaling = rp
+        if scaling is not None:
+            kind = scaling.get("rope_type", scaling.get("type", "default"))
+            if kind == "default":
+                scaling = None
+            elif kind != "llama3":
+                raise ValueError(f"rope_scaling type {kind!r} is not implemented (default and llama3 are)")
+            else:
+                scaling = {"rope_type": "llama3", "factor": float(scaling["factor"]),
+                           "low_freq_factor": float(scaling.get("low_freq_factor", 1.0)),
+                           "high_freq_factor": float(scaling.get("high_freq_factor", 4.0)),
+                           "original_max_position_embeddings": int(scaling["original_max_position_embeddings"])}
         return LlamaShape(hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
                           num_hidden_layers=cfg["num_hidden_layers"],
                           num_attention_heads=cfg["num_attention_heads"],
@@ -83,7 +114,7 @@ class LlamaShape:
                           vocab_size=cfg["vocab_size"], head_dim=cfg.get("head_dim"),
                           rms_norm_eps=cfg.get("rms_norm_eps", 1e-5), rope_theta=rope or 10000.0,
                           tie_word_embeddings=cfg.get("tie_word_embeddings", False),
-                          max_position_embeddings=cfg.get("max_position_embeddings", 8192))
+                          max_position_embeddings=cfg.get("max_position_embeddings", 8192), rope_scaling=scaling)
 
 
 # the shapes BASELINE.json names (SURVEY.md §8 header)
@@ -134,6 +165,18 @@ def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.T
 def rope_tables(shape: LlamaShape, seq: int, device, dtype):
     inv = 1.0 / (shape.rope_theta ** (torch.arange(0, shape.head_dim, 2, device=device, dtype=torch.float32)
                                      / shape.head_dim))
+    if shape.rope_scaling:
+        # transformers modeling_rope_utils._compute_llama3_parameters: long wavelengths are divided by `factor`,
+        # short ones kept, the band in between interpolated - this changes low-frequency dims at EVERY position
+        sc = shape.rope_scaling
+        old = sc["original_max_position_embeddings"]
+        lo_w, hi_w = old / sc["low_freq_factor"], old / sc["high_freq_factor"]
+        wavelen = 2 * math.pi / inv
+        inv_l = torch.where(wavelen > lo_w, inv / sc["factor"], inv)
+        smooth = (old / wavelen - sc["low_freq_factor"]) / (sc["high_freq_factor"] - sc["low_freq_factor"])
+        smoothed = (1 - smooth) * inv_l / sc["factor"] + smooth * inv_l
+        mid = ~(wavelen < hi_w) & ~(wavelen > lo_w)
+        inv = torch.where(mid, smoothed, inv_l)
     t = torch.arange(seq, device=device, dtype=torch.float32)
     f = torch.outer(t, inv)
     emb = torch.cat((f, f), dim=-1)

@@ -72,6 +72,70 @@ class Dist:
         return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
 
 
+
+class CalibSet:
+    """This rank's calibration samples as hidden states, grouped by sequence length.
+
+    llm-compressor calibrates every sample at its own length (batch size 1, no padding to a common length), so a
+    short sample must not truncate the others: samples of equal length form one group [n_g, L_g, hidden]; a
+    uniform token tensor is the one-group special case.  Samples are dealt to the ranks round-robin in
+    length-sorted order (balanced tokens per rank); `n_total` counts samples over all ranks (the Hessian's 2/n)."""
+
+    def __init__(self, shape: llama.LlamaShape, token_ids, emb: torch.Tensor, device, dist: "Dist"):
+        rows = self._rows(token_ids)
+        self.n_total = len(rows)
+        order = sorted(range(len(rows)), key=lambda i: (-int(rows[i].numel()), i))
+        mine = [rows[i] for i in order[dist.rank:: dist.world]] if dist.world > 1 else [rows[i] for i in order]
+        self.n_local = len(mine)
+        by_len: Dict[int, list] = {}
+        for r in mine:
+            by_len.setdefault(int(r.numel()), []).append(r)
+        self.groups, self.ropes, self.h2d_bytes = [], [], 0
+        for L in sorted(by_len, reverse=True):
+            ids = torch.stack(by_len[L]).to(device, non_blocking=True)
+            self.h2d_bytes += ids.numel() * ids.element_size()
+            self.groups.append(torch.nn.functional.embedding(ids, emb))
+            self.ropes.append(llama.rope_tables(shape, L, device, emb.dtype))
+        self.max_len = max(by_len) if by_len else 0
+        self.tokens_local = sum(g.shape[0] * g.shape[1] for g in self.groups)
+
+    @staticmethod
+    def _rows(token_ids):
+        if isinstance(token_ids, torch.Tensor):
+            if token_ids.dim() != 2:
+                raise ValueError("token ids must be [n_samples, seq]")
+            return list(token_ids.long().unbind(0))
+        rows = [torch.as_tensor(r, dtype=torch.long).reshape(-1) for r in token_ids]
+        if any(r.numel() == 0 for r in rows):
+            raise ValueError("empty calibration sample")
+        return rows
+
+    @classmethod
+    def from_hidden(cls, h: torch.Tensor, cos, sin, n_total: Optional[int] = None) -> "CalibSet":
+        """One uniform group from ready-made hidden states [n, seq, hidden] (kernel-level callers, tests)."""
+        c = cls.__new__(cls)
+        c.groups, c.ropes = [h], [(cos, sin)]
+        c.n_local = h.shape[0]
+        c.n_total = n_total if n_total is not None else h.shape[0]
+        c.max_len = h.shape[1]
+        c.tokens_local = h.shape[0] * h.shape[1]
+        c.h2d_bytes = 0
+        return c
+
+    def chunks(self, max_tokens: int):
+        """(group index, first sample, last sample) of every chunk; a chunk is <= max_tokens tokens of one group
+        (at least one sample)."""
+        for gi, g in enumerate(self.groups):
+            per = max(1, max_tokens // g.shape[1])
+            for a in range(0, g.shape[0], per):
+                yield gi, a, min(a + per, g.shape[0])
+
+    def propagate(self, shape, w, max_tokens: int) -> None:
+        for gi, a, b in self.chunks(max_tokens):
+            cos, sin = self.ropes[gi]
+            self.groups[gi][a:b] = llama.layer_forward(shape, w, self.groups[gi][a:b], cos, sin)
+
+
 def row_split(n: int, world: int, align: int = 1) -> List[int]:
     """Split n rows over `world` ranks in `align`-row units, remainder to the first ranks."""
     units = (n + align - 1) // align
@@ -334,8 +398,11 @@ class GPTQLayerQuantizer:
         kernels fill the SMs the big-K GEMMs leave idle.  The Cholesky status words are read once,
         after everything is queued; a failed factorisation (upstream: LinAlgError -> Hinv = I) is
         redone with the identity, which is rare enough not to matter."""
-        names = sorted(hessians, key=lambda n: -hessians[n].shape[0])
+        used = {input_of[lin] for lin in linears}
+        names = sorted((n for n in hessians if n in used), key=lambda n: -hessians[n].shape[0])
         out: Dict[str, LinearResult] = {}
+        if not names:
+            return out
         dev = next(iter(hessians.values())).device
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_streams"):
@@ -537,6 +604,43 @@ class _WeightPrefetcher:
         return w
 
 
+_LAYER_KEYS = {f"{lin}.weight" for lin in llama.LINEARS} | {"input_layernorm.weight", "post_attention_layernorm.weight"}
+
+
+def _check_layer_keys(host_sd) -> None:
+    """Every decoder-layer tensor must be one the driver consumes and writes back; anything else (biases, extra
+    norms, rotary buffers of another architecture) would be silently missing from the artifact."""
+    extra = sorted(k for k in host_sd if k.startswith("model.layers.") and k.split(".", 3)[3] not in _LAYER_KEYS
+                   and not k.endswith("rotary_emb.inv_freq"))
+    if extra:
+        raise ValueError(f"unsupported decoder-layer tensors (not a plain Llama layer): {extra[:4]}"
+                         f"{' ...' if len(extra) > 4 else ''}")
+
+
+def _ignored_linears(ignore) -> set:
+    """Module names excluded from quantization.  "lm_head" (the default) is never on the decoder-layer path; other
+    entries must name decoder Linears exactly ("model.layers.3.mlp.down_proj") or for all layers through the
+    `re:` form compressed-tensors uses ("re:.*down_proj"); anything that matches no Linear raises."""
+    import re
+    out = set()
+    for pat in ignore or ():
+        if pat == "lm_head":
+            continue
+        if pat.startswith("re:"):
+            rx = re.compile(pat[3:])
+            hit = [lin for lin in llama.LINEARS if rx.match(f"model.layers.0.{lin}")]
+            generic = all(rx.match(f"model.layers.{i}.{lin}") for lin in hit for i in (1, 17))
+            if not hit or not generic:
+                raise ValueError(f"ignore pattern {pat!r}: only patterns that select the same Linears in every decoder "
+                                 f"layer are supported (e.g. 're:.*down_proj')")
+            out.update(hit)
+        elif any(pat.endswith(lin) for lin in llama.LINEARS) and pat.startswith("model.layers."):
+            out.add(pat)
+        else:
+            raise ValueError(f"ignore entry {pat!r} does not name a decoder Linear (or lm_head)")
+    return out
+
+
 def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor], token_ids: torch.Tensor,
                         args: WeightArgs, device, fmt: str = "pack-quantized", percdamp: float = 0.01,
                         chunk_samples: int = 16, smooth_strength: Optional[float] = None,
@@ -550,43 +654,40 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
     dist = dist or Dist()
     res = ModelQuantResult()
     dev = torch.device(device)
-    n_total, seq = token_ids.shape
-    # sample sharding
-    per = row_split(n_total, dist.world)
-    s0 = sum(per[: dist.rank])
-    ids = token_ids[s0: s0 + per[dist.rank]].to(dev, non_blocking=True)
-    res.h2d_bytes += ids.numel() * ids.element_size()
-    n_local = ids.shape[0]
     emb = _to_dev(host_sd["model.embed_tokens.weight"], dev)
     res.h2d_bytes += emb.numel() * emb.element_size()
-    h = torch.nn.functional.embedding(ids, emb)
+    calib = CalibSet(shape, token_ids, emb, dev, dist)          # samples sharded over the ranks
+    res.h2d_bytes += calib.h2d_bytes
     del emb
-    cos, sin = llama.rope_tables(shape, seq, dev, h.dtype)
+    n_total, n_local = calib.n_total, calib.n_local
+    skip = _ignored_linears(ignore)
+    _check_layer_keys(host_sd)
     lq = GPTQLayerQuantizer(args, percdamp=percdamp, dist=dist)
     dims = shape.input_dims()
     sink = _HostSink(dev, res)
     fetch = _WeightPrefetcher(host_sd, dev, res)
     losses = {}
     L = shape.num_hidden_layers
-    chunk_samples = max(1, min(chunk_samples, n_local)) if n_local else 1
+    chunk_tokens = max(1, chunk_samples) * max(calib.max_len, 1)
     accs = cap = None
     for l in range(L):
         pre = f"model.layers.{l}."
         w = fetch.get(pre, f"model.layers.{l + 1}." if l + 1 < L else None)
         if smooth_strength is not None:
             from .smoothquant import smooth_layer
-            smooth_layer(shape, w, h, cos, sin, smooth_strength, chunk_samples, dist)
+            smooth_layer(shape, w, calib, None, None, smooth_strength, chunk_samples, dist)
         # pass 1: statistics with the layer's original weights (accumulators and capture buffers are reused)
         if accs is None:
+            hdt = host_sd[pre + "input_layernorm.weight"].dtype
             accs = {n: HessianAccumulator(k, dev) for n, k in dims.items()}
-            cap = {n: torch.empty((chunk_samples * seq, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
+            cap = {n: torch.empty((chunk_tokens, k), dtype=hdt, device=dev) for n, k in dims.items()}
         else:
             for acc in accs.values():
                 acc.reset()
-        for c0 in range(0, n_local, chunk_samples):
-            hb = h[c0: c0 + chunk_samples]
-            rows = hb.shape[0] * seq
-            llama.layer_forward(shape, w, hb, cos, sin, capture=cap, row0=0, stop_after="down_in")
+        for gi, a, b in calib.chunks(chunk_tokens):
+            hb = calib.groups[gi][a:b]
+            rows = hb.shape[0] * hb.shape[1]
+            llama.layer_forward(shape, w, hb, *calib.ropes[gi], capture=cap, row0=0, stop_after="down_in")
             for n in dims:
                 accs[n].add(cap[n][:rows], hb.shape[0])
                 lq.launches += 1
@@ -596,8 +697,13 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
             dist.all_reduce_sum(accs[n].H)
             hess[n] = accs[n].finalize(n_total)
             lq.launches += 1
-        results = lq.quantize_layer(w, hess)
+        linears = tuple(lin for lin in llama.LINEARS if f"{pre}{lin}" not in skip and lin not in skip)
+        results = lq.quantize_layer(w, hess, linears=linears)
         del hess
+        if dist.rank == 0:
+            for lin in llama.LINEARS:
+                if lin not in linears:                   # ignored module: stays dense in the artifact
+                    sink.put(f"{pre}{lin}.weight", w[f"{lin}.weight"])
         for lin, r in results.items():
             w[f"{lin}.weight"] = r.weight
             art, _codes = compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args, fmt=fmt)
@@ -610,8 +716,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
             for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
                 sink.put(pre + k, w[k])
         # pass 2: propagate through the quantized layer
-        for c0 in range(0, n_local, chunk_samples):
-            h[c0: c0 + chunk_samples] = llama.layer_forward(shape, w, h[c0: c0 + chunk_samples], cos, sin)
+        calib.propagate(shape, w, chunk_tokens)
         del w
         if progress:
             progress(l)
@@ -640,22 +745,18 @@ def quantize_model_awq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor]
     dist = dist or Dist()
     res = ModelQuantResult()
     dev = torch.device(device)
-    n_total, seq = token_ids.shape
-    per = row_split(n_total, dist.world)
-    s0 = sum(per[: dist.rank])
-    ids = token_ids[s0: s0 + per[dist.rank]].to(dev)
-    res.h2d_bytes += ids.numel() * ids.element_size()
-    n_local = ids.shape[0]
     emb = _to_dev(host_sd["model.embed_tokens.weight"], dev)
     res.h2d_bytes += emb.numel() * emb.element_size()
-    h = torch.nn.functional.embedding(ids, emb)
+    calib = CalibSet(shape, token_ids, emb, dev, dist)
+    res.h2d_bytes += calib.h2d_bytes
     del emb
-    cos, sin = llama.rope_tables(shape, seq, dev, h.dtype)
+    _check_layer_keys(host_sd)
+    chunk_tokens = max(1, chunk_samples) * max(calib.max_len, 1)
     l0 = cabi.launch_count()
     for l in range(shape.num_hidden_layers):
         pre = f"model.layers.{l}."
         w = _layer_weights(host_sd, pre, dev, res)
-        info = awq.awq_layer(shape, w, h, cos, sin, args, chunk_samples, dist, n_grid, duo_scaling)
+        info = awq.awq_layer(shape, w, calib, None, None, args, chunk_samples, dist, n_grid, duo_scaling)
         for lin in llama.LINEARS:
             wt = w[f"{lin}.weight"]
             scale, zp = awq.rtn_qparams(wt, args)
@@ -670,8 +771,7 @@ def quantize_model_awq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor]
                 res.tensors[pre + k] = w[k].cpu()
             for name, (_s, ratio, losses) in info.items():
                 res.losses[f"{pre}{name}.awq_ratio"] = ratio
-        for c0 in range(0, n_local, chunk_samples):
-            h[c0: c0 + chunk_samples] = llama.layer_forward(shape, w, h[c0: c0 + chunk_samples], cos, sin)
+        calib.propagate(shape, w, chunk_tokens)
         del w
         if progress:
             progress(l)

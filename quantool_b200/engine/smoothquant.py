@@ -34,20 +34,25 @@ def apply_scales(smooth_weight: torch.Tensor, balance_weights: List[torch.Tensor
     cabi.scale_matrix_(smooth_weight, s, divide=True)  # norm weight /= s
 
 
-def smooth_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor, cos, sin, alpha: float,
+def smooth_layer(shape: llama.LlamaShape, w: Dict[str, torch.Tensor], calib, cos=None, sin=None, alpha: float = 0.5,
                  chunk_samples: int = 8, dist=None) -> Dict[str, torch.Tensor]:
     """One calibration pass over this rank's samples, min/max all-reduce, fold in place into `w`.
+    `calib`: a pipeline.CalibSet, or hidden states [n, seq, hidden] together with `cos`/`sin`.
     Returns the smoothing scales per mapping (keyed by smooth-layer name)."""
-    dev = h.device
-    n_local, seq, _ = h.shape
+    from .pipeline import CalibSet
+    if isinstance(calib, torch.Tensor):
+        calib = CalibSet.from_hidden(calib, cos, sin)
+    dev = calib.groups[0].device if calib.groups else next(iter(w.values())).device
+    dtype = w["input_layernorm.weight"].dtype
     dims = shape.input_dims()
     names = [m[2] for m in MAPPINGS]
     stats = {n: cabi.new_minmax(dims[n], dev) for n in names}
-    cap = {n: torch.empty((chunk_samples * seq, k), dtype=h.dtype, device=dev) for n, k in dims.items()}
-    for c0 in range(0, n_local, chunk_samples):
-        hb = h[c0: c0 + chunk_samples]
-        rows = hb.shape[0] * seq
-        llama.layer_forward(shape, w, hb, cos, sin, capture=cap, row0=0, stop_after="mlp_in")
+    chunk_tokens = max(1, chunk_samples) * max(calib.max_len, 1)
+    cap = {n: torch.empty((chunk_tokens, k), dtype=dtype, device=dev) for n, k in dims.items()}
+    for gi, a, b in calib.chunks(chunk_tokens):
+        hb = calib.groups[gi][a:b]
+        rows = hb.shape[0] * hb.shape[1]
+        llama.layer_forward(shape, w, hb, *calib.ropes[gi], capture=cap, row0=0, stop_after="mlp_in")
         for n in names:
             cabi.channel_minmax(cap[n][:rows], *stats[n])
     out = {}

@@ -186,18 +186,25 @@ class LLMCompressorQuantizer(BaseQuantizer):
         cfg, sd = gguf_file.load_hf_model(path)
         return cfg, sd, path
 
-    def _token_ids(self, oneshot_kwargs: Dict[str, Any], source_dir: Optional[str]) -> torch.Tensor:
+    def _token_ids(self, oneshot_kwargs: Dict[str, Any], source_dir: Optional[str]):
+        """Calibration samples as token ids: a [n, seq] tensor when every sample has the same length, else a list
+        of 1-D tensors.  Like llm-compressor's oneshot every sample is calibrated at ITS OWN length (truncated to
+        `max_seq_length`, never to the shortest sample), `num_calibration_samples` defaults to 512 and the samples
+        are shuffled before the first `num_calibration_samples` are taken (`shuffle_calibration_samples`, default
+        True; seeded here so runs repeat)."""
         ds = oneshot_kwargs.get("dataset")
-        n = oneshot_kwargs.get("num_calibration_samples")
-        max_len = oneshot_kwargs.get("max_seq_length") or 2048
+        n = oneshot_kwargs.get("num_calibration_samples") or 512
+        max_len = oneshot_kwargs.get("max_seq_length")     # explicit: truncates everything; default: tokenizer only
+        tok_len = max_len or 384                           # llm-compressor DatasetArguments default for tokenization
+        shuffle = oneshot_kwargs.get("shuffle_calibration_samples", True)
+        if ds is None and oneshot_kwargs.get("dataset_path"):
+            ds = self._load_dataset_path(oneshot_kwargs["dataset_path"], oneshot_kwargs)
         if ds is None:
-            raise ValueError("this build calibrates from an in-memory `dataset` (token-id tensor, list of token lists, "
-                             "or a datasets.Dataset with `input_ids` or `text`); `dataset_path` loading needs the "
-                             "reference's dataset loader")
+            raise ValueError("no calibration data: pass `dataset` (token-id tensor, list of token lists, or a "
+                             "datasets.Dataset with `input_ids` or `text`) or a local `dataset_path`")
         if isinstance(ds, torch.Tensor):
-            ids = ds.long()
+            rows = list(ds.long().unbind(0))
         else:
-            rows = None
             cols = set(getattr(ds, "column_names", []) or [])
             if "input_ids" in cols:
                 rows = [list(r) for r in ds["input_ids"]]
@@ -205,19 +212,48 @@ class LLMCompressorQuantizer(BaseQuantizer):
                 from transformers import AutoTokenizer
                 tok = self.last_tokenizer or AutoTokenizer.from_pretrained(source_dir or self.model_id)
                 self.last_tokenizer = tok
-                rows = [tok(t, truncation=True, max_length=max_len)["input_ids"] for t in ds["text"]]
+                rows = [tok(t, truncation=True, max_length=tok_len)["input_ids"] for t in ds["text"]]
             elif isinstance(ds, (list, tuple)):
                 rows = [list(r) for r in ds]
             else:
                 raise ValueError("unsupported calibration dataset type")
-            rows = [r[:max_len] for r in rows if len(r) > 0]
-            seq = min(len(r) for r in rows)
-            ids = torch.tensor([r[:seq] for r in rows], dtype=torch.long)   # equal-length batch (no padding tokens)
-        if n:
-            ids = ids[: int(n)]
-        if ids.shape[1] > max_len:
-            ids = ids[:, :max_len]
-        return ids.contiguous()
+            rows = [torch.as_tensor(r, dtype=torch.long).reshape(-1) for r in rows]
+        empty = sum(1 for r in rows if r.numel() == 0)
+        if empty:
+            self.logger.warning(f"dropping {empty} empty calibration samples")
+        rows = [r[:max_len] if max_len else r for r in rows if r.numel() > 0]
+        if not rows:
+            raise ValueError("the calibration dataset holds no non-empty samples")
+        if shuffle and len(rows) > 1:
+            order = torch.randperm(len(rows), generator=torch.Generator().manual_seed(42)).tolist()
+            rows = [rows[i] for i in order]
+        rows = rows[: int(n)]
+        if len({int(r.numel()) for r in rows}) == 1:
+            return torch.stack(rows).contiguous()
+        return rows
+
+    def _load_dataset_path(self, path: str, kw: Dict[str, Any]):
+        """Local calibration files (`dataset_path`; the reference hands this key to oneshot, ref base.py:118-124):
+        .pt (token-id tensor), .json / .jsonl / .txt / .parquet / a `datasets.save_to_disk` directory with a `text`
+        or `input_ids` column.  Hub dataset names need network access and raise."""
+        if not os.path.exists(path):
+            raise ValueError(f"dataset_path {path!r} does not exist locally (hub datasets cannot be fetched here)")
+        if path.endswith(".pt"):
+            return torch.load(path)
+        import datasets
+        if os.path.isdir(path):
+            ds = datasets.load_from_disk(path)
+        else:
+            ext = path.rsplit(".", 1)[-1].lower()
+            kind = {"jsonl": "json", "json": "json", "txt": "text", "parquet": "parquet", "csv": "csv"}.get(ext)
+            if kind is None:
+                raise ValueError(f"dataset_path: unsupported file type .{ext}")
+            ds = datasets.load_dataset(kind, data_files=path)
+        if isinstance(ds, dict) or hasattr(ds, "keys"):
+            split = (kw.get("splits") or "train")
+            split = split if isinstance(split, str) else next(iter(split))
+            ds = ds[split if split in ds else next(iter(ds.keys()))]
+        return self.prepare_calibration_data(ds)
 
     def _oneshot(self, model, recipe, output_dir, save_compressed=True, **kw):
         from ...engine import artifacts, llama, pipeline, schemes
@@ -228,6 +264,7 @@ class LLMCompressorQuantizer(BaseQuantizer):
             if not isinstance(m, Modifier):
                 raise TypeError("recipe entries must be quantool_b200 Modifier objects (llm-compressor modifier "
                                 "instances / YAML recipe paths are not interpretable without llm-compressor)")
+        self._check_supported(mods, kw)
         cfg, sd, src = self._load_model(model)
         shape = llama.LlamaShape.from_hf_config(cfg)
         ids = self._token_ids({**kw, "dataset": kw.get("dataset")}, src)
@@ -243,13 +280,48 @@ class LLMCompressorQuantizer(BaseQuantizer):
             if q.block_size != 128:
                 raise ValueError("block_size other than 128 is not supported by the sm_100a GPTQ kernel")
             res = pipeline.quantize_model_gptq(shape, sd, ids, args, dev, fmt=fmt, percdamp=q.dampening_frac,
-                                               smooth_strength=smooth[0].smoothing_strength if smooth else None)
+                                               smooth_strength=smooth[0].smoothing_strength if smooth else None,
+                                               ignore=tuple(q.ignore))
         else:
             res = pipeline.quantize_model_awq(shape, sd, ids, args, dev, fmt=fmt, n_grid=q.n_grid,
                                               duo_scaling=q.duo_scaling)
         qcfg = artifacts.quantization_config(q.scheme, args.actorder, fmt, ignore=q.ignore)
-        qm = artifacts.QuantizedModel(cfg, res.tensors, qcfg, source_dir=src)
+        d = pipeline.Dist()
+        qm = artifacts.QuantizedModel(cfg, res.tensors, qcfg, source_dir=src, writer=(d.rank == 0))
         qm.stats = res
         if save_compressed:
-            qm.save_pretrained(output_dir, save_compressed=True)
+            qm.save_pretrained(output_dir, save_compressed=True)      # rank 0 writes; the other ranks hold no tensors
+        if d.on:
+            d.dist.barrier()
         return qm
+
+    @staticmethod
+    def _check_supported(mods, kw: Dict[str, Any]) -> None:
+        """Every accepted key is either honoured or rejected - nothing is silently dropped (the reference routes
+        these keys into the modifier / oneshot, ref base.py:110-130, gptq.py:75-84, awq.py:77-79)."""
+        def _as_list(v):
+            return [v] if isinstance(v, str) else list(v or [])
+        for m in mods:
+            if _as_list(m.targets) != ["Linear"]:
+                raise ValueError(f"targets={m.targets!r}: the sm_100a engine quantizes the decoder-layer Linears "
+                                 f"(targets='Linear'); use `ignore` to exclude modules")
+            if m.sequential_targets is not None and _as_list(m.sequential_targets) != ["LlamaDecoderLayer"]:
+                raise ValueError(f"sequential_targets={m.sequential_targets!r}: calibration is sequential per "
+                                 f"LlamaDecoderLayer (the llm-compressor default for Llama); other values are not supported")
+            if m.mappings is not None:
+                raise ValueError("custom `mappings` are not supported: the engine uses llm-compressor's Llama default "
+                                 "mappings")
+            if m.kind in ("awq", "smoothquant") and _as_list(m.ignore) not in ([], ["lm_head"]):
+                raise ValueError(f"`ignore` beyond ['lm_head'] is honoured by the gptq pass only (got {m.ignore!r} on "
+                                 f"{m.kind})")
+        st = kw.get("sequential_targets")
+        if st is not None and _as_list(st) != ["LlamaDecoderLayer"]:
+            raise ValueError(f"sequential_targets={st!r} is not supported (LlamaDecoderLayer only)")
+        for key in ("pipeline",):
+            if kw.get(key) not in (None, "sequential", "independent"):
+                raise ValueError(f"{key}={kw[key]!r} is not supported")
+        if kw.get("calibration_dataloader") is not None:
+            raise ValueError("`calibration_dataloader` is not supported: pass `dataset` or `dataset_path`")
+        if kw.get("pad_to_max_length") or kw.get("concatenate_data"):
+            raise ValueError("pad_to_max_length / concatenate_data are not supported: samples are calibrated at their "
+                             "own length")

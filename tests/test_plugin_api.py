@@ -210,3 +210,101 @@ def test_autogptq_and_autoawq_views_are_pure_repacks_cpu():
     assert torch.equal(nib[:, :, rev].reshape(K, N).t(), u)
     znib = torch.stack([(a["qzeros"] >> (4 * i)) & 0xF for i in range(8)], dim=2)
     assert torch.equal(znib[:, :, rev].reshape(K // gs, N).t(), zp.to(torch.int32) + 8)
+
+
+# ---- round 2: config keys are honoured or rejected, never dropped (ADVICE) -------------------
+def test_artifact_format_matches_compressed_tensors():
+    """The format per preset is what the installed compressed-tensors infers for a Linear with that scheme
+    (W8A16 is pack-quantized, W4A8 is int-quantized - not a function of num_bits alone)."""
+    import torch
+    from compressed_tensors.compressors.format import infer_module_format
+    from compressed_tensors.quantization import preset_name_to_scheme
+    from quantool_b200.engine import artifacts, schemes
+    for level in ("W4A16", "W4A16_ASYM", "W8A16", "W8A8", "INT8", "W4A8"):
+        want = infer_module_format(torch.nn.Linear, preset_name_to_scheme(level, ["Linear"])).value
+        assert artifacts.artifact_format(schemes.resolve(level).num_bits, level) == want, level
+    assert artifacts.artifact_format(8, "W8A16") == "pack-quantized"
+    assert artifacts.artifact_format(4, "W4A8") == "int-quantized"
+
+
+def test_unsupported_recipe_keys_raise():
+    import pytest
+    from quantool_b200.methods.llm_compressor.base import LLMCompressorQuantizer, Modifier
+    chk = LLMCompressorQuantizer._check_supported
+    chk([Modifier(kind="gptq", scheme="W4A16")], {})
+    chk([Modifier(kind="gptq", scheme="W4A16", targets=["Linear"], sequential_targets=["LlamaDecoderLayer"],
+                  ignore=["lm_head", "re:.*down_proj"])], {"sequential_targets": "LlamaDecoderLayer"})
+    for bad in (dict(targets=["re:.*q_proj"]), dict(sequential_targets=["LlamaAttention"]), dict(mappings=[["a"], "b"])):
+        with pytest.raises(ValueError):
+            chk([Modifier(kind="gptq", scheme="W4A16", **bad)], {})
+    with pytest.raises(ValueError):
+        chk([Modifier(kind="awq", scheme="W4A16", ignore=["lm_head", "re:.*down_proj"])], {})
+    for kw in ({"calibration_dataloader": object()}, {"pad_to_max_length": True}, {"sequential_targets": ["X"]}):
+        with pytest.raises(ValueError):
+            chk([Modifier(kind="gptq", scheme="W4A16")], kw)
+
+
+def test_ignore_patterns():
+    import pytest
+    from quantool_b200.engine.pipeline import _ignored_linears
+    assert _ignored_linears(("lm_head",)) == set()
+    assert _ignored_linears(["lm_head", "re:.*down_proj"]) == {"mlp.down_proj"}
+    assert _ignored_linears(["model.layers.3.self_attn.o_proj"]) == {"model.layers.3.self_attn.o_proj"}
+    for bad in ("re:.*layers\\.0\\..*q_proj", "model.norm", "re:.*nothing"):
+        with pytest.raises(ValueError):
+            _ignored_linears([bad])
+
+
+def test_calibration_rows_keep_their_own_length(tmp_path):
+    """A short sample does not truncate the others; n defaults to 512; shuffled (seeded); dataset_path files load."""
+    import json
+    import torch
+    from quantool_b200.methods.llm_compressor.gptq import GPTQ
+    q = GPTQ("org/m")
+    rows = [list(range(1, 1 + n)) for n in (5, 40, 40, 17, 40)]
+    out = q._token_ids({"dataset": rows, "shuffle_calibration_samples": False}, None)
+    assert isinstance(out, list) and [int(r.numel()) for r in out] == [5, 40, 40, 17, 40]
+    out = q._token_ids({"dataset": rows, "max_seq_length": 16, "num_calibration_samples": 3,
+                        "shuffle_calibration_samples": False}, None)
+    assert [int(r.numel()) for r in out] == [5, 16, 16]
+    t = torch.arange(600 * 8).reshape(600, 8)
+    out = q._token_ids({"dataset": t}, None)
+    assert isinstance(out, torch.Tensor) and out.shape == (512, 8)
+    assert not torch.equal(out, t[:512]) and torch.equal(out, q._token_ids({"dataset": t}, None))   # shuffled, repeatable
+    p = tmp_path / "calib.jsonl"
+    with open(p, "w") as f:
+        for r in rows:
+            f.write(json.dumps({"input_ids": r}) + "\n")
+    out = q._token_ids({"dataset_path": str(p), "shuffle_calibration_samples": False}, None)
+    assert [int(r.numel()) for r in out] == [5, 40, 40, 17, 40]
+    import pytest
+    with pytest.raises(ValueError):
+        q._token_ids({"dataset_path": "org/some-hub-dataset"}, None)
+
+
+def test_llama_config_validation_and_llama3_rope():
+    import pytest
+    import torch
+    from quantool_b200.engine import llama
+    base = llama.SHAPES["llama-3.2-1b"].to_hf_config()
+    assert llama.LlamaShape.from_hf_config(base).rope_scaling is None
+    for bad in ({"model_type": "qwen2"}, {"architectures": ["MistralForCausalLM"]}, {"attention_bias": True},
+                {"mlp_bias": True}, {"sliding_window": 4096}, {"rope_scaling": {"rope_type": "yarn", "factor": 4.0}},
+                {"hidden_act": "gelu"}):
+        with pytest.raises(ValueError):
+            llama.LlamaShape.from_hf_config({**base, **bad})
+    rs = {"factor": 32.0, "high_freq_factor": 4.0, "low_freq_factor": 1.0, "original_max_position_embeddings": 8192,
+          "rope_type": "llama3"}
+    shape = llama.LlamaShape.from_hf_config({**base, "rope_scaling": rs})
+    assert shape.rope_scaling["rope_type"] == "llama3" and shape.to_hf_config()["rope_scaling"]["factor"] == 32.0
+    cos, sin = llama.rope_tables(shape, 64, "cpu", torch.float32)
+    # reference: transformers' own llama3 frequency computation
+    from transformers import LlamaConfig
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+    hf = LlamaConfig(**{k: v for k, v in base.items() if k not in ("architectures", "torch_dtype")}, rope_scaling=rs)
+    inv, _ = ROPE_INIT_FUNCTIONS["llama3"](hf, "cpu")
+    f = torch.outer(torch.arange(64, dtype=torch.float32), inv)
+    want = torch.cat((f, f), dim=-1)
+    assert torch.allclose(cos, want.cos(), atol=1e-6) and torch.allclose(sin, want.sin(), atol=1e-6)
+    plain, _ = llama.rope_tables(llama.SHAPES["llama-3.2-1b"], 64, "cpu", torch.float32)
+    assert not torch.allclose(cos, plain, atol=1e-3)      # the scaling matters below 2048 positions too

@@ -171,3 +171,41 @@ def test_autogptq_view_is_a_pure_repack():
     qw = v["qweight"].cpu()
     u = torch.stack([(qw >> (4 * i)) & 0xF for i in range(8)], dim=1).reshape(K, N).t()
     assert torch.equal((u - 8).to(torch.int8), codes.cpu())
+
+
+def test_gptq_ragged_calibration_and_ignore(tmp_path):
+    """Samples of different lengths are calibrated at their own length (one short sample must not truncate the rest)
+    and an `ignore` pattern leaves the matched Linears dense in the artifact and listed in the config."""
+    import quantool_b200.methods  # noqa: F401
+    from safetensors.torch import load_file
+    from quantool_b200 import QuantizerRegistry
+    from quantool_b200.engine import llama, pipeline, schemes
+    shape, sd, path = _write_model(tmp_path)
+    g = torch.Generator().manual_seed(5)
+    lens = [96, 96, 7, 64, 96, 64, 96, 33]
+    rows = [torch.randint(0, shape.vocab_size, (n,), generator=g).tolist() for n in lens]
+    q = QuantizerRegistry.create("gptq", model_id="org/tiny-llama")
+    out = q.quantize(model=path, level="W4A16", dataset=rows, output_dir=str(tmp_path / "out"),
+                     method_kwargs={"ignore": ["lm_head", "re:.*down_proj"]})
+    qc = json.load(open(os.path.join(out, "config.json")))["quantization_config"]
+    assert qc["ignore"] == ["lm_head", "re:.*down_proj"]
+    t = load_file(os.path.join(out, "model.safetensors"))
+    assert "model.layers.0.mlp.down_proj.weight" in t and "model.layers.0.mlp.down_proj.weight_packed" not in t
+    assert torch.equal(t["model.layers.1.mlp.down_proj.weight"], sd["model.layers.1.mlp.down_proj.weight"])
+    assert "model.layers.0.mlp.up_proj.weight_packed" in t
+    # the ragged run equals "every sample on its own": Hessian of layer 0's first input from the CalibSet groups
+    args = schemes.resolve("W4A16")
+    calib = pipeline.CalibSet(shape, rows, sd["model.embed_tokens.weight"].cuda(), "cuda", pipeline.Dist(enabled=False))
+    assert calib.n_total == len(lens) and calib.tokens_local == sum(lens)
+    assert sorted((g.shape[1], g.shape[0]) for g in calib.groups) == [(7, 1), (33, 1), (64, 2), (96, 4)]
+    # a truncate-to-shortest run (the old behaviour) gives different codes
+    q2 = QuantizerRegistry.create("gptq", model_id="org/tiny-llama")
+    out2 = q2.quantize(model=path, level="W4A16", dataset=[r[:7] for r in rows], output_dir=str(tmp_path / "out2"),
+                       shuffle_calibration_samples=False)
+    t2 = load_file(os.path.join(out2, "model.safetensors"))
+    k = "model.layers.1.mlp.up_proj.weight_packed"
+    assert not torch.equal(t[k], t2[k])
+    with pytest.raises(ValueError):
+        bad = dict(sd)
+        bad["model.layers.0.self_attn.q_proj.bias"] = torch.zeros(shape.hidden_size)
+        pipeline.quantize_model_gptq(shape, bad, torch.tensor(rows[0]).reshape(1, -1), args, "cuda")
