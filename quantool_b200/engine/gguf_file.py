@@ -106,10 +106,128 @@ def load_hf_model(model_path: str):
     return cfg, sd
 
 
-def convert_hf_to_f16_gguf(model_path: str, out_file: str, outtype: str = "f16") -> str:
-    """HF checkpoint -> GGUF with 2-D tensors in fp16 (or fp32) and 1-D tensors in fp32."""
+def _tokenizer_pre(model_path: str) -> str:
+    """`tokenizer.ggml.pre` (which pre-tokenizer regex llama.cpp applies).  convert_hf_to_gguf.py identifies it by
+    hashing the tokenization of a fixed probe text against a table; that table is not on this box, so the family is
+    read off the pre-tokenizer description in tokenizer.json instead (the regex IS what the hash fingerprints)."""
+    try:
+        with open(os.path.join(model_path, "tokenizer.json")) as f:
+            pre = json.load(f).get("pre_tokenizer") or {}
+    except Exception:
+        return "default"
+    kinds, patterns, digits = [], [], False
+
+    def walk(node):
+        nonlocal digits
+        if isinstance(node, dict):
+            if "type" in node:
+                kinds.append(node["type"])
+            if node.get("type") == "Digits" and node.get("individual_digits"):
+                digits = True
+            pat = node.get("pattern")
+            if isinstance(pat, dict):
+                patterns.extend(str(v) for v in pat.values())
+            for v in node.values():
+                walk(v)
+        elif isinstance(node, list):
+            for v in node:
+                walk(v)
+    walk(pre)
+    rx = " ".join(patterns)
+    if "\\p{N}{1,3}" in rx and "(?i:" in rx:
+        return "llama-bpe"                    # Llama-3 family
+    if digits and "ByteLevel" in kinds:
+        return "smollm"                       # SmolLM / SmolLM2: Digits(individual) + ByteLevel
+    if "ByteLevel" in kinds:
+        return "gpt-2"
+    return "default"
+
+
+def write_vocab(w, model_path: str, cfg: dict, require_tokenizer: bool = True) -> bool:
+    """tokenizer.ggml.* metadata, as convert_hf_to_gguf.py LlamaModel.set_vocab writes it: sentencepiece
+    (`tokenizer.model`) -> model "llama" with scores; byte-level BPE (`tokenizer.json`) -> model "gpt2" with merges;
+    then the special-token ids / chat template through gguf.SpecialVocab.  llama.cpp refuses to load a file without
+    `tokenizer.ggml.model`, so a missing tokenizer is an error unless the caller opts out (synthetic benchmarks)."""
+    import gguf
+    from gguf import vocab as gv
+    n_vocab = int(cfg["vocab_size"])
+    if os.path.exists(os.path.join(model_path, "tokenizer.model")):
+        v = gv.SentencePieceVocab(gv.Path(model_path))
+        tokens, scores, types = [], [], []
+        for text, score, tt in v.all_tokens():
+            tokens.append(text); scores.append(score); types.append(int(tt))
+        while len(tokens) < n_vocab:
+            tokens.append(f"[PAD{len(tokens)}]".encode()); scores.append(-1000.0); types.append(int(gguf.TokenType.UNUSED))
+        w.add_tokenizer_model("llama")
+        w.add_tokenizer_pre("default")
+        w.add_token_list(tokens)
+        w.add_token_scores(scores)
+        w.add_token_types(types)
+        gguf.SpecialVocab(model_path, n_vocab=len(tokens)).add_to_gguf(w)
+        return True
+    if os.path.exists(os.path.join(model_path, "tokenizer.json")):
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(model_path)
+        vocab = tok.get_vocab()
+        rev = {i: t for t, i in vocab.items()}
+        added = tok.get_added_vocab()
+        dec = tok.added_tokens_decoder
+        tokens, types = [], []
+        for i in range(max(n_vocab, len(rev))):
+            if i not in rev:
+                tokens.append(f"[PAD{i}]"); types.append(int(gguf.TokenType.UNUSED))
+                continue
+            t = rev[i]
+            if t in added:
+                special = (i in dec and dec[i].special) or (t.startswith("<|") and t.endswith("|>"))
+                types.append(int(gguf.TokenType.CONTROL if special else gguf.TokenType.USER_DEFINED))
+            else:
+                types.append(int(gguf.TokenType.NORMAL))
+            tokens.append(t)
+        w.add_tokenizer_model("gpt2")
+        w.add_tokenizer_pre(_tokenizer_pre(model_path))
+        w.add_token_list(tokens)
+        w.add_token_types(types)
+        gguf.SpecialVocab(model_path, load_merges=True, n_vocab=len(tokens)).add_to_gguf(w)
+        return True
+    if require_tokenizer:
+        raise FileNotFoundError(f"{model_path} holds neither tokenizer.model nor tokenizer.json: the GGUF would lack "
+                                f"tokenizer.ggml.* and llama.cpp could not load it (the reference's "
+                                f"convert_hf_to_gguf.py fails here too); pass require_tokenizer=False only for "
+                                f"synthetic weight-packing runs")
+    return False
+
+
+def _rope_freq_factors(cfg: dict, head_dim: int, rope_theta: float):
+    """llama3 rope scaling travels as the `rope_freqs.weight` tensor (convert_hf_to_gguf LlamaModel.generate_extra_tensors)."""
+    rs = cfg.get("rope_scaling") or {}
+    if rs.get("rope_type", rs.get("type")) != "llama3":
+        return None
+    import math
+    factor = float(rs.get("factor", 8.0))
+    low, high = float(rs.get("low_freq_factor", 1.0)), float(rs.get("high_freq_factor", 4.0))
+    old = float(rs.get("original_max_position_embeddings", 8192))
+    out = []
+    for k in range(0, head_dim, 2):
+        freq = 1.0 / (rope_theta ** (k / head_dim))
+        wavelen = 2 * math.pi / freq
+        if wavelen < old / high:
+            out.append(1.0)
+        elif wavelen > old / low:
+            out.append(factor)
+        else:
+            smooth = (old / wavelen - low) / (high - low)
+            out.append(1.0 / ((1 - smooth) / factor + smooth))
+    return np.asarray(out, dtype=np.float32)
+
+
+def convert_hf_to_f16_gguf(model_path: str, out_file: str, outtype: str = "f16", require_tokenizer: bool = True) -> str:
+    """HF checkpoint -> GGUF with 2-D tensors in fp16 (or fp32) and 1-D tensors in fp32, plus the metadata
+    llama.cpp needs to load it (architecture hyper-parameters, rope, tokenizer)."""
     import gguf
     cfg, sd = load_hf_model(model_path)
+    if cfg.get("model_type", "llama") != "llama":
+        raise ValueError(f"convert: model_type={cfg.get('model_type')!r} is not supported (llama only)")
     n_layers = cfg["num_hidden_layers"]
     n_head = cfg["num_attention_heads"]
     n_kv = cfg.get("num_key_value_heads", n_head)
@@ -124,8 +242,18 @@ def convert_hf_to_f16_gguf(model_path: str, out_file: str, outtype: str = "f16")
     w.add_layer_norm_rms_eps(cfg.get("rms_norm_eps", 1e-5))
     rope = cfg.get("rope_theta") or (cfg.get("rope_parameters") or {}).get("rope_theta") or 10000.0
     w.add_rope_freq_base(float(rope))
+    head_dim = cfg.get("head_dim") or cfg["hidden_size"] // n_head
+    w.add_rope_dimension_count(int(head_dim))
+    rs = cfg.get("rope_scaling") or {}
+    if rs.get("rope_type", rs.get("type")) == "linear" and "factor" in rs:
+        w.add_rope_scaling_type(gguf.RopeScalingType.LINEAR)
+        w.add_rope_scaling_factor(float(rs["factor"]))
     w.add_vocab_size(cfg["vocab_size"])
     w.add_file_type(int(gguf.LlamaFileType.MOSTLY_F16 if outtype == "f16" else gguf.LlamaFileType.ALL_F32))
+    write_vocab(w, model_path, cfg, require_tokenizer)
+    ff = _rope_freq_factors(cfg, int(head_dim), float(rope))
+    if ff is not None:
+        w.add_tensor("rope_freqs.weight", ff)
     tied = cfg.get("tie_word_embeddings", False)
     for name, t in sd.items():
         if tied and name == "lm_head.weight":
@@ -191,6 +319,8 @@ def quantize_gguf(input_gguf: str, out_file: str, ftype: str, devices: Optional[
         else:
             w.add_key_value(key, val, vt)
     w.add_file_type(int(getattr(gguf.LlamaFileType, "MOSTLY_" + ftype)))
+    if "general.quantization_version" not in r.fields:
+        w.add_quantization_version(gguf.GGML_QUANT_VERSION)       # llama-quantize stamps every quantized file
     names = [t.name for t in r.tensors]
     has_output = "output.weight" in names
     plan = []

@@ -85,7 +85,8 @@ class GGUF(BaseQuantizer):
             raise NotImplementedError(f"direct conversion to outtype {outtype!r} is not implemented (f16, f32 are)")
         out_file = Path(output_path) / f"model.{outtype}.gguf"
         self.logger.info(f"Converting {model_path} -> {out_file}")
-        return gguf_file.convert_hf_to_f16_gguf(model_path, str(out_file), outtype)
+        return gguf_file.convert_hf_to_f16_gguf(model_path, str(out_file), outtype,
+                                                require_tokenizer=getattr(self, "_require_tokenizer", True))
 
     def _quantize_gguf(self, input_gguf: Union[str, Path], output_path: Union[str, Path], quant: str) -> str:
         from ...engine import gguf_file
@@ -110,6 +111,9 @@ class GGUF(BaseQuantizer):
                  output_dir: Optional[Union[str, Path]] = None, **kwargs) -> Union[str, List[str]]:
         output_path = self._ensure_output_directory(output_dir)
         model_path = getattr(model, "name_or_path", str(model))
+        # additive key: synthetic weight-only directories (benchmarks) may skip the tokenizer metadata; real models
+        # always carry it, as the reference's convert_hf_to_gguf.py requires
+        self._require_tokenizer = bool(kwargs.pop("require_tokenizer", True))
         self.source_model = model
         if isinstance(level, list):
             base_gguf = self._convert_hf(model_path, output_path, "f16")

@@ -105,6 +105,8 @@ def test_cli_end_to_end_gptq_and_gguf(tmp_path):
     mdir.mkdir()
     save_file(sd, str(mdir / "model.safetensors"), metadata={"format": "pt"})
     json.dump(shape.to_hf_config(), open(mdir / "config.json", "w"))
+    from _tiny import write_tiny_tokenizer
+    write_tiny_tokenizer(str(mdir))
     ids = torch.randint(0, 512, (10, 64), generator=torch.Generator().manual_seed(0))
     torch.save(ids, tmp_path / "calib.pt")
     out = tmp_path / "out_gptq"

@@ -18,6 +18,8 @@ def _write_model(tmp_path, layers=2, hidden=256, inter=512, heads=4, kv=2, vocab
     d.mkdir()
     save_file(sd, str(d / "model.safetensors"), metadata={"format": "pt"})
     json.dump(shape.to_hf_config(), open(d / "config.json", "w"))
+    from _tiny import write_tiny_tokenizer
+    write_tiny_tokenizer(str(d))
     return shape, sd, str(d)
 
 
@@ -90,6 +92,17 @@ def test_gguf_plugin_end_to_end_bit_exact_vs_oracle(tmp_path):
     for out, ftype in zip(outs, ["Q8_0", "Q4_K_M"]):
         r = gguf.GGUFReader(out)
         names = {t.name: t for t in r.tensors}
+        # metadata llama.cpp needs at load time (convert_hf_to_gguf.py + llama-quantize write all of these)
+        for key in ("general.architecture", "general.file_type", "general.quantization_version", "llama.block_count",
+                    "llama.embedding_length", "llama.attention.head_count", "llama.attention.head_count_kv",
+                    "llama.rope.dimension_count", "llama.rope.freq_base", "llama.vocab_size", "tokenizer.ggml.model",
+                    "tokenizer.ggml.pre", "tokenizer.ggml.tokens", "tokenizer.ggml.token_type", "tokenizer.ggml.merges",
+                    "tokenizer.ggml.bos_token_id", "tokenizer.ggml.eos_token_id"):
+            assert key in r.fields, key
+        assert r.fields["tokenizer.ggml.model"].contents() == "gpt2"
+        assert int(r.fields["general.quantization_version"].contents()) == 2
+        assert len(r.fields["tokenizer.ggml.tokens"].contents()) == shape.vocab_size
+        assert int(r.fields["llama.rope.dimension_count"].contents()) == shape.head_dim
         assert "token_embd.weight" in names and "blk.1.ffn_down.weight" in names and "output.weight" not in names
         seen_types = set()
         for hf_name, w in sd.items():
@@ -112,8 +125,15 @@ def test_gguf_plugin_end_to_end_bit_exact_vs_oracle(tmp_path):
             assert {"Q5_0", "Q8_0", "Q4_K", "Q6_K", "F32"} <= seen_types
     q.save_pretrained(str(tmp_path / "saved"))
     assert sorted(os.listdir(tmp_path / "saved")) == ["tiny-llama-Q4_K_M.gguf", "tiny-llama-Q8_0.gguf"]
+    # a directory without tokenizer files cannot become a loadable GGUF: error unless explicitly waived
+    for fn in os.listdir(path):
+        if fn.startswith("tokenizer") or fn == "special_tokens_map.json":
+            os.remove(os.path.join(path, fn))
+    with pytest.raises(FileNotFoundError):
+        q.quantize(model=path, level="Q8_0", output_dir=str(tmp_path / "gg3"))
+    q.quantize(model=path, level="Q8_0", output_dir=str(tmp_path / "gg3"), require_tokenizer=False)
     # 576-wide rows cannot hold K-quants: Q3_K_S falls back to IQ4_NL there (llama.cpp's rule), bit-exact vs the oracle
-    out = q.quantize(model=path, level="Q3_K_S", output_dir=str(tmp_path / "gg2"))
+    out = q.quantize(model=path, level="Q3_K_S", output_dir=str(tmp_path / "gg2"), require_tokenizer=False)
     r = gguf.GGUFReader(out)
     types = {t.name: t for t in r.tensors}
     tq = types["blk.0.attn_q.weight"]
