@@ -450,14 +450,14 @@ class GPTQLayerQuantizer:
 
 
 def accumulate_layer_hessians(inputs: Dict[str, torch.Tensor], n_samples_local: int, n_samples_total: int,
-                              dist: Optional[Dist] = None) -> Dict[str, torch.Tensor]:
+                              dist: Optional[Dist] = None, syrk_events=None) -> Dict[str, torch.Tensor]:
     """inputs: name -> [T_local, K] bf16 activations.  One tcgen05 SYRK launch per distinct
-    input, one all-reduce, one finalize."""
+    input, one all-reduce, one finalize.  syrk_events: {name: (start, end)} CUDA events around the SYRK alone."""
     dist = dist or Dist()
     out = {}
     for name, x in inputs.items():
         acc = HessianAccumulator(x.shape[-1], x.device)
-        acc.add(x, n_samples_local)
+        acc.add(x, n_samples_local, syrk_events=(syrk_events or {}).get(name))
         acc.sync_diagonal()
         dist.all_reduce_sum(acc.H)
         out[name] = acc.finalize(n_samples_total)
