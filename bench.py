@@ -31,6 +31,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # see quantool_b200/__init__.py (must precede CUDA init)
 
 import torch  # noqa: E402
 
@@ -569,6 +570,9 @@ def main():
     Kmax = max(dims.values())
     hess_events = []
 
+    from quantool_b200.engine.gptq import HessianAccumulator
+    accs = {n: HessianAccumulator(k, dev) for n, k in dims.items()}
+
     def hot_step(record=False):
         for l in range(L):
             ev = {}
@@ -576,8 +580,10 @@ def main():
                 ev = {n: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                       for n, x in acts.items() if x.shape[-1] == Kmax}
                 hess_events.extend(ev.values())
-            hess = pipeline.accumulate_layer_hessians(acts, n_local, a.samples, d, syrk_events=ev)
-            res = lq.quantize_layer(weights[l], hess)
+            # raw sums per rank; the NCCL all-reduce of each H, its 2/n scaling, the chain and the column loops run
+            # per distinct input on that input's stream and communicator lane (what quantize_model_gptq does)
+            done = pipeline.accumulate_layer_sums(acts, n_local, accs, syrk_events=ev)
+            res = lq.quantize_layer(weights[l], None, accs=accs, n_total=a.samples, acc_events=done)
             for lin, r in res.items():
                 compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args)
 
@@ -632,7 +638,7 @@ def main():
 
     # ---- e2e through the plugin-level entry with host buffers -------------------------------
     e2e = parity = None
-    del acts
+    del acts, accs
     lq.drop_scratch()
     if not a.no_e2e:
         host_sd = {}

@@ -104,6 +104,13 @@ int qt_hessian_finalize(float* H, int K, float factor, void* stream);
 int qt_hessian_diag_accumulate(const void* X, int dtype, int64_t T, int K, float* diag, float* scratch, void* stream);
 int qt_hessian_set_diagonal(float* H, int K, const float* diag, void* stream);
 int qt_hessian_set_splits(int splits);   /* tuning: force the token split count (0 = heuristic) */
+/* Packed upper block-triangle of a K x K fp32 matrix: what the multi-GPU path puts on NVLink instead of the full
+ * square ("all-reduce the packed triangle").  Row block i (128 rows) is stored from column
+ * floor(128 i / align) * align; align = 256 for the raw Hessian sums (the SYRK's tile width), 128 for the
+ * upper-triangular factor U.  zero_below != 0 also clears everything left of the stored part (U on receivers). */
+int64_t qt_tri_packed_elems(int K, int align);
+int qt_tri_pack(const float* M, int K, int align, float* packed, void* stream);
+int qt_tri_unpack(const float* packed, int K, int align, int zero_below, float* M, void* stream);
 /* dead[i] = (H[i][i]==0); damp = percdamp*mean(diag); Hf = J P^T (H' + damp I) P J (lower triangle),
  * perm int32 [K] or NULL, dead uint8 [K], damp_scratch fp32 [1] */
 int qt_gptq_prepare_hessian(const float* H, const int* perm, int K, float percdamp, float* Hf, uint8_t* dead,

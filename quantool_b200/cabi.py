@@ -40,6 +40,9 @@ _SIGS = {
     "qt_hessian_finalize": [_vp, _i32, _f32, _vp],
     "qt_hessian_diag_accumulate": [_vp, _i32, _i64, _i32, _vp, _vp, _vp],
     "qt_hessian_set_diagonal": [_vp, _i32, _vp, _vp],
+    "qt_tri_packed_elems": [_i32, _i32],
+    "qt_tri_pack": [_vp, _i32, _i32, _vp, _vp],
+    "qt_tri_unpack": [_vp, _i32, _i32, _i32, _vp, _vp],
     "qt_gptq_prepare_hessian": [_vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp],
     "qt_gptq_hinv_factor": [_vp, _vp, _vp, _i32, _vp, _vp],
     "qt_gptq_hinv_factor_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp],
@@ -67,7 +70,7 @@ _SIGS = {
     "qt_split_tf32_transpose": [_vp, _vp, _vp, _i32, _vp],
 }
 _RESTYPE = {"qt_last_error": ctypes.c_char_p, "qt_launch_count": ctypes.c_ulonglong,
-            "qt_gguf_batch_table_bytes": ctypes.c_int64}
+            "qt_gguf_batch_table_bytes": ctypes.c_int64, "qt_tri_packed_elems": ctypes.c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -309,6 +312,34 @@ def hessian_finalize(H: torch.Tensor, factor: float) -> None:
     _dev(H, "H")
     with torch.cuda.device(H.device):
         _check(lib().qt_hessian_finalize(_p(H), H.shape[0], float(factor), _stream()), "qt_hessian_finalize")
+
+
+def tri_packed_elems(K: int, align: int) -> int:
+    n = int(lib().qt_tri_packed_elems(K, align))
+    if n < 0:
+        raise QtError("qt_tri_packed_elems: invalid arguments")
+    return n
+
+
+def tri_pack(M: torch.Tensor, align: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Packed upper block-triangle of a square fp32 matrix (align 256: raw Hessian sums, 128: the factor U)."""
+    _dev(M, "M")
+    K = M.shape[0]
+    n = tri_packed_elems(K, align)
+    if out is None:
+        out = torch.empty((n,), dtype=torch.float32, device=M.device)
+    assert out.numel() >= n and out.dtype == torch.float32
+    with torch.cuda.device(M.device):
+        _check(lib().qt_tri_pack(_p(M), K, align, _p(out), _stream()), "qt_tri_pack")
+    return out[:n]
+
+
+def tri_unpack(packed: torch.Tensor, M: torch.Tensor, align: int, zero_below: bool = False) -> torch.Tensor:
+    _dev(M, "M")
+    _dev(packed, "packed")
+    with torch.cuda.device(M.device):
+        _check(lib().qt_tri_unpack(_p(packed), M.shape[0], align, int(zero_below), _p(M), _stream()), "qt_tri_unpack")
+    return M
 
 
 def gptq_prepare_hessian(H: torch.Tensor, perm: Optional[torch.Tensor], percdamp: float):

@@ -415,7 +415,12 @@ template <int DT, bool VIA_F16>
 __global__ void __launch_bounds__(256) pack_iq4nl_kernel(const Segs segs) {
     __shared__ float sx[kSimpleBlocksPerCta][33];
     __shared__ __align__(16) uint8_t sout[kSimpleBlocksPerCta * 18];
+    __shared__ float tbl[16];
     const int t = threadIdx.x;
+    if (t < 16) {
+        const float vals[16] = QT_IQ4NL_VALUES;
+        tbl[t] = vals[t];
+    }
     for (int tile = blockIdx.x; tile < segs.total_tiles; tile += gridDim.x) {
         int lt;
         const Seg sg = seg_of(segs, tile, lt);
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(256) pack_iq4nl_kernel(const Segs segs) {
         float v[32];
 #pragma unroll
         for (int l = 0; l < 32; ++l) v[l] = sx[t][l];
-        kq::iq4nl_block(v, sout + t * 18);
+        kq::iq4nl_block(tbl, v, sout + t * 18);
         __syncthreads();
         copy_out(dst + base * 18, sout, nvalid * 18);
         __syncthreads();

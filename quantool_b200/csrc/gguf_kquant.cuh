@@ -688,8 +688,13 @@ QT_HD void q3k_phase_c(int t, S& s) {
 // IQ4_NL (llama.cpp's fallback for Q2_K / Q3_K rows that are not a multiple of 256): one thread per 32-element
 // block.  quantize_row_iq4_nl_impl(32, 32, quant_weights = NULL, ntry = 7): weights x^2, 1 + 15 candidate scales.
 // ------------------------------------------------------------------------------------
+// kvalues_iq4nl.  The packer indexes the table with data-dependent indices: a `switch` became divergent branches
+// (one thread per block, every lane somewhere else: 155 ms for 235 M elements), so the callers pass a 16-entry
+// table - shared memory on the device (16 distinct banks: conflict-free), a static array on the host.
+#define QT_IQ4NL_VALUES {-127.f, -104.f, -83.f, -65.f, -49.f, -35.f, -22.f, -10.f, 1.f, 13.f, 25.f, 38.f, 53.f, 69.f, 89.f, 113.f}
+
 QT_HD float iq4nl_value(int i) {
-    // kvalues_iq4nl; a switch keeps it in immediates on both host and device
+    // immediates, for compile-time or warp-uniform indices (dequantize)
     switch (i) {
         case 0: return -127.f; case 1: return -104.f; case 2: return -83.f; case 3: return -65.f;
         case 4: return -49.f; case 5: return -35.f; case 6: return -22.f; case 7: return -10.f;
@@ -698,26 +703,30 @@ QT_HD float iq4nl_value(int i) {
     }
 }
 
-// best_index_int8(16, kvalues_iq4nl, x): nearest table value, ties to the upper one
-QT_HD int iq4nl_best_index(float x) {
-    if (x <= -127.f) return 0;
-    if (x >= 113.f) return 15;
+// best_index_int8(16, kvalues_iq4nl, x): nearest table value, ties to the upper one.  Branch-free form of the
+// reference's bisection: with 16 entries it ends after at most 4 halvings, and a halving of an interval of width 1
+// is a no-op (mav == ml, x >= tbl[ml] holds), so four unconditional rounds give the same (ml, mu).
+QT_HD int iq4nl_best_index(const float* tbl, float x) {
     int ml = 0, mu = 15;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {          // 16 entries: the bisection ends after at most 4 halvings
-        if (mu - ml > 1) {
-            const int mav = (ml + mu) / 2;
-            if (x < iq4nl_value(mav)) mu = mav; else ml = mav;
-        }
+    for (int it = 0; it < 4; ++it) {
+        const int mav = (ml + mu) >> 1;
+        const bool below = x < tbl[mav];
+        mu = below ? mav : mu;
+        ml = below ? ml : mav;
     }
-    return x - iq4nl_value(mu - 1) < iq4nl_value(mu) - x ? mu - 1 : mu;
+    const int lo = mu > 0 ? mu - 1 : 0;
+    int r = (x - tbl[lo] < tbl[mu] - x) ? lo : mu;
+    r = (x >= 113.f) ? 15 : r;
+    r = (x <= -127.f) ? 0 : r;
+    return r;
 }
 
-QT_HD void iq4nl_sums(const float (&x)[32], float id, float& sumqx, float& sumq2) {
+QT_HD void iq4nl_sums(const float* tbl, const float (&x)[32], float id, float& sumqx, float& sumq2) {
     sumqx = 0.f; sumq2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const float q = iq4nl_value(iq4nl_best_index(id * x[j]));
+        const float q = tbl[iq4nl_best_index(tbl, id * x[j])];
         const float w = x[j] * x[j];
         sumqx += w * q * x[j];
         sumq2 += w * q * q;
@@ -725,7 +734,7 @@ QT_HD void iq4nl_sums(const float (&x)[32], float id, float& sumqx, float& sumq2
 }
 
 // out: 18 bytes (fp16 d, 16 bytes of nibbles: element j low, j + 16 high)
-QT_HD void iq4nl_block(const float (&x)[32], uint8_t* out) {
+QT_HD void iq4nl_block(const float* tbl, const float (&x)[32], uint8_t* out) {
     float amax = 0.f, mx = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -736,13 +745,13 @@ QT_HD void iq4nl_block(const float (&x)[32], uint8_t* out) {
     if (!(amax < 1e-15f)) {
         float d = -mx / -127.f;
         float sumqx, sumq2;
-        iq4nl_sums(x, 1 / d, sumqx, sumq2);
+        iq4nl_sums(tbl, x, 1 / d, sumqx, sumq2);
         d = sumqx / sumq2;
         float best = d * sumqx;
 #pragma unroll 1
         for (int itry = -7; itry <= 7; ++itry) {
             const float id = (itry + -127.f) / mx;
-            iq4nl_sums(x, id, sumqx, sumq2);
+            iq4nl_sums(tbl, x, id, sumqx, sumq2);
             if (sumq2 > 0 && sumqx * sumqx > best * sumq2) {
                 d = sumqx / sumq2; best = d * sumqx;
             }
@@ -754,7 +763,7 @@ QT_HD void iq4nl_block(const float (&x)[32], uint8_t* out) {
     const float id = scale ? 1 / scale : 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-        out[2 + j] = (uint8_t)(iq4nl_best_index(id * x[j]) | (iq4nl_best_index(id * x[16 + j]) << 4));
+        out[2 + j] = (uint8_t)(iq4nl_best_index(tbl, id * x[j]) | (iq4nl_best_index(tbl, id * x[16 + j]) << 4));
 }
 
 }  // namespace kq

@@ -295,6 +295,49 @@ __global__ void __launch_bounds__(256) set_diag_kernel(float* __restrict__ H, in
 
 static int g_force_splits = 0;
 
+
+// ---- packed upper block-triangle (what crosses NVLink) ------------------------------------------------------
+// Before `finalize` H holds raw sums only in the 128 x 256 tiles that touch the upper triangle, and the inverse
+// factor U is upper-triangular: shipping the K x K square through the all-reduce / broadcast moves twice the bytes
+// (822 MB instead of 420 MB at K = 14336).  Row block i (128 rows) is stored from column c0(i) = floor(128 i / align)
+// * align to K, blocks back to back; align = 256 for H (the SYRK's tile width), 128 for U.
+__device__ __forceinline__ long long tri_block_offset(int i, int K, int align) {
+    long long off = 0;
+    for (int b = 0; b < i; b++) off += 128LL * (K - ((b * 128) / align) * align);
+    return off;
+}
+
+template <bool UNPACK>
+__global__ void __launch_bounds__(256) tri_pack_kernel(float* __restrict__ M, float* __restrict__ P, int K, int align,
+                                                       int zero_below) {
+    const int i = blockIdx.x;
+    const int c0 = ((i * 128) / align) * align;
+    const int w = K - c0;
+    const long long off = tri_block_offset(i, K, align);
+    const int rows = min(128, K - i * 128);
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        float* mrow = M + (long long)(i * 128 + r) * K;
+        float* prow = P + off + (long long)r * w;
+        if (((K | c0) & 3) == 0) {
+            float4* m4 = reinterpret_cast<float4*>(mrow + c0);
+            float4* p4 = reinterpret_cast<float4*>(prow);
+            for (int c = threadIdx.x; c < (w >> 2); c += 256) {
+                if (UNPACK) m4[c] = p4[c]; else p4[c] = m4[c];
+            }
+            if (UNPACK && zero_below) {
+                float4* z4 = reinterpret_cast<float4*>(mrow);
+                for (int c = threadIdx.x; c < (c0 >> 2); c += 256) z4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int c = threadIdx.x; c < w; c += 256) {
+                if (UNPACK) mrow[c0 + c] = prow[c]; else prow[c] = mrow[c0 + c];
+            }
+            if (UNPACK && zero_below)
+                for (int c = threadIdx.x; c < c0; c += 256) mrow[c] = 0.f;
+        }
+    }
+}
+
 }  // namespace hess
 }  // namespace qt
 
@@ -410,6 +453,32 @@ int qt_hessian_set_diagonal(float* H, int K, const float* diag, void* stream) {
     if (!H || !diag || K <= 0) return QT_ERR_INVALID;
     set_diag_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(H, K, diag);
     return check_launch("hessian_set_diagonal");
+}
+
+// Packed upper block-triangle of a K x K fp32 matrix (see tri_pack_kernel).  align: 256 for raw Hessian sums,
+// 128 for the upper-triangular factor U.  qt_tri_packed_elems gives the element count of the packed buffer.
+int64_t qt_tri_packed_elems(int K, int align) {
+    if (K <= 0 || (align != 128 && align != 256)) return -1;
+    long long n = 0;
+    for (int b = 0; b * 128 < K; b++) {
+        const int rows = (K - b * 128) < 128 ? (K - b * 128) : 128;
+        n += (long long)rows * (K - ((b * 128) / align) * align);
+    }
+    return n;
+}
+
+int qt_tri_pack(const float* M, int K, int align, float* packed, void* stream) {
+    if (!M || !packed || K <= 0 || (align != 128 && align != 256)) return QT_ERR_INVALID;
+    dim3 grid((K + 127) / 128, 16);
+    tri_pack_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(M), packed, K, align, 0);
+    return check_launch("tri_pack");
+}
+
+int qt_tri_unpack(const float* packed, int K, int align, int zero_below, float* M, void* stream) {
+    if (!M || !packed || K <= 0 || (align != 128 && align != 256)) return QT_ERR_INVALID;
+    dim3 grid((K + 127) / 128, 16);
+    tri_pack_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(M, const_cast<float*>(packed), K, align, zero_below);
+    return check_launch("tri_unpack");
 }
 
 }  // extern "C"

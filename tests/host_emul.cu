@@ -51,10 +51,11 @@ static void emul_k23(const float* x, uint8_t* out, int64_t nsuper) {
 
 extern "C" {
 void emul_iq4_nl(const float* x, uint8_t* out, int64_t nblocks) {
+    static const float tbl[16] = QT_IQ4NL_VALUES;
     for (int64_t b = 0; b < nblocks; b++) {
         float v[32];
         for (int j = 0; j < 32; j++) v[j] = x[b * 32 + j];
-        iq4nl_block(v, out + b * 18);
+        iq4nl_block(tbl, v, out + b * 18);
     }
 }
 void emul_q2_K(const float* x, uint8_t* out, int64_t nsuper) { emul_k23<84, false>(x, out, nsuper); }
