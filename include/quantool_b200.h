@@ -137,6 +137,9 @@ int qt_flip_upper(const float* X, float* U, int K, void* stream);
 int qt_gptq_permute_in(const void* W, int dtype, const int* perm, const uint8_t* dead, float* Wp, int N, int K,
                        void* stream);
 int qt_gptq_permute_out(const float* Wp, const int* inv_perm, void* out, int dtype, int N, int K, void* stream);
+/* tuning / A-B checks: 1 = run every 128-column block through the generic block kernel (also used for partial
+ * blocks), 0 (default) = the lean full-block kernel.  Both produce the same bits. */
+int qt_gptq_set_block_kernel(int generic);
 /* blocked column loop (block 128).  mode 0: re-fit group qparams at group starts (group_size 32/64/128),
  * 1: static scales looked up through g_idx (actorder=weight), 2: one scale per row.  W in/out.
  * U_hi/U_lo (qt_split_tf32_transpose of U) non-NULL: lazy update on the tensor cores, batched over 512-column

@@ -66,6 +66,7 @@ _SIGS = {
     "qt_awq_scale_qdq": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
     "qt_sq_err_sum": [_vp, _vp, _i32, _i64, _vp, _vp],
     "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "qt_gptq_set_block_kernel": [_i32],
     "qt_split_tf32": [_vp, _vp, _vp, _i64, _vp],
     "qt_split_tf32_transpose": [_vp, _vp, _vp, _i32, _vp],
 }

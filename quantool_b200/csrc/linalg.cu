@@ -32,11 +32,12 @@ constexpr int LDS_ = NB + 1;
 // shared memory (the block is padded to 128 x 128 with an identity so every loop is uniform):
 //   factor : 4 panels of 32 columns, left-looking.  (1) panel -= L[:, :c0] * L[c0:c0+32, :c0]^T with
 //            all 256 threads (3x4 register tiles), (2) 32x32 diagonal factor by one warp in registers
-//            (right-looking, shuffle broadcasts), (3) rows below solved against it, one thread per row.
-//            Measured with clock64: the kernel is bound by the 128 sequential pivots (~450 cycles
-//            each for (2), ~350 for (3)), not by throughput.
-//   invert : 32x32 diagonal inverses by 4 warps (forward substitution, one column per lane), then
-//            two merge levels  Y21 = -Y22 * (L21 * Y11)  as register-tiled shared-memory GEMMs.
+//            (right-looking, shuffle broadcasts, no lane masks), (2b) its inverse by the same warp,
+//            (3) rows below = (rows) * inverse^T as a product over all threads.  The kernel is bound by the
+//            128 sequential pivots; the first version (masked updates: ~450 cycles per pivot, rows below
+//            solved one thread per row: ~350 cycles per pivot column) took 86 us.
+//   invert : the 32x32 diagonal inverses come from (2b); two merge levels  Y21 = -Y22 * (L21 * Y11)  as
+//            register-tiled shared-memory GEMMs.
 // Writes L into A's lower triangle and L^-1 into X's diagonal block.  A non-positive / NaN pivot
 // records info = 1-based global column and substitutes 1 (caller applies upstream's Hinv = I).
 __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ A, float* __restrict__ X, int ld,
@@ -110,13 +111,13 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ A, f
             }
             __syncthreads();
         }
-        // (2) 32 x 32 diagonal block by warp 0, left-looking (Crout): lane = row; column j is
-        //     L[i][j] = (a[i][j] - sum_{k<j} L[i][k] L[j][k]) / L[j][j].  Real loops (small code: the
-        //     fully unrolled register version stalled on instruction fetch), no store->load
-        //     dependence inside the k loop, row reads are conflict-free (stride 129).
+        // (2) 32 x 32 diagonal block by warp 0, right-looking, the block lives in registers (lane = row).  No lane
+        //     masks in the rank-1 update: entries above the diagonal (column k in a lane < k) are never read again,
+        //     so every lane runs the same shuffle + FMA stream (the masked form cost ~450 cycles per pivot).
+        //     (2b) the same warp then inverts the factor by forward substitution (lane = column of the inverse,
+        //     kept in registers; L rows are shared-memory broadcasts).  That inverse is the diagonal block of the
+        //     final L^-1 AND turns the solve of the rows below into a product (3).
         if (warp == 0) {
-            // right-looking, the 32 x 32 block lives in registers (lane = row); ~1.1k instructions, the only
-            // fully unrolled region of this kernel so it stays inside the instruction cache
             float a[32];
             int badcol = -1;
 #pragma unroll
@@ -126,64 +127,78 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ A, f
                 float d = __shfl_sync(0xffffffffu, a[j], j);
                 if (!(d > 0.f)) { d = 1.f; if (badcol < 0) badcol = c0 + j; }
                 const float inv = rsqrtf(d);      // ~2 ulp: well inside fp32 Cholesky noise
-                const float lij = (lane > j) ? a[j] * inv : 0.f;
-                a[j] = (lane == j) ? d * inv : ((lane > j) ? lij : a[j]);
+                const float lij = a[j] * inv;
+                a[j] = (lane == j) ? d * inv : lij;
                 if (lane == j) dinv[c0 + j] = inv;
 #pragma unroll
-                for (int k = 0; k < 32; k++) {
-                    if (k > j) {
-                        const float lkj = __shfl_sync(0xffffffffu, lij, k);
-                        a[k] = (lane >= k) ? fmaf(-lij, lkj, a[k]) : a[k];
-                    }
+                for (int k = j + 1; k < 32; k++) {
+                    const float lkj = __shfl_sync(0xffffffffu, lij, k);
+                    a[k] = fmaf(-lij, lkj, a[k]);
                 }
             }
             if (badcol >= 0 && lane == 0) atomicCAS(info, 0, kofs + badcol + 1);
 #pragma unroll
             for (int j = 0; j < 32; j++)
                 if (j <= lane) L[c0 + lane][c0 + j] = a[j];
+            __syncwarp();
+            // (2b) Y11 = L11^-1, column `lane`: y[i] = (delta - sum_{k<i} L[i][k] y[k]) / L[i][i]
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const float* li = &L[c0 + i][c0];
+                float s0 = (i == lane) ? 1.f : 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < i; k++) {
+                    const float t = li[k];
+                    if ((k & 3) == 0) s0 = fmaf(-t, y[k], s0);
+                    else if ((k & 3) == 1) s1 = fmaf(-t, y[k], s1);
+                    else if ((k & 3) == 2) s2 = fmaf(-t, y[k], s2);
+                    else s3 = fmaf(-t, y[k], s3);
+                }
+                y[i] = (i >= lane) ? ((s0 + s1) + (s2 + s3)) * dinv[c0 + i] : 0.f;
+                Y[c0 + i][c0 + lane] = y[i];
+            }
         }
         __syncthreads();
-        // (3) rows below the diagonal block: x * L11^T = a, one thread per row, in place in smem
-        if (tid < NB - c0 - 32) {
-            float* x = &L[c0 + 32 + tid][c0];
-            for (int j = 0; j < 32; j++) {
-                const float* lj = &L[c0 + j][c0];
-                float s0 = x[j], s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                int k = 0;
-                for (; k + 3 < j; k += 4) {
-                    const float a0 = x[k], a1 = x[k + 1], a2 = x[k + 2], a3 = x[k + 3];
-                    const float b0 = lj[k], b1 = lj[k + 1], b2 = lj[k + 2], b3 = lj[k + 3];
-                    s0 = fmaf(-a0, b0, s0); s1 = fmaf(-a1, b1, s1);
-                    s2 = fmaf(-a2, b2, s2); s3 = fmaf(-a3, b3, s3);
+        // (3) rows below the diagonal block: P = A[:, c0:c0+32] * Y11^T (Y11 lower-triangular: k <= c).  Thread =
+        //     (row, column parity): 96 rows x 2 at most; the row segment is read into registers before any thread
+        //     of the row writes (barrier in between).
+        {
+            const int nbelow = NB - c0 - 32;
+            const int rrow = tid % 96, par = tid / 96;           // par is warp-uniform (96 = 3 warps)
+            const bool act = par < 2 && rrow < nbelow;
+            float o[16];
+            if (act) {
+                float x[32];
+                const float* xr = &L[c0 + 32 + rrow][c0];
+#pragma unroll
+                for (int k = 0; k < 32; k++) x[k] = xr[k];
+#pragma unroll
+                for (int cc = 0; cc < 16; cc++) {
+                    const int c = 2 * cc + par;
+                    const float* yc = &Y[c0 + c][c0];
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        if (k <= 2 * cc + 1) {                    // k <= c for par = 1; one harmless zero term for par = 0
+                            if (k & 1) s1 = fmaf(x[k], yc[k], s1); else s0 = fmaf(x[k], yc[k], s0);
+                        }
+                    }
+                    o[cc] = s0 + s1;
                 }
-                for (; k < j; k++) s0 = fmaf(-x[k], lj[k], s0);
-                x[j] = ((s0 + s1) + (s2 + s3)) * dinv[c0 + j];
+            }
+            __syncthreads();
+            if (act) {
+                float* xr = &L[c0 + 32 + rrow][c0];
+#pragma unroll
+                for (int cc = 0; cc < 16; cc++) xr[2 * cc + par] = o[cc];
             }
         }
         __syncthreads();
     }
 
     // ---------------- invert ----------------
-    // (a) 32 x 32 diagonal inverses: warp w < 4 owns block w, lane c owns column c of the inverse
-    //     (forward substitution; Y column reads/writes are lane-consecutive, L reads are broadcasts)
-    if (warp < 4) {
-        const int b0 = 32 * warp, c = lane;
-        for (int i = 0; i < 32; i++) {
-            const float* li = &L[b0 + i][b0];
-            float s0 = (i == c) ? 1.f : 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            int k = 0;
-            for (; k + 3 < i; k += 4) {
-                const float a0 = li[k], a1 = li[k + 1], a2 = li[k + 2], a3 = li[k + 3];
-                const float b0_ = Y[b0 + k][b0 + c], b1 = Y[b0 + k + 1][b0 + c], b2 = Y[b0 + k + 2][b0 + c],
-                            b3 = Y[b0 + k + 3][b0 + c];
-                s0 = fmaf(-a0, b0_, s0); s1 = fmaf(-a1, b1, s1);
-                s2 = fmaf(-a2, b2, s2); s3 = fmaf(-a3, b3, s3);
-            }
-            for (; k < i; k++) s0 = fmaf(-li[k], Y[b0 + k][b0 + c], s0);
-            Y[b0 + i][b0 + c] = (i >= c) ? ((s0 + s1) + (s2 + s3)) * dinv[b0 + i] : 0.f;
-        }
-    }
-    __syncthreads();
+    // the 32 x 32 diagonal inverses are already in Y (2b); two merge levels  Y21 = -Y22 * (L21 * Y11)
     // (b) level 32: pairs (0,1) and (2,3); 128 threads per pair, 2 x 4 outputs per thread
     {
         const int pr = tid >> 7, t = tid & 127;
@@ -271,6 +286,129 @@ __global__ void __launch_bounds__(256) potrf_inv_kernel(float* __restrict__ A, f
             const long long g = (long long)(kofs + i) * ld + kofs + j4;
             *reinterpret_cast<float4*>(A + g) = make_float4(L[i][j4], L[i][j4 + 1], L[i][j4 + 2], L[i][j4 + 3]);
             *reinterpret_cast<float4*>(X + g) = make_float4(Y[i][j4], Y[i][j4 + 1], Y[i][j4 + 2], Y[i][j4 + 3]);
+        }
+    }
+}
+
+// The two single-tile products on the blocked Cholesky's critical path, in ONE launch over 10 CTAs:
+//     P_top <- P_top * (L_kk^-1)^T          (TRSM of the nb2 rows right below the diagonal block, as a product)
+//     D     <- D - P_top * P_top^T          (the next diagonal block, lower 32 x 32 tiles)
+// They used to be two 128 x 128 x 128 FFMA GEMM launches of one CTA each (24-35 us apiece, CUPTI) between every
+// pair of potrf_inv launches.  CTA (ti, tj), tj <= ti, owns tile (ti, tj) of D and computes the two 32-row strips of
+// the solved panel it needs itself (redundantly across CTAs: no grid-wide dependency); the diagonal CTAs write their
+// strip back as the new P_top.  fp32 FFMA, fixed summation order.
+constexpr int PT_LD = NB + 1;
+constexpr size_t PT_SMEM = (size_t)(NB + 4 * 32) * PT_LD * sizeof(float);
+
+__device__ __forceinline__ void panel_strip(const float (*Ps)[PT_LD], const float (*Xs)[PT_LD], float (*Ss)[PT_LD], int tid) {
+    // S[r][c] = sum_{j <= c} P[r][j] X[c][j];  thread = rows 4 rg .. +3, columns lane + 32 m
+    const int lane = tid & 31, rg = tid >> 5;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) acc[a][m] = 0.f;
+#pragma unroll
+    for (int jb = 0; jb < 4; jb++) {
+#pragma unroll 4
+        for (int jj = 0; jj < 32; jj++) {
+            const int j = 32 * jb + jj;
+            float pv[4], xv[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) pv[a] = Ps[4 * rg + a][j];
+#pragma unroll
+            for (int m = 0; m < 4; m++)
+                if (m >= jb) xv[m] = Xs[lane + 32 * m][j];       // columns c < 32 jb have X[c][j] = 0 for this j
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int m = 0; m < 4; m++)
+                    if (m >= jb) acc[a][m] = fmaf(pv[a], xv[m], acc[a][m]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) Ss[4 * rg + a][lane + 32 * m] = acc[a][m];
+}
+
+__global__ void __launch_bounds__(256) panel_top_kernel(float* __restrict__ A, float* __restrict__ X, int ld, int k,
+                                                        int nb, int nb2) {
+    extern __shared__ float sm[];
+    float(*Xs)[PT_LD] = reinterpret_cast<float(*)[PT_LD]>(sm);
+    float(*Pi)[PT_LD] = reinterpret_cast<float(*)[PT_LD]>(sm + NB * PT_LD);
+    float(*Pj)[PT_LD] = reinterpret_cast<float(*)[PT_LD]>(sm + (NB + 32) * PT_LD);
+    float(*Si)[PT_LD] = reinterpret_cast<float(*)[PT_LD]>(sm + (NB + 64) * PT_LD);
+    float(*Sj)[PT_LD] = reinterpret_cast<float(*)[PT_LD]>(sm + (NB + 96) * PT_LD);
+    const int tid = threadIdx.x;
+    int ti = 0, tj = blockIdx.x;                     // lower-triangular tile index -> (ti, tj)
+    while (tj > ti) { tj -= ti + 1; ti++; }
+    if (32 * ti >= nb2) return;
+    const int r0 = k + nb;                           // first row of the panel's top rows (= next diagonal block)
+    // X_kk (lower-triangular inverse of the diagonal block), zero-padded
+    for (int q = tid; q < NB * (NB / 4); q += 256) {
+        const int i = q >> 5, j4 = (q & 31) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nb && j4 < nb) v = *reinterpret_cast<const float4*>(X + (long long)(k + i) * ld + k + j4);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) Xs[i][j4 + t] = (j4 + t <= i && j4 + t < nb) ? e[t] : 0.f;
+    }
+    for (int q = tid; q < 2 * 32 * (NB / 4); q += 256) {
+        const int which = q >> 10, rr = (q >> 5) & 31, j4 = (q & 31) * 4;
+        const int row = 32 * (which ? tj : ti) + rr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < nb2 && j4 < nb) v = *reinterpret_cast<const float4*>(A + (long long)(r0 + row) * ld + k + j4);
+        float(*P)[PT_LD] = which ? Pj : Pi;
+        P[rr][j4] = v.x; P[rr][j4 + 1] = v.y; P[rr][j4 + 2] = v.z; P[rr][j4 + 3] = v.w;
+    }
+    __syncthreads();
+    panel_strip(Pi, Xs, Si, tid);
+    if (tj != ti) panel_strip(Pj, Xs, Sj, tid);
+    __syncthreads();
+    const float(*Sb)[PT_LD] = (tj != ti) ? Sj : Si;
+    if (tj == ti) {
+        // The solved strip is the new P_top - but other CTAs of this grid may not have read the ORIGINAL rows yet,
+        // so it goes to the same position of X (below diagonal block k: unused until the triangular inverse
+        // overwrites it) and panel_top_commit_kernel copies it into A afterwards, off the critical path.
+        for (int q = tid; q < 32 * (NB / 4); q += 256) {
+            const int rr = q >> 5, j4 = (q & 31) * 4;
+            const int row = 32 * ti + rr;
+            if (row < nb2 && j4 < nb)
+                *reinterpret_cast<float4*>(X + (long long)(r0 + row) * ld + k + j4) =
+                    make_float4(Si[rr][j4], Si[rr][j4 + 1], Si[rr][j4 + 2], Si[rr][j4 + 3]);
+        }
+    }
+    // D tile (ti, tj) -= Si * Sb^T : thread = row tid / 8, columns tid % 8 + 8 m
+    {
+        const int r = tid >> 3, cg = tid & 7;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int j = 0; j < NB; j++) {
+            const float av = Si[r][j];
+#pragma unroll
+            for (int m = 0; m < 4; m++) acc[m] = fmaf(av, Sb[cg + 8 * m][j], acc[m]);
+        }
+        const int grow = 32 * ti + r;
+        if (grow < nb2) {
+            float* drow = A + (long long)(r0 + grow) * ld + r0 + 32 * tj;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int c = cg + 8 * m;
+                if (32 * tj + c < nb2) drow[c] -= acc[m];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) panel_top_commit_kernel(float* __restrict__ A, const float* __restrict__ X, int ld,
+                                                               int k, int nb, int nb2) {
+    const int r0 = k + nb;
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < nb2 * (NB / 4); q += gridDim.x * 256) {
+        const int row = q >> 5, j4 = (q & 31) * 4;
+        if (j4 < nb) {
+            const long long g = (long long)(r0 + row) * ld + k + j4;
+            *reinterpret_cast<float4*>(A + g) = *reinterpret_cast<const float4*>(X + g);
         }
     }
 }
@@ -548,6 +686,7 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
                              cudaStream_t st) {
     const size_t smem = (2 * NB * LDS_ + 64 * 65 + NB) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(panel_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM);
     if (e != cudaSuccess) { set_last_error("potrf smem attr", e); return QT_ERR_CUDA; }
     LookAhead& la = lookahead(st);
     bool potrf_ahead = false, far_pending = false;
@@ -577,14 +716,9 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
             t.alpha = 1.f; t.beta = 0.f;
             int rc;
             if (nb2 > 0) {
-                t.A = P; t.C = P; t.M = nb2;
-                rc = sgemm(true, t, 1, st);
-                if (rc) return rc;
-                GemmArgs sd{};   // next diagonal block -= P_top P_top^T
-                sd.A = P; sd.B = P; sd.C = A + (long long)(k + nb) * ld + (k + nb);
-                sd.M = nb2; sd.N = nb2; sd.Kd = nb; sd.lda = sd.ldb = sd.ldc = ld;
-                sd.alpha = -1.f; sd.beta = 1.f;
-                rc = sgemm(true, sd, 1, st);
+                // top rows of the TRSM + update of the next diagonal block: one 10-CTA launch (panel_top_kernel)
+                panel_top_kernel<<<10, 256, PT_SMEM, st>>>(A, X, ld, k, nb, nb2);
+                rc = check_launch("panel_top");
                 if (rc) return rc;
                 if (la.ok) {
                     if (cudaEventRecord(la.panel_ready, st) != cudaSuccess) return QT_ERR_CUDA;
@@ -595,6 +729,9 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
                     if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
                     potrf_ahead = true;
                 }
+                panel_top_commit_kernel<<<8, 256, 0, st>>>(A, X, ld, k, nb, nb2);
+                rc = check_launch("panel_top_commit");
+                if (rc) return rc;
             }
             if (rem > nb2) {     // rest of the TRSM
                 float* Pr = P + (long long)nb2 * ld;

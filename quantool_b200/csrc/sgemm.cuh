@@ -176,6 +176,75 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmArgs g) {
         }
 }
 
+// ---- Kd = 128, "NT": the panel products of the blocked Cholesky -------------------------------------------
+// The chain's TRSMs and inner SYRK updates are skinny (N = 128..384, inner dimension exactly 128) and sit between
+// latency-bound kernels, so what matters is how long ONE tile takes: the slab pipeline above makes eight dependent
+// global-memory round trips for Kd = 128 (24-35 us per launch, CUPTI).  Here the whole k range of a 64 x 128 tile
+// is staged with one wave of cp.async (both operands k-contiguous, rows padded to 132 floats: LDS.128 along k is
+// conflict-free), one barrier, then 4 x 8 outputs per thread straight from shared memory.
+constexpr int SK_BM = 64, SK_BN = 128, SK_KD = 128, SK_LD = SK_KD + 4;
+constexpr size_t SK_SMEM = (size_t)(SK_BM + SK_BN) * SK_LD * sizeof(float);
+
+template <int UNUSED>   // a template so that the header can be included from several translation units
+__global__ void __launch_bounds__(256, 2) sgemm_nt_k128_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) float sk_sm[];
+    float(*As)[SK_LD] = reinterpret_cast<float(*)[SK_LD]>(sk_sm);
+    float(*Bs)[SK_LD] = reinterpret_cast<float(*)[SK_LD]>(sk_sm + SK_BM * SK_LD);
+    const int m0 = blockIdx.y * SK_BM, n0 = blockIdx.x * SK_BN;
+    if (g.lower_tiles_only && n0 > m0 + g.tri_row_offset + SK_BM - 1) return;
+    const int tid = threadIdx.x;
+    // (64 + 128) rows x 32 float4: 24 cp.async per thread, all in flight at once; out-of-range rows are zero-filled
+    for (int q = tid; q < (SK_BM + SK_BN) * (SK_KD / 4); q += 256) {
+        const int r = q >> 5, k4 = (q & 31) * 4;
+        const float* src;
+        bool ok;
+        float* dst;
+        if (r < SK_BM) { ok = (m0 + r) < g.M; src = g.A + (long long)(ok ? m0 + r : 0) * g.lda + k4; dst = &As[r][k4]; }
+        else { const int n = r - SK_BM; ok = (n0 + n) < g.N; src = g.B + (long long)(ok ? n0 + n : 0) * g.ldb + k4; dst = &Bs[n][k4]; }
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        const int bytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;          // rows 4 ty + i, columns tx + 16 j
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < SK_KD; k += 4) {
+        float4 a[4], b[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(&As[4 * ty + i][k]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) b[j] = *reinterpret_cast<const float4*>(&Bs[tx + 16 * j][k]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+                acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+                acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+                acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int m = m0 + 4 * ty + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int n = n0 + tx + 16 * j;
+            if (n >= g.N) continue;
+            float* cp = g.C + (long long)m * g.ldc + n;
+            *cp = (g.beta != 0.f) ? g.alpha * acc[i][j] + g.beta * (*cp) : g.alpha * acc[i][j];
+        }
+    }
+}
+
 // returns QT_OK / QT_ERR_INVALID (alignment contract: dims and leading dims multiples of 4,
 // pointers 16-byte aligned).  Empty problems are a no-op.
 inline int sgemm(bool b_nk, const GemmArgs& g, int batch, cudaStream_t st) {
@@ -183,6 +252,18 @@ inline int sgemm(bool b_nk, const GemmArgs& g, int batch, cudaStream_t st) {
     if ((g.N & 3) || (g.Kd & 3) || (g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return QT_ERR_INVALID;
     if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || ((uintptr_t)g.C & 15)) return QT_ERR_INVALID;
     if ((g.strideA & 3) || (g.strideB & 3) || (g.strideC & 3)) return QT_ERR_INVALID;
+    if (b_nk && g.Kd == SK_KD && batch == 1 && !g.a_lower_tri && !g.b_lower_tri) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(sgemm_nt_k128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM) !=
+                cudaSuccess)
+                return QT_ERR_CUDA;
+            attr_set = true;
+        }
+        dim3 sgrid((g.N + SK_BN - 1) / SK_BN, (g.M + SK_BM - 1) / SK_BM, 1);
+        sgemm_nt_k128_kernel<0><<<sgrid, 256, SK_SMEM, st>>>(g);
+        return check_launch("sgemm_nt_k128");
+    }
     dim3 grid((g.N + GBN - 1) / GBN, (g.M + GBM - 1) / GBM, batch);
     if (b_nk) sgemm_kernel<true><<<grid, 256, 0, st>>>(g);
     else      sgemm_kernel<false><<<grid, 256, 0, st>>>(g);

@@ -504,7 +504,9 @@ def test_gptq_baseline_widths_own_hessian(N, K, T):
         floor = (codes_2 == codes_p).float().mean().item()
         print(f"    ill-conditioned case: oracle(H) vs oracle(H rounded differently) agree on {floor:.5f}")
         assert agree_p >= min(floor, 0.999) - 0.004, (agree_p, floor)
-    assert agree_o >= 0.99, agree_o
+    # vs the oracle's OWN permutation: 6 % of 14336 positions are fp32 near-ties (asserted above to be ties), and each
+    # swapped pair that straddles a group boundary changes that group's members, hence its scale and its 128 codes
+    assert agree_o >= (0.99 if K <= 8192 else 0.95), agree_o
     assert abs(e_c - e_o) <= 0.01 * e_o
     assert abs(e_c - e_p) <= 0.01 * e_p
 
@@ -529,3 +531,33 @@ def test_tri_pack_round_trip(K, align):
     out2 = torch.full((K, K), 7.0, device="cuda")
     cabi.tri_unpack(p, out2, align, zero_below=True)
     assert torch.equal(out2, torch.where(stored, M, torch.zeros_like(M)))
+
+
+@pytest.mark.parametrize("level,actorder,N,K", [("W4A16", "group", 200, 1024), ("W4A16", "weight", 96, 512),
+                                                ("W8A16", None, 77, 768), ("W4A16_ASYM", "group", 130, 1024),
+                                                ("W4A16", "group", 4100, 256)])
+def test_lean_block_kernel_equals_generic(level, actorder, N, K):
+    """The lean full-block column kernel (division through a refined reciprocal, magic-constant rounding, group
+    parameters fitted before the walk) must give the same bits as the generic kernel: fake-quantized weight,
+    scales, zero points and per-row losses."""
+    from quantool_b200 import cabi
+    from quantool_b200.engine import gptq as eg, schemes
+    g = torch.Generator().manual_seed(N + K)
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16).cuda()
+    W[3, :] = 0                                           # an all-zero row (scale -> eps)
+    W[5, 17] = 3.0                                        # an outlier
+    x = _acts(2048, K, seed=K)
+    acc = eg.HessianAccumulator(K, "cuda")
+    acc.add(x.cuda())
+    H = acc.finalize()
+    args = schemes.resolve(level, actorder)
+    outs = []
+    try:
+        for generic in (1, 0):
+            cabi.lib().qt_gptq_set_block_kernel(generic)
+            r = eg.quantize_linear(W, H, args)
+            outs.append((r.weight.clone(), r.scale.clone(), r.zero_point.clone(), r.losses.clone()))
+    finally:
+        cabi.lib().qt_gptq_set_block_kernel(0)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
