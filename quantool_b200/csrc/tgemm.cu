@@ -55,6 +55,10 @@ struct Args {
     int accumulate, lower_only, a_tri, b_tri;
     int chain_kc;   // k chunks accumulated in TMEM before the partial sum is flushed to C (see Problem::max_chain)
     uint32_t idesc;
+    int single;     // hi * hi only
+    const float* E; // reduction epilogue (see Problem::E)
+    long long lde;
+    double* loss;
 };
 
 struct Tile {
@@ -126,12 +130,12 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
                 for (int kc = tl.kc0; kc < tl.kc1; kc++, it++) {   // sub-ranges need no special handling here
                     const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&empty[stage], ph ^ 1);
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], a.single ? A_BYTES + B_BYTES : STAGE_BYTES);
                     uint8_t* s = smem + stage * STAGE_BYTES;
                     tma_load_2d(s, &map_ahi, &full[stage], ca + kc * KC, ra);
-                    tma_load_2d(s + A_BYTES, &map_alo, &full[stage], ca + kc * KC, ra);
+                    if (!a.single) tma_load_2d(s + A_BYTES, &map_alo, &full[stage], ca + kc * KC, ra);
                     tma_load_2d(s + 2 * A_BYTES, &map_bhi, &full[stage], cb + kc * KC, rb);
-                    tma_load_2d(s + 2 * A_BYTES + B_BYTES, &map_blo, &full[stage], cb + kc * KC, rb);
+                    if (!a.single) tma_load_2d(s + 2 * A_BYTES + B_BYTES, &map_blo, &full[stage], cb + kc * KC, rb);
                 }
             }
         }
@@ -164,8 +168,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
                             const uint64_t bhi = make_desc_sw128(sb_hi + k * UMMA_K * 4, 16, 1024);
                             const uint64_t blo = make_desc_sw128(sb_lo + k * UMMA_K * 4, 16, 1024);
                             tc_mma_tf32(d_tmem, ahi, bhi, a.idesc, (kc > k0 || k > 0) ? 1u : 0u);
-                            tc_mma_tf32(d_tmem, ahi, blo, a.idesc, 1u);
-                            tc_mma_tf32(d_tmem, alo, bhi, a.idesc, 1u);
+                            if (!a.single) {
+                                tc_mma_tf32(d_tmem, ahi, blo, a.idesc, 1u);
+                                tc_mma_tf32(d_tmem, alo, bhi, a.idesc, 1u);
+                            }
                         }
                         tc_commit(&empty[stage]);
                     }
@@ -177,6 +183,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
         const int lg = warp & 3;
         uint8_t* my = epi + (warp - 2) * 2 * 4096;
         uint32_t li = 0, nstore = 0;
+        double wsum = 0.0;      // reduction epilogue: this lane's share of sum(acc * E)
         Tile tl;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             if (!decode(a, t, tl)) continue;
@@ -188,6 +195,41 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
                 li++;
                 mbar_wait(&tfull[acc], aph);
                 tc_fence_after();
+                if (a.E) {
+                    // lane = row: 32 consecutive fp32 of E per sub-tile (one 128-byte line per lane), fp32 products
+                    // summed per sub-tile, fp64 across sub-tiles
+                    if (row_local < a.M) {
+#pragma unroll 1
+                        for (int cc = 0; cc < BN / 32; cc++) {
+                            if (tl.tn * BN + cc * 32 >= a.N) break;
+                            uint32_t r[32];
+                            tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * BN + cc * 32, r);
+                            if (row_local + lane < a.M) {
+                                const float* e = a.E + (long long)(crow + lane) * a.lde + ccol0 + cc * 32;
+                                const int ncol = min(32, a.N - (tl.tn * BN + cc * 32));
+                                float s4 = 0.f;
+                                if (ncol == 32) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) {
+                                        const float4 v = *reinterpret_cast<const float4*>(e + 4 * c);
+                                        s4 = fmaf(__uint_as_float(r[4 * c]), v.x, s4);
+                                        s4 = fmaf(__uint_as_float(r[4 * c + 1]), v.y, s4);
+                                        s4 = fmaf(__uint_as_float(r[4 * c + 2]), v.z, s4);
+                                        s4 = fmaf(__uint_as_float(r[4 * c + 3]), v.w, s4);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < 32; c++)
+                                        if (c < ncol) s4 = fmaf(__uint_as_float(r[c]), e[c], s4);
+                                }
+                                wsum += (double)s4;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tempty[acc]);
+                    continue;
+                }
                 // partial sums of one tile are applied in order: the previous flush must have completed
                 const bool first = (k0 == tl.kc0);
                 if (!first && lane == 0) bulk_wait<0>();
@@ -223,6 +265,11 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
             }
         }
         if (lane == 0) bulk_wait<0>();
+        if (a.E) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wsum += __shfl_down_sync(0xffffffffu, wsum, o);
+            if (lane == 0 && wsum != 0.0) atomicAdd(a.loss, wsum);
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -232,20 +279,26 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
 
 int launch(const Problem& p, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return QT_OK;
-    if (p.Kd <= 0 || (p.Kd % KC) || !p.A.hi || !p.A.lo || !p.B.hi || !p.B.lo || !p.C) return QT_ERR_INVALID;
+    if (p.Kd <= 0 || (p.Kd % KC) || !p.A.hi || !p.B.hi) return QT_ERR_INVALID;
+    if (!p.single && (!p.A.lo || !p.B.lo)) return QT_ERR_INVALID;
+    if (p.E ? (!p.loss || (p.lde & 3) || ((uintptr_t)p.E & 15) || p.batch != 1) : !p.C) return QT_ERR_INVALID;
     if (p.batch > 1 && ((p.M % BM) || (p.N % BN))) return QT_ERR_INVALID;
     if ((p.A.ld & 3) || (p.B.ld & 3) || (p.ldc & 3)) return QT_ERR_INVALID;
     const CUtensorMapDataType F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const CUtensorMapSwizzle SW = CU_TENSOR_MAP_SWIZZLE_128B;
     // stores / reduce-adds are clipped to the last batch's sub-block
     int crows = p.c_row0 + (p.batch - 1) * p.c_sr + p.M, ccols = p.c_col0 + (p.batch - 1) * p.c_sc + p.N;
-    if (crows > p.c_rows || ccols > p.c_cols) return QT_ERR_INVALID;
+    if (!p.E && (crows > p.c_rows || ccols > p.c_cols)) return QT_ERR_INVALID;
+    const float* a_lo = p.single ? p.A.hi : p.A.lo;      // unused maps still need a valid address
+    const float* b_lo = p.single ? p.B.hi : p.B.lo;
+    float* c_ptr = p.E ? const_cast<float*>(p.E) : p.C;
+    const uint64_t c_ld = p.E ? (uint64_t)p.lde : (uint64_t)p.ldc;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc;
     bool ok = make_map_2d(&ma_hi, F32, p.A.hi, p.A.cols, p.A.rows, (uint64_t)p.A.ld * 4, KC, BM, SW) &&
-              make_map_2d(&ma_lo, F32, p.A.lo, p.A.cols, p.A.rows, (uint64_t)p.A.ld * 4, KC, BM, SW) &&
+              make_map_2d(&ma_lo, F32, a_lo, p.A.cols, p.A.rows, (uint64_t)p.A.ld * 4, KC, BM, SW) &&
               make_map_2d(&mb_hi, F32, p.B.hi, p.B.cols, p.B.rows, (uint64_t)p.B.ld * 4, KC, BN, SW) &&
-              make_map_2d(&mb_lo, F32, p.B.lo, p.B.cols, p.B.rows, (uint64_t)p.B.ld * 4, KC, BN, SW) &&
-              make_map_2d(&mc, F32, p.C, ccols, crows, (uint64_t)p.ldc * 4, 32, 32, SW);
+              make_map_2d(&mb_lo, F32, b_lo, p.B.cols, p.B.rows, (uint64_t)p.B.ld * 4, KC, BN, SW) &&
+              make_map_2d(&mc, F32, c_ptr, ccols, crows, c_ld * 4, 32, 32, SW);
     if (!ok) { set_last_error("tgemm tensor maps", cudaErrorInvalidValue); return QT_ERR_CUDA; }
     static bool attr_set = false;
     if (!attr_set) {
@@ -265,6 +318,9 @@ int launch(const Problem& p, cudaStream_t st) {
     a.accumulate = p.accumulate; a.lower_only = p.lower_tiles_only; a.a_tri = p.a_tri; a.b_tri = p.b_tri;
     a.chain_kc = p.max_chain >= KC ? p.max_chain / KC : 1;
     a.idesc = p.negate ? make_idesc(true) : make_idesc(false);
+    a.single = p.single ? 1 : 0;
+    a.E = p.E; a.lde = p.lde; a.loss = p.loss;
+    if (p.E) a.chain_kc = a.kchunks;          // one chain per tile: every flush would re-read the E tile
     int dev = 0, nsm = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -294,6 +350,24 @@ int qt_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, cons
     p.M = M; p.N = N; p.Kd = Kd;
     p.negate = flags & 1; p.accumulate = (flags >> 1) & 1; p.lower_tiles_only = (flags >> 2) & 1;
     p.a_tri = (flags >> 4) & 3; p.b_tri = (flags >> 6) & 3;
+    return tgemm::launch(p, (cudaStream_t)stream);
+}
+
+// AWQ reconstruction loss of a single-Linear parent in Gram form (SURVEY.md B.3, section 7 hard part 6):
+//     *loss += sum_{m,n} (D G)[m][n] * D[m][n] = tr(D G D^T) = || X D^T ||_F^2     with G = X^T X (symmetric),
+// D = candidate weight - weight [M, K] fp32 (tf32-exact values), G [K, K] fp32 rounded to tf32.  One tf32 tcgen05
+// GEMM whose epilogue multiplies the accumulator tile by the D tile and reduces: neither the candidate output
+// [T, M] nor D G is ever written.  K % 32 == 0; pointers 16-byte aligned.
+int qt_awq_gram_loss(const float* D, const float* G, int M, int K, double* loss, void* stream) {
+    if (!D || !G || !loss || M <= 0 || K <= 0 || (K % 32)) return QT_ERR_INVALID;
+    if (((uintptr_t)D | (uintptr_t)G) & 15) return QT_ERR_INVALID;
+    tgemm::Problem p;
+    p.A = {D, nullptr, M, K, K};
+    p.B = {G, nullptr, K, K, K};
+    p.C = nullptr; p.c_rows = M; p.c_cols = K; p.ldc = K;
+    p.M = M; p.N = K; p.Kd = K;
+    p.single = true;
+    p.E = D; p.lde = K; p.loss = loss;
     return tgemm::launch(p, (cudaStream_t)stream);
 }
 

@@ -29,6 +29,13 @@ struct Problem {
     int a_tri = 0;                 // 1: A[m][k] = 0 for k > m (lower), 2: = 0 for k < m (upper) - k range is trimmed
     int b_tri = 0;                 // same for B[n][k]
     int max_chain = 128;           // longest k span accumulated in TMEM before the partial sum is flushed to C
+    // single-product mode: A.hi * B.hi only (plain tf32 GEMM, a third of the tensor work; lo pointers unused)
+    bool single = false;
+    // reduction epilogue (AWQ Gram-form loss): nothing is stored; *loss += sum_{m,n} acc[m][n] * E[c_row0+m][c_col0+n]
+    // (E row-major fp32, leading dimension lde; fp64 atomic per warp).  C is ignored.
+    const float* E = nullptr;
+    int lde = 0;
+    double* loss = nullptr;
 };
 
 // stream-ordered; returns QT_OK / negative error code
