@@ -172,6 +172,17 @@ int qt_awq_wmean_accumulate(const void* W, int dtype, int N, int K, int group_si
 /* out = pseudo_quantize(W * s) / s in one pass (AWQ grid-search candidate) */
 int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int group_size, int num_bits,
                      int symmetric, void* out, void* stream);
+/* Gram-form reconstruction loss for a single-Linear AWQ parent (o_proj / down_proj mappings; UPSTREAM AWQModifier
+ * _compute_loss on F.linear outputs, SURVEY.md B.3 and section 7 hard part 6):
+ *   || X D^T ||_F^2 = tr(D G D^T),  G = X^T X (qt_hessian_accumulate + qt_hessian_finalize(.., 1.0), cast to bf16),
+ *   D = pseudo_quant(W * s) / s - W.
+ * qt_awq_scale_qdq_delta writes D for one grid point (bf16 operand + fp32 copy, group_size 32 / 64 / 128);
+ * qt_awq_gram_loss runs ONE kind::f16 tcgen05 GEMM (D * G, fp32 in TMEM) whose epilogue multiplies by the fp32 D
+ * tile and reduces into *loss (device double, += ): neither the candidate output nor D*G is materialised. */
+int qt_awq_scale_qdq_delta(const void* W, int dtype, int N, int K, const float* s, int group_size, int num_bits,
+                           int symmetric, void* delta_bf16, float* delta_f32, void* stream);
+int qt_awq_gram_loss(const void* D_bf16, const float* D_f32, const void* G_bf16, int M, int K, double* loss, void* stream);
+
 /* *out (device double) += sum (a-b)^2 */
 int qt_sq_err_sum(const void* a, const void* b, int dtype, int64_t n, double* out, void* stream);
 

@@ -65,6 +65,8 @@ _SIGS = {
     "qt_awq_wmean_accumulate": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "qt_awq_scale_qdq": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp],
     "qt_sq_err_sum": [_vp, _vp, _i32, _i64, _vp, _vp],
+    "qt_awq_scale_qdq_delta": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
+    "qt_awq_gram_loss": [_vp, _vp, _vp, _i32, _i32, _vp, _vp],
     "qt_gptq_quantize_weight": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "qt_gptq_set_block_kernel": [_i32],
     "qt_split_tf32": [_vp, _vp, _vp, _i64, _vp],
@@ -629,6 +631,33 @@ def awq_scale_qdq(w: torch.Tensor, s: torch.Tensor, group_size: int, num_bits: i
         _check(lib().qt_awq_scale_qdq(_p(w), _DT[w.dtype], N, K, _p(s), max(group_size or 0, 0), num_bits,
                                       int(symmetric), _p(out), _stream()), "qt_awq_scale_qdq")
     return out
+
+
+def awq_scale_qdq_delta(w: torch.Tensor, s: torch.Tensor, group_size: int, num_bits: int, symmetric: bool,
+                        d_bf16: torch.Tensor, d_f32: torch.Tensor) -> None:
+    """D = pseudo_quant(W * s) / s - W as bf16 (MMA operand) and fp32 (epilogue operand) for `awq_gram_loss`."""
+    _dev(w, "w"); _dev(s, "s"); _dev(d_bf16, "d_bf16"); _dev(d_f32, "d_f32")
+    assert s.dtype == torch.float32 and d_bf16.dtype == torch.bfloat16 and d_f32.dtype == torch.float32
+    assert d_bf16.shape == w.shape and d_f32.shape == w.shape
+    N, K = w.shape
+    with torch.cuda.device(w.device):
+        _check(lib().qt_awq_scale_qdq_delta(_p(w), _DT[w.dtype], N, K, _p(s), int(group_size), num_bits, int(symmetric),
+                                            _p(d_bf16), _p(d_f32), _stream()), "qt_awq_scale_qdq_delta")
+
+
+def awq_gram_loss(d_bf16: torch.Tensor, d_f32: torch.Tensor, g_bf16: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc (device float64 scalar) += tr(D G D^T) = ||X D^T||_F^2 with G = X^T X: one tcgen05 GEMM with a reducing
+    epilogue (nothing is written but the scalar)."""
+    _dev(d_bf16, "d_bf16"); _dev(d_f32, "d_f32"); _dev(g_bf16, "g_bf16")
+    M, K = d_bf16.shape
+    assert g_bf16.shape == (K, K) and g_bf16.dtype == torch.bfloat16 and acc.dtype == torch.float64
+    with torch.cuda.device(d_bf16.device):
+        _check(lib().qt_awq_gram_loss(_p(d_bf16), _p(d_f32), _p(g_bf16), M, K, _p(acc), _stream()), "qt_awq_gram_loss")
+
+
+def awq_gram_ok(K: int, group_size: int) -> bool:
+    """Shapes the Gram-form loss kernel takes (K-major bf16 tiles of 64, 16-column lanes)."""
+    return K % 64 == 0 and group_size in (32, 64, 128)
 
 
 def sq_err_sum(a: torch.Tensor, b: torch.Tensor, acc: torch.Tensor) -> None:

@@ -172,6 +172,148 @@ __global__ void __launch_bounds__(256) scale_qdq_kernel(const void* __restrict__
     }
 }
 
+// Same arithmetic, group_size 32 / 64 / 128: LPG = group_size / 16 consecutive lanes share a group and every lane owns
+// 16 consecutive columns (two 128-bit loads of a 16-bit row), so a warp works on 32 / LPG groups at once with 16
+// independent elements per lane - the one-group-per-warp form above is bound by the latency of its serial
+// min/max -> divide -> divide chain (12 % of HBM peak, ncu issue 78 %).
+// DELTA: instead of the candidate weight, write D = candidate - W (exact in fp32) as bf16 (the MMA operand of the
+// Gram-form loss) and as fp32 (its epilogue operand).
+template <int DT>
+QT_D void ld16(const void* p, long long i, float v[16]) {
+    if (DT == QT_F32) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 a = *reinterpret_cast<const float4*>((const float*)p + i + 4 * q);
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const uint4 a = *reinterpret_cast<const uint4*>((const char*)p + (i + 8 * q) * 2);
+            const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (DT == QT_F16) {
+                    v[8 * q + 2 * t] = f16_bits_to_float(u[t] & 0xffffu);
+                    v[8 * q + 2 * t + 1] = f16_bits_to_float(u[t] >> 16);
+                } else {
+                    v[8 * q + 2 * t] = __uint_as_float(u[t] << 16);
+                    v[8 * q + 2 * t + 1] = __uint_as_float(u[t] & 0xffff0000u);
+                }
+            }
+        }
+    }
+}
+template <int DT>
+QT_D void st16(void* p, long long i, const float v[16]) {
+    if (DT == QT_F32) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            *reinterpret_cast<float4*>((float*)p + i + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            uint32_t u[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (DT == QT_F16) {
+                    u[t] = (uint32_t)__half_as_ushort(__float2half_rn(v[8 * q + 2 * t])) |
+                           ((uint32_t)__half_as_ushort(__float2half_rn(v[8 * q + 2 * t + 1])) << 16);
+                } else {
+                    u[t] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[8 * q + 2 * t])) |
+                           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[8 * q + 2 * t + 1])) << 16);
+                }
+            }
+            *reinterpret_cast<uint4*>((char*)p + (i + 8 * q) * 2) = make_uint4(u[0], u[1], u[2], u[3]);
+        }
+    }
+}
+
+template <int DT, int LPG, bool DELTA>
+__global__ void __launch_bounds__(256) scale_qdq16_kernel(const void* __restrict__ W, const float* __restrict__ s, int N,
+                                                          int K, int num_bits, int symmetric, void* __restrict__ out,
+                                                          float* __restrict__ delta_f32) {
+    const float max_int_s = (float)((1 << (num_bits - 1)) - 1), min_int_s = -(float)(1 << (num_bits - 1));
+    const float max_int_a = (float)((1 << num_bits) - 1);
+    const int cpr = K >> 4;                                   // 16-column chunks per row (a multiple of LPG)
+    const long long total = (long long)N * cpr;
+    for (long long base = (long long)blockIdx.x * 256; base < total; base += (long long)gridDim.x * 256) {
+        const long long ch = base + threadIdx.x;
+        const bool valid = ch < total;                        // whole groups are valid or not (total % LPG == 0)
+        const long long chc = valid ? ch : total - 1;
+        const long long row = chc / cpr;
+        const int c0 = (int)(chc - row * cpr) << 4;
+        const long long idx = row * K + c0;
+        float w[16], ks[16], keep[16];
+        ld16<DT>(W, idx, w);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 a = *reinterpret_cast<const float4*>(s + c0 + 4 * q);
+            ks[4 * q] = a.x; ks[4 * q + 1] = a.y; ks[4 * q + 2] = a.z; ks[4 * q + 3] = a.w;
+        }
+        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            keep[i] = rnd<DT>(w[i] * ks[i]);
+            mn = fminf(mn, keep[i]);
+            mx = fmaxf(mx, keep[i]);
+        }
+#pragma unroll
+        for (int o = LPG / 2; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        float sc, z = 0.f;
+        if (symmetric) {
+            const float max_val = fmaxf(fmaxf(fabsf(mn), fabsf(mx)), rnd<DT>(1e-5f));
+            sc = rnd<DT>(max_val / max_int_s);
+        } else {
+            sc = rnd<DT>(fmaxf(rnd<DT>(mx - mn), rnd<DT>(1e-5f)) / max_int_a);
+            z = -rintf(rnd<DT>(mn / sc));
+            z = fminf(fmaxf(z, 0.f), max_int_a);
+        }
+        float o16[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            float dq;
+            if (symmetric) {
+                float q = rintf(rnd<DT>(keep[i] / sc));
+                q = fminf(fmaxf(q, min_int_s), max_int_s);
+                dq = rnd<DT>(q * sc);
+            } else {
+                float q = rnd<DT>(rintf(rnd<DT>(keep[i] / sc)) + z);
+                q = fminf(fmaxf(q, 0.f), max_int_a);
+                dq = rnd<DT>(rnd<DT>(q - z) * sc);
+            }
+            o16[i] = dq / ks[i];
+        }
+        if (!valid) continue;
+        if (DELTA) {
+            float d[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) d[i] = rnd<DT>(o16[i]) - w[i];
+            st16<QT_BF16>(out, idx, d);
+            st16<QT_F32>(delta_f32, idx, d);
+        } else {
+            st16<DT>(out, idx, o16);
+        }
+    }
+}
+
+template <int DT, bool DELTA>
+static int launch_qdq16(const void* W, const float* s, int N, int K, int gs, int num_bits, int symmetric, void* out,
+                        float* delta_f32, cudaStream_t st) {
+    const long long total = (long long)N * (K >> 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    const unsigned g = (unsigned)blocks;
+    if (gs == 128) scale_qdq16_kernel<DT, 8, DELTA><<<g, 256, 0, st>>>(W, s, N, K, num_bits, symmetric, out, delta_f32);
+    else if (gs == 64) scale_qdq16_kernel<DT, 4, DELTA><<<g, 256, 0, st>>>(W, s, N, K, num_bits, symmetric, out, delta_f32);
+    else scale_qdq16_kernel<DT, 2, DELTA><<<g, 256, 0, st>>>(W, s, N, K, num_bits, symmetric, out, delta_f32);
+    return check_launch("awq_scale_qdq16");
+}
+
 // sum over i of rnd(a[i] - b[i])^2 ; fp32 per-thread partials, fp64 block total -> atomicAdd(double)
 template <int DT>
 __global__ void __launch_bounds__(256) sq_err_kernel(const void* __restrict__ a, const void* __restrict__ b,
@@ -233,6 +375,14 @@ int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int
     const int gs = group_size > 0 ? group_size : K;
     if (K % gs || (gs & 3) || (K & 3) || ((uintptr_t)W & 15) || ((uintptr_t)out & 15) || ((uintptr_t)s & 15)) return QT_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((gs == 32 || gs == 64 || gs == 128) && !(K & 15)) {
+        switch (dtype) {
+            case QT_F32: return launch_qdq16<QT_F32, false>(W, s, N, K, gs, num_bits, symmetric, out, nullptr, st);
+            case QT_F16: return launch_qdq16<QT_F16, false>(W, s, N, K, gs, num_bits, symmetric, out, nullptr, st);
+            case QT_BF16: return launch_qdq16<QT_BF16, false>(W, s, N, K, gs, num_bits, symmetric, out, nullptr, st);
+            default: return QT_ERR_INVALID;
+        }
+    }
     const int grid = (N + 7) / 8;
     switch (dtype) {
         case QT_F32: scale_qdq_kernel<QT_F32><<<grid, 256, 0, st>>>(W, s, N, K, gs, num_bits, symmetric, out); break;
@@ -241,6 +391,23 @@ int qt_awq_scale_qdq(const void* W, int dtype, int N, int K, const float* s, int
         default: return QT_ERR_INVALID;
     }
     return check_launch("awq_scale_qdq");
+}
+
+// D = pseudo_quant(W * s) / s - W for the Gram-form loss of a single-Linear parent (qt_awq_gram_loss): the same
+// candidate weight as qt_awq_scale_qdq (rounded to the weight's dtype, as torch would hold it), minus W, written as
+// bf16 [N, K] (delta_bf16) and fp32 [N, K] (delta_f32).  group_size 32 / 64 / 128 only.
+int qt_awq_scale_qdq_delta(const void* W, int dtype, int N, int K, const float* s, int group_size, int num_bits,
+                           int symmetric, void* delta_bf16, float* delta_f32, void* stream) {
+    if (!W || !s || !delta_bf16 || !delta_f32 || N <= 0 || K <= 0 || num_bits < 2 || num_bits > 8) return QT_ERR_INVALID;
+    if (!(group_size == 32 || group_size == 64 || group_size == 128) || (K % group_size)) return QT_ERR_UNSUPPORTED;
+    if (((uintptr_t)W | (uintptr_t)delta_bf16 | (uintptr_t)delta_f32 | (uintptr_t)s) & 15) return QT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case QT_F32: return launch_qdq16<QT_F32, true>(W, s, N, K, group_size, num_bits, symmetric, delta_bf16, delta_f32, st);
+        case QT_F16: return launch_qdq16<QT_F16, true>(W, s, N, K, group_size, num_bits, symmetric, delta_bf16, delta_f32, st);
+        case QT_BF16: return launch_qdq16<QT_BF16, true>(W, s, N, K, group_size, num_bits, symmetric, delta_bf16, delta_f32, st);
+        default: return QT_ERR_INVALID;
+    }
 }
 
 // *out (device double, zeroed by the caller) += sum (a - b)^2 over n elements

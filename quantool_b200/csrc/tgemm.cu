@@ -56,6 +56,8 @@ struct Args {
     int chain_kc;   // k chunks accumulated in TMEM before the partial sum is flushed to C (see Problem::max_chain)
     uint32_t idesc;
     int single;     // hi * hi only
+    int bf16;       // operands are bf16 (kind::f16), k chunk = 64 elements
+    int kce;        // elements per k chunk (one 128-byte swizzle row): 32 fp32 or 64 bf16
     const float* E; // reduction epilogue (see Problem::E)
     long long lde;
     double* loss;
@@ -73,13 +75,14 @@ QT_D bool decode(const Args& a, int t, Tile& o) {
     o.tn = r / a.m_tiles;       // n-major: consecutive CTAs share the same B rows (L2 reuse)
     o.tm = r - o.tn * a.m_tiles;
     if (a.lower_only && o.tn * BN > o.tm * BM + BM - 1) return false;
-    int k0 = 0, k1 = a.kchunks * KC;
+    const int KCe = a.kce;
+    int k0 = 0, k1 = a.kchunks * KCe;
     if (a.a_tri == 1) k1 = min(k1, o.tm * BM + BM);
     if (a.a_tri == 2) k0 = max(k0, o.tm * BM);
     if (a.b_tri == 1) k1 = min(k1, o.tn * BN + BN);
     if (a.b_tri == 2) k0 = max(k0, o.tn * BN);
-    o.kc0 = k0 / KC;
-    o.kc1 = (k1 + KC - 1) / KC;
+    o.kc0 = k0 / KCe;
+    o.kc1 = (k1 + KCe - 1) / KCe;
     return o.kc1 > o.kc0;
 }
 
@@ -132,10 +135,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
                     mbar_wait(&empty[stage], ph ^ 1);
                     mbar_expect_tx(&full[stage], a.single ? A_BYTES + B_BYTES : STAGE_BYTES);
                     uint8_t* s = smem + stage * STAGE_BYTES;
-                    tma_load_2d(s, &map_ahi, &full[stage], ca + kc * KC, ra);
-                    if (!a.single) tma_load_2d(s + A_BYTES, &map_alo, &full[stage], ca + kc * KC, ra);
-                    tma_load_2d(s + 2 * A_BYTES, &map_bhi, &full[stage], cb + kc * KC, rb);
-                    if (!a.single) tma_load_2d(s + 2 * A_BYTES + B_BYTES, &map_blo, &full[stage], cb + kc * KC, rb);
+                    tma_load_2d(s, &map_ahi, &full[stage], ca + kc * a.kce, ra);
+                    if (!a.single) tma_load_2d(s + A_BYTES, &map_alo, &full[stage], ca + kc * a.kce, ra);
+                    tma_load_2d(s + 2 * A_BYTES, &map_bhi, &full[stage], cb + kc * a.kce, rb);
+                    if (!a.single) tma_load_2d(s + 2 * A_BYTES + B_BYTES, &map_blo, &full[stage], cb + kc * a.kce, rb);
                 }
             }
         }
@@ -167,6 +170,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
                             const uint64_t alo = make_desc_sw128(sa_lo + k * UMMA_K * 4, 16, 1024);
                             const uint64_t bhi = make_desc_sw128(sb_hi + k * UMMA_K * 4, 16, 1024);
                             const uint64_t blo = make_desc_sw128(sb_lo + k * UMMA_K * 4, 16, 1024);
+                            if (a.bf16) {          // 32 bytes per step either way: 8 tf32 or 16 bf16
+                                tc_mma_bf16(d_tmem, ahi, bhi, a.idesc, (kc > k0 || k > 0) ? 1u : 0u);
+                                continue;
+                            }
                             tc_mma_tf32(d_tmem, ahi, bhi, a.idesc, (kc > k0 || k > 0) ? 1u : 0u);
                             if (!a.single) {
                                 tc_mma_tf32(d_tmem, ahi, blo, a.idesc, 1u);
@@ -279,12 +286,16 @@ tgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant_
 
 int launch(const Problem& p, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return QT_OK;
-    if (p.Kd <= 0 || (p.Kd % KC) || !p.A.hi || !p.B.hi) return QT_ERR_INVALID;
+    const int kce = p.bf16 ? 2 * KC : KC;
+    const int esz = p.bf16 ? 2 : 4;
+    if (p.bf16 && !p.single) return QT_ERR_INVALID;
+    if (p.Kd <= 0 || (p.Kd % kce) || !p.A.hi || !p.B.hi) return QT_ERR_INVALID;
     if (!p.single && (!p.A.lo || !p.B.lo)) return QT_ERR_INVALID;
     if (p.E ? (!p.loss || (p.lde & 3) || ((uintptr_t)p.E & 15) || p.batch != 1) : !p.C) return QT_ERR_INVALID;
     if (p.batch > 1 && ((p.M % BM) || (p.N % BN))) return QT_ERR_INVALID;
-    if ((p.A.ld & 3) || (p.B.ld & 3) || (p.ldc & 3)) return QT_ERR_INVALID;
+    if ((p.A.ld & (p.bf16 ? 7 : 3)) || (p.B.ld & (p.bf16 ? 7 : 3)) || (!p.E && (p.ldc & 3))) return QT_ERR_INVALID;
     const CUtensorMapDataType F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapDataType OPT = p.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : F32;
     const CUtensorMapSwizzle SW = CU_TENSOR_MAP_SWIZZLE_128B;
     // stores / reduce-adds are clipped to the last batch's sub-block
     int crows = p.c_row0 + (p.batch - 1) * p.c_sr + p.M, ccols = p.c_col0 + (p.batch - 1) * p.c_sc + p.N;
@@ -294,10 +305,10 @@ int launch(const Problem& p, cudaStream_t st) {
     float* c_ptr = p.E ? const_cast<float*>(p.E) : p.C;
     const uint64_t c_ld = p.E ? (uint64_t)p.lde : (uint64_t)p.ldc;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mc;
-    bool ok = make_map_2d(&ma_hi, F32, p.A.hi, p.A.cols, p.A.rows, (uint64_t)p.A.ld * 4, KC, BM, SW) &&
-              make_map_2d(&ma_lo, F32, a_lo, p.A.cols, p.A.rows, (uint64_t)p.A.ld * 4, KC, BM, SW) &&
-              make_map_2d(&mb_hi, F32, p.B.hi, p.B.cols, p.B.rows, (uint64_t)p.B.ld * 4, KC, BN, SW) &&
-              make_map_2d(&mb_lo, F32, b_lo, p.B.cols, p.B.rows, (uint64_t)p.B.ld * 4, KC, BN, SW) &&
+    bool ok = make_map_2d(&ma_hi, OPT, p.A.hi, p.A.cols, p.A.rows, (uint64_t)p.A.ld * esz, kce, BM, SW) &&
+              make_map_2d(&ma_lo, OPT, a_lo, p.A.cols, p.A.rows, (uint64_t)p.A.ld * esz, kce, BM, SW) &&
+              make_map_2d(&mb_hi, OPT, p.B.hi, p.B.cols, p.B.rows, (uint64_t)p.B.ld * esz, kce, BN, SW) &&
+              make_map_2d(&mb_lo, OPT, b_lo, p.B.cols, p.B.rows, (uint64_t)p.B.ld * esz, kce, BN, SW) &&
               make_map_2d(&mc, F32, c_ptr, ccols, crows, c_ld * 4, 32, 32, SW);
     if (!ok) { set_last_error("tgemm tensor maps", cudaErrorInvalidValue); return QT_ERR_CUDA; }
     static bool attr_set = false;
@@ -310,14 +321,17 @@ int launch(const Problem& p, cudaStream_t st) {
     a.m_tiles = (p.M + BM - 1) / BM;
     a.n_tiles = (p.N + BN - 1) / BN;
     a.batch = p.batch;
-    a.kchunks = p.Kd / KC;
+    a.kchunks = p.Kd / kce;
+    a.kce = kce; a.bf16 = p.bf16 ? 1 : 0;
     a.M = p.M; a.N = p.N;
     a.a_row0 = p.a_row0; a.a_col0 = p.a_col0; a.b_row0 = p.b_row0; a.b_col0 = p.b_col0;
     a.c_row0 = p.c_row0; a.c_col0 = p.c_col0;
     a.a_sr = p.a_sr; a.a_sc = p.a_sc; a.b_sr = p.b_sr; a.b_sc = p.b_sc; a.c_sr = p.c_sr; a.c_sc = p.c_sc;
     a.accumulate = p.accumulate; a.lower_only = p.lower_tiles_only; a.a_tri = p.a_tri; a.b_tri = p.b_tri;
-    a.chain_kc = p.max_chain >= KC ? p.max_chain / KC : 1;
+    a.chain_kc = p.max_chain >= kce ? p.max_chain / kce : 1;
     a.idesc = p.negate ? make_idesc(true) : make_idesc(false);
+    // kind::f16 with bf16 operands: format 1 at bits 7 and 10 instead of tf32's 2
+    if (p.bf16) a.idesc = (a.idesc & ~((7u << 7) | (7u << 10))) | (1u << 7) | (1u << 10);
     a.single = p.single ? 1 : 0;
     a.E = p.E; a.lde = p.lde; a.loss = p.loss;
     if (p.E) a.chain_kc = a.kchunks;          // one chain per tile: every flush would re-read the E tile
@@ -354,20 +368,20 @@ int qt_gemm_tf32x3(const float* a_hi, const float* a_lo, const float* b_hi, cons
 }
 
 // AWQ reconstruction loss of a single-Linear parent in Gram form (SURVEY.md B.3, section 7 hard part 6):
-//     *loss += sum_{m,n} (D G)[m][n] * D[m][n] = tr(D G D^T) = || X D^T ||_F^2     with G = X^T X (symmetric),
-// D = candidate weight - weight [M, K] fp32 (tf32-exact values), G [K, K] fp32 rounded to tf32.  One tf32 tcgen05
-// GEMM whose epilogue multiplies the accumulator tile by the D tile and reduces: neither the candidate output
-// [T, M] nor D G is ever written.  K % 32 == 0; pointers 16-byte aligned.
-int qt_awq_gram_loss(const float* D, const float* G, int M, int K, double* loss, void* stream) {
-    if (!D || !G || !loss || M <= 0 || K <= 0 || (K % 32)) return QT_ERR_INVALID;
-    if (((uintptr_t)D | (uintptr_t)G) & 15) return QT_ERR_INVALID;
+//     *loss += sum_{m,n} (D G)[m][n] * E[m][n] = tr(D G D^T) = || X D^T ||_F^2     with G = X^T X (symmetric),
+// D = candidate weight - weight [M, K] as bf16 (the MMA operand), E the same matrix in fp32, G [K, K] bf16.  One
+// kind::f16 tcgen05 GEMM (fp32 accumulation in TMEM) whose epilogue multiplies the accumulator tile by the E tile
+// and reduces: neither the candidate output [T, M] nor D G is ever written.  K % 64 == 0; 16-byte aligned.
+int qt_awq_gram_loss(const void* D_bf16, const float* E, const void* G_bf16, int M, int K, double* loss, void* stream) {
+    if (!D_bf16 || !E || !G_bf16 || !loss || M <= 0 || K <= 0 || (K % 64)) return QT_ERR_INVALID;
+    if (((uintptr_t)D_bf16 | (uintptr_t)G_bf16 | (uintptr_t)E) & 15) return QT_ERR_INVALID;
     tgemm::Problem p;
-    p.A = {D, nullptr, M, K, K};
-    p.B = {G, nullptr, K, K, K};
+    p.A = {reinterpret_cast<const float*>(D_bf16), nullptr, M, K, K};
+    p.B = {reinterpret_cast<const float*>(G_bf16), nullptr, K, K, K};
     p.C = nullptr; p.c_rows = M; p.c_cols = K; p.ldc = K;
     p.M = M; p.N = K; p.Kd = K;
-    p.single = true;
-    p.E = D; p.lde = K; p.loss = loss;
+    p.single = true; p.bf16 = true;
+    p.E = E; p.lde = K; p.loss = loss;
     return tgemm::launch(p, (cudaStream_t)stream);
 }
 

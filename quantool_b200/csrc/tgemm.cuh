@@ -31,6 +31,9 @@ struct Problem {
     int max_chain = 128;           // longest k span accumulated in TMEM before the partial sum is flushed to C
     // single-product mode: A.hi * B.hi only (plain tf32 GEMM, a third of the tensor work; lo pointers unused)
     bool single = false;
+    // bf16 operands (implies single): A.hi / B.hi point at __nv_bfloat16 arrays, ld / cols in elements; kind::f16,
+    // fp32 accumulation.  Kd % 64 == 0.
+    bool bf16 = false;
     // reduction epilogue (AWQ Gram-form loss): nothing is stored; *loss += sum_{m,n} acc[m][n] * E[c_row0+m][c_col0+n]
     // (E row-major fp32, leading dimension lde; fp64 atomic per warp).  C is ignored.
     const float* E = nullptr;

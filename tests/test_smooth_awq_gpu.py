@@ -181,3 +181,33 @@ def test_model_pipeline_vs_oracle(method):
                 # (W8A8 after smoothing: the int8 step is as small as one bf16 ulp of the smoothed weight, so
                 #  a bf16 flip in a smoothing scale shows up in this error)
                 assert abs(e_c - e_o) <= (0.08 if method == "gptq" else 0.2) * e_o, (key, e_c, e_o)
+
+
+@pytest.mark.parametrize("N,K,T,gs", [(256, 1024, 4096, 128), (96, 512, 1000, 64), (130, 2048, 2048, 32)])
+def test_awq_gram_loss_equals_forward_loss(N, K, T, gs):
+    """Single-Linear AWQ parent: tr(D G D^T) from the tensor-core GEMM with the reducing epilogue equals
+    ||X D^T||_F^2 computed directly in fp64 (bf16 operands of the MMA: 3e-3), and the candidate weight behind D
+    is bit-identical to the one `awq_scale_qdq` produces."""
+    from quantool_b200 import cabi
+    g = torch.Generator().manual_seed(N + K)
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16).cuda()
+    x = torch.randn((T, K), generator=g)
+    x[:, ::97] *= 8.0
+    x = x.to(torch.bfloat16).cuda()
+    s = (torch.rand((K,), generator=g) + 0.5).cuda()
+    cand = cabi.awq_scale_qdq(W, s, gs, 4, True)
+    d16 = torch.empty((N, K), dtype=torch.bfloat16, device="cuda")
+    d32 = torch.empty((N, K), dtype=torch.float32, device="cuda")
+    cabi.awq_scale_qdq_delta(W, s, gs, 4, True, d16, d32)
+    assert torch.equal(d32, cand.float() - W.float())
+    assert torch.equal(d16, d32.to(torch.bfloat16))
+    H = torch.zeros((K, K), dtype=torch.float32, device="cuda")
+    cabi.hessian_accumulate(x[: (T // 8) * 8].contiguous(), H)
+    cabi.hessian_finalize(H, 1.0)
+    xe = x[: (T // 8) * 8]
+    acc = torch.zeros((2,), dtype=torch.float64, device="cuda")
+    cabi.awq_gram_loss(d16, d32, H.to(torch.bfloat16), acc[0:1])
+    ref = ((xe.double() @ d32.double().t()) ** 2).sum().item()
+    got = acc[0].item()
+    assert abs(got - ref) <= 3e-3 * ref, (got, ref)
+    assert acc[1].item() == 0.0
