@@ -238,6 +238,29 @@ def layer_forward(shape: LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor
     return h + F.linear(d, w["mlp.down_proj.weight"])
 
 
+def layer_forward_pre_down(shape: LlamaShape, w: Dict[str, torch.Tensor], h: torch.Tensor, cos, sin,
+                           d_out: torch.Tensor) -> torch.Tensor:
+    """The layer up to (not including) down_proj: returns the post-attention residual [B, S, hidden] and writes
+    silu(gate) * up into d_out [B*S, intermediate].  Same ops, same rounding points as `layer_forward`."""
+    B, S, _ = h.shape
+    x = rms_norm(h, w["input_layernorm.weight"], shape.rms_norm_eps)
+    q, k, v = _qkv_rope(shape, w, x, cos, sin)
+    a = _attend(shape, q, k, v)
+    del q, k, v
+    h = h + F.linear(a, w["self_attn.o_proj.weight"])
+    x = rms_norm(h, w["post_attention_layernorm.weight"], shape.rms_norm_eps)
+    g = F.linear(x, w["mlp.gate_proj.weight"])
+    u = F.linear(x, w["mlp.up_proj.weight"])
+    cabi.silu_mul(g, u, out=d_out.view(B, S, d_out.shape[1]))
+    return h
+
+
+def layer_forward_down(w: Dict[str, torch.Tensor], h: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+    """h [T, hidden] (post-attention residual) + down_proj(d), d [T, intermediate]: the product is rounded to the
+    model dtype before the residual add, as in `layer_forward`."""
+    return h + F.linear(d, w["mlp.down_proj.weight"])
+
+
 def attention_forward(shape: LlamaShape, w: Dict[str, torch.Tensor], x: torch.Tensor, cos, sin) -> torch.Tensor:
     """self_attn(x) on normed input x [B,S,hidden] -> [B,S,hidden] (AWQ parent module of q/k/v)."""
     q, k, v = _qkv_rope(shape, w, x, cos, sin)

@@ -59,10 +59,10 @@ class Dist:
                     Dist._lanes[j] = self.dist.new_group(ranks=list(range(self.world)))
         return Dist(True, group=Dist._lanes[i])
 
-    def all_reduce_sum(self, t, async_op: bool = False):
+    def all_reduce_sum(self, t):
         if self.on:
-            return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group, async_op=async_op)
-        return None if async_op else t
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
 
     def all_reduce_max(self, t):
         if self.on:
@@ -188,6 +188,28 @@ class CalibSet:
         for gi, a, b in self.chunks(max_tokens):
             cos, sin = self.ropes[gi]
             self.groups[gi][a:b] = llama.layer_forward(shape, w, self.groups[gi][a:b], cos, sin)
+
+    def propagate_pre_down(self, shape, w, max_tokens: int, dbuf: torch.Tensor, hbuf: torch.Tensor) -> None:
+        """First part of the propagation pass: hbuf <- post-attention residual, dbuf <- down_proj inputs (both
+        token-major, chunk after chunk).  Needs every Linear of the layer except down_proj; the hidden states
+        themselves stay untouched, so the part can be redone."""
+        row0 = 0
+        for gi, a, b in self.chunks(max_tokens):
+            cos, sin = self.ropes[gi]
+            hb = self.groups[gi][a:b]
+            n = hb.shape[0] * hb.shape[1]
+            hm = llama.layer_forward_pre_down(shape, w, hb, cos, sin, dbuf[row0: row0 + n])
+            hbuf[row0: row0 + n].copy_(hm.view(n, -1))
+            row0 += n
+
+    def propagate_down(self, w, max_tokens: int, dbuf: torch.Tensor, hbuf: torch.Tensor) -> None:
+        """Second part: hidden states <- hbuf + down_proj(dbuf)."""
+        row0 = 0
+        for gi, a, b in self.chunks(max_tokens):
+            hb = self.groups[gi][a:b]
+            n = hb.shape[0] * hb.shape[1]
+            hb.copy_(llama.layer_forward_down(w, hbuf[row0: row0 + n], dbuf[row0: row0 + n]).view(hb.shape))
+            row0 += n
 
 
 def row_split(n: int, world: int, align: int = 1) -> List[int]:
@@ -448,11 +470,14 @@ class GPTQLayerQuantizer:
     # ---- one decoder layer from ready-made activations ----------------------------------
     def quantize_layer(self, weights: Dict[str, torch.Tensor], hessians: Optional[Dict[str, torch.Tensor]],
                        linears=llama.LINEARS, input_of=llama.INPUT_OF, accs=None, n_total: Optional[int] = None,
-                       acc_events=None) -> Dict[str, LinearResult]:
+                       acc_events=None, defer: bool = False):
         """hessians: finalized H per distinct input name - or `accs`: name -> HessianAccumulator holding this rank's
         raw sums (then the cross-rank reduction and the 2/n scaling happen here, on the input's own stream and
         communicator lane, so the all-reduce of one input runs underneath the other inputs' kernels;
-        acc_events[name] = CUDA event after which accs[name] is complete).  Returns per-Linear results.
+        acc_events[name] = CUDA event after which accs[name] is complete).  Returns per-Linear results - or, with
+        `defer`, a `_PendingLayer`: everything is queued but nothing is joined, so the caller can make the current
+        stream wait for SOME inputs (`wait_inputs`), queue work that only needs their Linears (the propagation
+        pass through attention and gate/up) underneath the largest-K chain, and call `finish()` afterwards.
 
         The distinct inputs of a layer are independent, and the small-K inverse-factor chains are
         bound by the latency of their sequential pivots, not by throughput: each input runs on its
@@ -506,26 +531,60 @@ class GPTQLayerQuantizer:
             done.append(ev)
             for t in (Hin, *(weights[f"{l}.weight"] for l in linears if input_of[l] == inp)):
                 t.record_stream(st)
-        for ev in done:
-            main.wait_event(ev)
-        for r in out.values():
-            for t in (r.weight, r.scale, r.zero_point, r.loss):
-                t.record_stream(main)
-        infos = torch.cat([ctxs[n].info for n in names]).cpu()          # one sync per layer
-        for idx, inp in enumerate(names):
-            if int(infos[idx]) != 0:
-                ctx = ctxs[inp]
-                cabi.set_identity(ctx.U)
-                self.split_for_tensor_cores(ctx)
-                for lin in linears:
-                    if input_of[lin] == inp:
-                        out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx, d=self.dist.lane(idx))
-        return out
+        pending = _PendingLayer(self, weights, linears, input_of, names, ctxs, done, out, main)
+        if defer:
+            return pending
+        return pending.finish()
+
+    def _requantize_identity(self, ctx: InputContext, idx: int, weights, linears, input_of, inp, out) -> None:
+        cabi.set_identity(ctx.U)
+        self.split_for_tensor_cores(ctx)
+        for lin in linears:
+            if input_of[lin] == inp:
+                out[lin] = self.quantize_linear(weights[f"{lin}.weight"], ctx, d=self.dist.lane(idx))
 
     def _pack_scratch(self, K: int, dev, idx: int) -> torch.Tensor:
         """Staging buffer of the packed-triangle all-reduce: the chain's W workspace of the same slot (free until
         the chain starts, which is after the reduction)."""
         return self._buf(f"W#{idx}", (K, K), torch.float32, dev).reshape(-1)
+
+
+class _PendingLayer:
+    """A decoder layer whose per-input work is queued on the input streams but not joined yet."""
+
+    def __init__(self, lq, weights, linears, input_of, names, ctxs, events, out, main):
+        self.lq, self.weights, self.linears, self.input_of = lq, weights, linears, input_of
+        self.names, self.ctxs, self.events, self.out, self.main = names, ctxs, events, out, main
+        self.redone: List[str] = []      # inputs whose factorisation failed and were redone with Hinv = I
+
+    def linears_of(self, inp: str) -> List[str]:
+        return [lin for lin in self.linears if self.input_of[lin] == inp]
+
+    def wait_inputs(self, inputs) -> Dict[str, "LinearResult"]:
+        """Make the current stream wait for the named inputs only; returns the results of their Linears."""
+        got = {}
+        for idx, inp in enumerate(self.names):
+            if inp in inputs:
+                self.main.wait_event(self.events[idx])
+                for lin in self.linears_of(inp):
+                    r = self.out[lin]
+                    for t in (r.weight, r.scale, r.zero_point, r.loss):
+                        t.record_stream(self.main)
+                    got[lin] = r
+        return got
+
+    def finish(self) -> Dict[str, "LinearResult"]:
+        for ev in self.events:
+            self.main.wait_event(ev)
+        for r in self.out.values():
+            for t in (r.weight, r.scale, r.zero_point, r.loss):
+                t.record_stream(self.main)
+        infos = torch.cat([self.ctxs[n].info for n in self.names]).cpu()          # one sync per layer
+        for idx, inp in enumerate(self.names):
+            if int(infos[idx]) != 0:
+                self.lq._requantize_identity(self.ctxs[inp], idx, self.weights, self.linears, self.input_of, inp, self.out)
+                self.redone.append(inp)
+        return self.out
 
 
 def accumulate_layer_hessians(inputs: Dict[str, torch.Tensor], n_samples_local: int, n_samples_total: int,
@@ -764,7 +823,7 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
     losses = {}
     L = shape.num_hidden_layers
     chunk_tokens = max(1, chunk_samples) * max(calib.max_len, 1)
-    accs = cap = None
+    accs = cap = dbuf = hbuf = None
     for l in range(L):
         pre = f"model.layers.{l}."
         w = fetch.get(pre, f"model.layers.{l + 1}." if l + 1 < L else None)
@@ -789,24 +848,46 @@ def quantize_model_gptq(shape: llama.LlamaShape, host_sd: Dict[str, torch.Tensor
         lq.launches += len(dims)
         linears = tuple(lin for lin in llama.LINEARS if f"{pre}{lin}" not in skip and lin not in skip)
         # cross-rank reduction, 2/n scaling, chain and column loops: per input, on its own stream + NCCL lane
-        results = lq.quantize_layer(w, None, linears=linears, accs=accs, n_total=n_total)
+        pend = lq.quantize_layer(w, None, linears=linears, accs=accs, n_total=n_total, defer=True)
         if dist.rank == 0:
             for lin in llama.LINEARS:
                 if lin not in linears:                   # ignored module: stays dense in the artifact
                     sink.put(f"{pre}{lin}.weight", w[f"{lin}.weight"])
-        for lin, r in results.items():
-            w[f"{lin}.weight"] = r.weight
-            art, _codes = compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args, fmt=fmt)
-            lq.launches += 2
-            if dist.rank == 0:
-                for k, t in art.items():
-                    sink.put(f"{pre}{lin}.{k}", t)
-                losses[f"{pre}{lin}"] = r.loss
+
+        def emit(res):
+            for lin, r in res.items():
+                w[f"{lin}.weight"] = r.weight
+                art, _codes = compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args, fmt=fmt)
+                lq.launches += 2
+                if dist.rank == 0:
+                    for k, t in art.items():
+                        sink.put(f"{pre}{lin}.{k}", t)
+                    losses[f"{pre}{lin}"] = r.loss
+
+        # pass 2, first part: everything up to down_proj only needs q/k/v/o/gate/up - it runs underneath the chain
+        # and the column loop of the K = intermediate_size input (latency-bound kernels that leave most SMs idle)
+        early = [n for n in pend.names if n != "down_in"]
+        split = "down_in" in pend.names and bool(early)
+        if split:
+            emit(pend.wait_inputs(early))
+            if dbuf is None:
+                dbuf = torch.empty((calib.tokens_local, dims["down_in"]), dtype=hdt, device=dev)
+                hbuf = torch.empty((calib.tokens_local, shape.hidden_size), dtype=hdt, device=dev)
+            calib.propagate_pre_down(shape, w, chunk_tokens, dbuf, hbuf)
+        results = pend.finish()
+        redo = split and any(n in early for n in pend.redone)
+        emit({lin: r for lin, r in results.items()
+              if not split or redo or lin in pend.linears_of("down_in") or pend.input_of[lin] in pend.redone})
+        if redo:      # a failed factorisation (Hinv = I fallback) changed weights the first part already used
+            calib.propagate_pre_down(shape, w, chunk_tokens, dbuf, hbuf)
         if dist.rank == 0:
             for k in ("input_layernorm.weight", "post_attention_layernorm.weight"):
                 sink.put(pre + k, w[k])
-        # pass 2: propagate through the quantized layer
-        calib.propagate(shape, w, chunk_tokens)
+        # pass 2, rest: the down projection (or the whole layer when nothing could be split off)
+        if split:
+            calib.propagate_down(w, chunk_tokens, dbuf, hbuf)
+        else:
+            calib.propagate(shape, w, chunk_tokens)
         del w
         if progress:
             progress(l)

@@ -58,6 +58,25 @@ def _worker(rank, world, port, q):
         mn = torch.tensor([float(rank), -float(rank)])
         d.all_reduce_min(mn)
         assert mn.tolist() == [0.0, -float(world - 1)]
+        # 5. the Dist API contract the CUDA path relies on: reductions return their tensor, every lane is its own
+        #    process group (one NCCL communicator per concurrently processed input), equal row blocks are gathered
+        #    straight into the result, H / U move as plain collectives on CPU tensors
+        v = d.all_reduce_sum(torch.tensor([1.0 + rank]))
+        assert v is not None and v.tolist() == [sum(1.0 + r for r in range(world))]
+        l0, l1 = d.lane(0), d.lane(1)
+        assert l0.on and l1.on and l0.group is not None and l0.group is not l1.group
+        assert d.lane(1).group is l1.group                      # cached, created once
+        a = l0.all_reduce_sum(torch.tensor([float(rank)]))
+        b = l1.all_reduce_max(torch.tensor([float(rank)]))
+        assert a.tolist() == [float(sum(range(world)))] and b.tolist() == [float(world - 1)]
+        eq = l1.all_gather_rows(torch.full((2, 3), float(rank)), [2] * world)
+        assert eq.shape == (2 * world, 3) and eq[:, 0].tolist() == [float(r) for r in range(world) for _ in range(2)]
+        Hs = torch.full((4, 4), 1.0 + rank)
+        l0.all_reduce_hessian(Hs)
+        assert Hs[0, 0].item() == sum(1.0 + r for r in range(world))
+        Us = torch.full((4, 4), float(rank))
+        l1.broadcast_upper(Us, 1)
+        assert Us[0, 0].item() == 1.0
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
