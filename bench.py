@@ -455,13 +455,47 @@ def awq_block(a, shape, dev, d, hbm, peaks):
     return out
 
 
-def parity_block(shape, args, host_sd, token_ids, dev, d, sharded_result, n_samples):
-    """Every multi-GPU bench run doubles as a parity check: rank 0 re-runs decoder layer 0 of the e2e workload
-    UNSHARDED (all samples, all rows on one GPU) and compares its `weight_packed` with what the sharded run produced.
-    H differs between the two by fp32 summation order only, so this is a code-agreement fraction."""
+def parity_block(shape, args, host_sd, token_ids, dev, d, sharded_result, n_samples, seq):
+    """Every multi-GPU bench run doubles as a parity check.
+    A. Layer level at the workload's own shapes, IDENTICAL all-reduced H on both sides: `quantize_layer` with rows
+       sharded over the ranks (owner-computes chain on its NCCL lane, packed broadcast of U, gathered rows) must give
+       bit-identical `weight_packed` / `weight_scale` / `weight_g_idx` to the unsharded run of the same kernels.
+    B. Rank 0 re-runs decoder layer 0 of the e2e workload UNSHARDED and compares with what the sharded run produced:
+       H differs by fp32 summation order only.  Reported: summed GPTQ loss of layer 0 on both sides (the objective)
+       and the code agreement - which on random-init weights is low BY CONSTRUCTION with actorder=group: diag(H) is
+       nearly flat, so argsort(diag H) is decided by the last bits and every swap moves group boundaries."""
     import hashlib
     from quantool_b200.engine import llama, pipeline
+    from quantool_b200.engine.gptq import compress_linear
     out = {}
+    # ---- A
+    per = pipeline.row_split(min(n_samples, 16), d.world)
+    acts = {n: synth_acts(max(per[d.rank], 1) * seq, k, dev, 900 + i + 100 * d.rank)[: per[d.rank] * seq]
+            for i, (n, k) in enumerate(shape.input_dims().items())}
+    hess = pipeline.accumulate_layer_hessians(acts, per[d.rank], sum(per), d)
+    del acts
+    w = llama.random_layer_weights(shape, 0, dev)
+    lq_sh = pipeline.GPTQLayerQuantizer(args, dist=d)
+    res_sh = lq_sh.quantize_layer(w, hess)
+    lq_sh.drop_scratch()
+    lq_1 = pipeline.GPTQLayerQuantizer(args, dist=pipeline.Dist(enabled=False))
+    res_1 = lq_1.quantize_layer(w, hess)
+    lq_1.drop_scratch()
+    same = True
+    sha = hashlib.sha256()
+    for lin in llama.LINEARS:
+        a_sh, _ = compress_linear(res_sh[lin].weight, res_sh[lin].scale, res_sh[lin].zero_point, res_sh[lin].g_idx, args)
+        a_1, _ = compress_linear(res_1[lin].weight, res_1[lin].scale, res_1[lin].zero_point, res_1[lin].g_idx, args)
+        for k in a_1:
+            same = same and torch.equal(a_sh[k], a_1[k])
+        sha.update(a_sh["weight_packed"].cpu().numpy().tobytes())
+    flag = torch.tensor([int(same)], device=dev)
+    d.all_reduce_min(flag)
+    out["layer_identical_given_same_H"] = bool(flag.item())
+    out["layer_weight_packed_sha"] = sha.hexdigest()[:16]
+    del hess, res_sh, res_1, w
+    torch.cuda.empty_cache()
+    # ---- B
     if d.rank == 0:
         sha = hashlib.sha256()
         for k in sorted(sharded_result.tensors):
@@ -478,9 +512,15 @@ def parity_block(shape, args, host_sd, token_ids, dev, d, sharded_result, n_samp
                 for sft in range(0, 32, 4):
                     same += int((((p1 >> sft) & 15) == ((p2 >> sft) & 15)).sum())
                 tot += p1.numel() * 8
+        l_1 = sum(v for k, v in r1.losses.items())
+        l_sh = sum(v for k, v in sharded_result.losses.items() if k.startswith("model.layers.0."))
+        out["layer0_gptq_loss_sharded_vs_unsharded"] = [l_sh, l_1]
+        out["layer0_loss_rel_diff"] = abs(l_sh - l_1) / max(abs(l_1), 1e-30)
         out["code_agreement_layer0_vs_unsharded"] = same / max(tot, 1)
         out["note"] = ("world=1: the same path run twice (determinism check)" if d.world == 1 else
-                       f"{d.world} ranks (samples + rows sharded, NCCL all-reduce of H) vs one rank doing everything")
+                       f"{d.world} ranks (samples + rows sharded, NCCL all-reduce of H) vs one rank doing everything; "
+                       "random-init weights give a nearly flat diag(H), so with actorder=group the permutation - and with "
+                       "it the codes - follow the last bits of H: the loss and check A are the parity figures")
     if d.on:
         d.dist.barrier()
     return out
@@ -671,10 +711,12 @@ def main():
                "path": "quantool_b200.engine.pipeline.quantize_model_gptq (what GPTQ.quantize() runs): pinned host "
                        "weights + token ids -> layer forwards -> Hessians -> GPTQ -> packed host tensors"}
         try:
-            parity = parity_block(shape, args, host_sd, token_ids, dev, d, r, a.samples)
+            parity = parity_block(shape, args, host_sd, token_ids, dev, d, r, a.samples, a.seq)
             if e2e is not None and parity:
                 e2e["artifact_sha"] = parity.get("artifact_sha")
                 e2e["code_agreement"] = parity.get("code_agreement_layer0_vs_unsharded")
+                e2e["layer_identical_given_same_H"] = parity.get("layer_identical_given_same_H")
+                e2e["layer0_loss_rel_diff"] = parity.get("layer0_loss_rel_diff")
         except Exception as ex:
             parity = {"error": repr(ex)[:300]}
         del host_sd, r

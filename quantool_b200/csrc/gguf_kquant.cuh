@@ -32,6 +32,15 @@ QT_HD int nearest_int(float fval) {
 
 QT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// (float)clamp(nearest_int(v), lo, hi) without leaving the float domain: rounding is monotonic and lo / hi are
+// integers, so clamping first and rounding with the same magic constant gives the same value - two min/max (ALU
+// pipe) and two adds instead of add + mask + subtract + two integer min/max + I2F.  Valid for |v| < 2^22 like
+// nearest_int itself (the candidate searches produce |v| <= nmax + 1).
+QT_HD float round_clamp_f(float v, float lo, float hi) {
+    v = fminf(fmaxf(v, lo), hi);
+    return (v + 12582912.f) - 12582912.f;
+}
+
 // ------------------------------------------------------------------------------------
 // make_qkx2_quants(n=32, nmax, x, weights=av_x+|x|, rmin, rdelta, nstep, use_mad=false)
 // Thread-private.  Instead of keeping L[]/Laux[] arrays it remembers the (iscale, min)
@@ -51,17 +60,21 @@ QT_HD void qkx2_search(const float (&x)[32], int nmax, float rmin, float rdelta,
 #pragma unroll
     for (int l = 0; l < 32; ++l) sum_x2 += x[l] * x[l];
     const float av_x = sqrtf(sum_x2 / 32);
+    const float fmax_ = (float)nmax;
 
+    // weights[i] = av_x + |x[i]| is the same value every time the reference recomputes it: kept in registers
+    float wt[32];
     float mn = x[0], mx = x[0];
-    float sum_w = av_x + fabsf(x[0]);
+    wt[0] = av_x + fabsf(x[0]);
+    float sum_w = wt[0];
     float sum_x = sum_w * x[0];
 #pragma unroll
     for (int i = 1; i < 32; ++i) {
         if (x[i] < mn) mn = x[i];
         if (x[i] > mx) mx = x[i];
-        const float w = av_x + fabsf(x[i]);
-        sum_w += w;
-        sum_x += w * x[i];
+        wt[i] = av_x + fabsf(x[i]);
+        sum_w += wt[i];
+        sum_x += wt[i] * x[i];
     }
     if (mn > 0) mn = 0;
     if (mx == mn) {
@@ -73,11 +86,10 @@ QT_HD void qkx2_search(const float (&x)[32], int nmax, float rmin, float rdelta,
     float best_error = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
-        float diff = scale * l + mn - x[i];
+        const float lf = round_clamp_f(iscale * (x[i] - mn), 0.f, fmax_);
+        float diff = scale * lf + mn - x[i];
         diff = diff * diff;
-        const float w = av_x + fabsf(x[i]);
-        best_error += w * diff;
+        best_error += wt[i] * diff;
     }
     r.l_iscale = iscale; r.l_min = mn; r.all_zero = 0;
     for (int is = 0; is <= nstep; ++is) {
@@ -86,10 +98,8 @@ QT_HD void qkx2_search(const float (&x)[32], int nmax, float rmin, float rdelta,
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
-            lf[i] = (float)l;
-            const float w = av_x + fabsf(x[i]);
-            const float wl = w * lf[i];
+            lf[i] = round_clamp_f(iscale * (x[i] - mn), 0.f, fmax_);
+            const float wl = wt[i] * lf[i];
             sum_l += wl;
             sum_l2 += wl * lf[i];
             sum_xl += wl * x[i];
@@ -107,8 +117,7 @@ QT_HD void qkx2_search(const float (&x)[32], int nmax, float rmin, float rdelta,
             for (int i = 0; i < 32; ++i) {
                 float diff = this_scale * lf[i] + this_min - x[i];
                 diff = diff * diff;
-                const float w = av_x + fabsf(x[i]);
-                cur_error += w * diff;
+                cur_error += wt[i] * diff;
             }
             if (cur_error < best_error) {
                 r.l_iscale = iscale; r.l_min = mn;   // the pair Laux was generated with
@@ -285,14 +294,17 @@ QT_HD void qx_search(K6Thread& th) {
         return;
     }
     th.all_zero = 0;
+    // w = x*x and w*x are the same values in every candidate (C evaluates w*x[i]*l as (w*x[i])*l): kept in registers
+    float w[16], wx[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { w[i] = th.x[i] * th.x[i]; wx[i] = w[i] * th.x[i]; }
     float iscale = -nmax / mx;
     float sumlx = 0, suml2 = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int l = clampi(nearest_int(iscale * th.x[i]), -nmax, nmax - 1);
-        const float w = th.x[i] * th.x[i];
-        sumlx += w * th.x[i] * l;
-        suml2 += w * l * l;
+        const float l = round_clamp_f(iscale * th.x[i], -32.f, 31.f);
+        sumlx += wx[i] * l;
+        suml2 += w[i] * l * l;
     }
     float scale = suml2 ? sumlx / suml2 : 0.0f;
     float best = scale * sumlx;
@@ -303,10 +315,9 @@ QT_HD void qx_search(K6Thread& th) {
         sumlx = suml2 = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int l = clampi(nearest_int(iscale * th.x[i]), -nmax, nmax - 1);
-            const float w = th.x[i] * th.x[i];
-            sumlx += w * th.x[i] * l;
-            suml2 += w * l * l;
+            const float l = round_clamp_f(iscale * th.x[i], -32.f, 31.f);
+            sumlx += wx[i] * l;
+            suml2 += w[i] * l * l;
         }
         if (suml2 > 0 && sumlx * sumlx > best * suml2) {
             th.l_iscale = iscale;
@@ -440,7 +451,7 @@ QT_HD void qkx2_search_q2(const float (&x)[16], Qkx2Result& r) {
     float best_mad = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
+        const float l = round_clamp_f(iscale * (x[i] - mn), 0.f, 3.f);
         const float diff = fabsf(scale * l + mn - x[i]);
         best_mad += fabsf(x[i]) * diff;
     }
@@ -451,8 +462,7 @@ QT_HD void qkx2_search_q2(const float (&x)[16], Qkx2Result& r) {
         float sum_l = 0, sum_l2 = 0, sum_xl = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int l = clampi(nearest_int(iscale * (x[i] - mn)), 0, nmax);
-            lf[i] = (float)l;
+            lf[i] = round_clamp_f(iscale * (x[i] - mn), 0.f, 3.f);
             const float wl = fabsf(x[i]) * lf[i];
             sum_l += wl;
             sum_l2 += wl * lf[i];
