@@ -568,6 +568,117 @@ __global__ void __launch_bounds__(256) dequant_k_kernel(const uint8_t* __restric
     for (int l = 0; l < 32; l += 4) st_f4(y + l, out[l], out[l + 1], out[l + 2], out[l + 3]);
 }
 
+// ---- staged form: 128-bit loads of the packed bytes, fully coalesced 128-bit stores -------------------------------
+// The kernels above read every packed byte with its own global load and store 64-128 contiguous bytes per THREAD
+// (a warp-wide store touches 32 half-filled sectors): 25-55 % of HBM peak, at or below vLLM's ggml_dequantize.  Here
+// a CTA stages the packed bytes of 8192 output elements in shared memory with 128-bit loads, and thread t of step k
+// decodes elements 1024 k + 4 t .. + 3, so that consecutive lanes store consecutive float4s.  One element is decoded by
+// `dq_elem` with exactly the expressions of the kernels above (llama.cpp dequantize_row_* / gguf-py).
+template <int TYPE>
+QT_D float dq_elem(const uint8_t* b, int e) {
+    if (TYPE == T_Q8_0) {
+        return (float)(int)(signed char)b[2 + e] * ld_f16(b);
+    } else if (TYPE == T_IQ4_NL) {
+        const uint8_t q = b[2 + (e & 15)];
+        return ld_f16(b) * kq::iq4nl_value(e >= 16 ? (q >> 4) : (q & 0xF));
+    } else if (TYPE == T_Q4_0 || TYPE == T_Q4_1 || TYPE == T_Q5_0 || TYPE == T_Q5_1) {
+        constexpr bool kSym = (TYPE == T_Q4_0 || TYPE == T_Q5_0);
+        constexpr bool k5 = (TYPE == T_Q5_0 || TYPE == T_Q5_1);
+        constexpr int kHdr = kSym ? 2 : 4;
+        const float d = ld_f16(b);
+        const float m = kSym ? 0.f : ld_f16(b + 2);
+        const uint8_t* qs = b + kHdr + (k5 ? 4 : 0);
+        const uint8_t q = qs[e & 15];
+        int x = e >= 16 ? (q >> 4) : (q & 0xF);
+        if (k5) {
+            const uint32_t qh = b[kHdr] | (b[kHdr + 1] << 8) | (b[kHdr + 2] << 16) | ((uint32_t)b[kHdr + 3] << 24);
+            x |= (int)((qh >> e) & 1) << 4;
+        }
+        if (kSym) return (float)(x - (k5 ? 16 : 8)) * d;
+        return (float)x * d + m;
+    } else if (TYPE == T_Q4_K || TYPE == T_Q5_K) {
+        const int j = e >> 5, l = e & 31;
+        const float d = ld_f16(b), mn = ld_f16(b + 2);
+        int sc, m;
+        scale_min_k4(j, b + 4, sc, m);
+        const float d1 = d * sc, m1 = mn * m;
+        const uint8_t* q = b + (TYPE == T_Q4_K ? 16 : 48) + 32 * (j >> 1);
+        int x = (j & 1) ? (q[l] >> 4) : (q[l] & 0xF);
+        if (TYPE == T_Q5_K) x += ((b[16 + l] >> j) & 1) ? 16 : 0;
+        return d1 * x - m1;
+    } else if (TYPE == T_Q2_K) {
+        const int j = e >> 5, l = e & 31;
+        const int n = j >> 2, sh = 2 * (j & 3);
+        const float d = ld_f16(b + 80), mn = ld_f16(b + 82);
+        const uint8_t sc = b[2 * j + l / 16];
+        const float dl = d * (sc & 0xF), ml = mn * (sc >> 4);
+        return dl * (float)((b[16 + 32 * n + l] >> sh) & 3) - ml;
+    } else if (TYPE == T_Q3_K) {
+        const int j = e >> 5, l = e & 31;
+        const int n = j >> 2, sh = 2 * (j & 3);
+        const float d = ld_f16(b + 108);
+        const uint8_t* scb = b + 96;
+        const int is = 2 * j + l / 16;
+        const int lo = is < 8 ? (scb[is] & 0xF) : (scb[is - 8] >> 4);
+        const int hi = (scb[8 + is % 4] >> (2 * (is / 4))) & 3;
+        const float dl = d * (float)((int)(signed char)(lo | (hi << 4)) - 32);
+        return dl * (float)((int)((b[32 + 32 * n + l] >> sh) & 3) - (((b[l] >> j) & 1) ? 0 : 4));
+    } else {  // Q6_K
+        const int j = e >> 5, l = e & 31;
+        const float d = ld_f16(b + 208);
+        const int n = j >> 2, k = j & 3;
+        const uint8_t* ql = b + 64 * n;
+        const int8_t* sc = reinterpret_cast<const int8_t*>(b + 192) + 8 * n;
+        const int lo = (k & 1) ? ql[l + 32] : ql[l];
+        const int nibble = (k >= 2) ? (lo >> 4) : (lo & 0xF);
+        const int q = (int)(signed char)(nibble | (((b[128 + 32 * n + l] >> (2 * k)) & 3) << 4)) - 32;
+        return d * sc[l / 16 + 2 * k] * q;
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(256) dequant_staged_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                             int64_t nblocks) {
+    constexpr int BE = block_elems(TYPE), BB = block_bytes(TYPE);
+    constexpr int NBLK = 8192 / BE;                      // blocks per tile: 256 (32-element types) or 32 (K types)
+    static_assert((NBLK * BB) % 16 == 0, "a tile of packed blocks must be 16-byte granular");
+    __shared__ __align__(16) uint8_t sb[NBLK * BB];
+    const int tid = threadIdx.x;
+    const int64_t ntiles = (nblocks + NBLK - 1) / NBLK;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * NBLK;
+        const int nv = (int)((nblocks - base) < NBLK ? (nblocks - base) : NBLK);
+        const int bytes = nv * BB;
+        const uint8_t* g = src + base * BB;
+        for (int i = tid; i < (bytes >> 4); i += 256) *reinterpret_cast<uint4*>(sb + 16 * i) = ldg_stream(g + 16 * i);
+        for (int i = (bytes & ~15) + tid; i < bytes; i += 256) sb[i] = g[i];
+        __syncthreads();
+        float* out = dst + base * BE;
+        const int nelem = nv * BE;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int e = 1024 * k + 4 * tid;
+            if (e < nelem) {
+                const uint8_t* b = sb + (e / BE) * BB;
+                const int p = e % BE;
+                const float v0 = dq_elem<TYPE>(b, p), v1 = dq_elem<TYPE>(b, p + 1), v2 = dq_elem<TYPE>(b, p + 2),
+                            v3 = dq_elem<TYPE>(b, p + 3);
+                uint4 u;
+                u.x = __float_as_uint(v0); u.y = __float_as_uint(v1); u.z = __float_as_uint(v2); u.w = __float_as_uint(v3);
+                stg_stream(out + e, u);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int TYPE>
+static void launch_dequant_staged(const uint8_t* s, float* dst, int64_t nblk, cudaStream_t st) {
+    const int64_t ntiles = (nblk + 8192 / block_elems(TYPE) - 1) / (8192 / block_elems(TYPE));
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    dequant_staged_kernel<TYPE><<<(unsigned)(ntiles < cap ? ntiles : cap), 256, 0, st>>>(s, dst, nblk);
+}
+
 // ---------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------
@@ -716,6 +827,22 @@ int qt_gguf_dequantize(int ggml_type, const void* src, int64_t nrows, int64_t nc
     const int64_t nblk = nrows * (ncols / be);
     cudaStream_t st = (cudaStream_t)stream;
     const uint8_t* s = (const uint8_t*)src;
+    if (((uintptr_t)src & 15) == 0) {        // staged kernels: 128-bit loads of the packed bytes
+        switch (ggml_type) {
+            case T_Q4_0: launch_dequant_staged<T_Q4_0>(s, dst, nblk, st); break;
+            case T_Q4_1: launch_dequant_staged<T_Q4_1>(s, dst, nblk, st); break;
+            case T_Q5_0: launch_dequant_staged<T_Q5_0>(s, dst, nblk, st); break;
+            case T_Q5_1: launch_dequant_staged<T_Q5_1>(s, dst, nblk, st); break;
+            case T_Q8_0: launch_dequant_staged<T_Q8_0>(s, dst, nblk, st); break;
+            case T_IQ4_NL: launch_dequant_staged<T_IQ4_NL>(s, dst, nblk, st); break;
+            case T_Q2_K: launch_dequant_staged<T_Q2_K>(s, dst, nblk, st); break;
+            case T_Q3_K: launch_dequant_staged<T_Q3_K>(s, dst, nblk, st); break;
+            case T_Q4_K: launch_dequant_staged<T_Q4_K>(s, dst, nblk, st); break;
+            case T_Q5_K: launch_dequant_staged<T_Q5_K>(s, dst, nblk, st); break;
+            case T_Q6_K: launch_dequant_staged<T_Q6_K>(s, dst, nblk, st); break;
+        }
+        return qt::check_launch("qt_gguf_dequantize");
+    }
     if (be == 32) {
         const int64_t nthreads = nblk * 2;
         const unsigned grid = (unsigned)((nthreads + 255) / 256);

@@ -8,7 +8,8 @@ Two checks, each on a tiny-but-wide Llama (hidden 1024, intermediate 2816: both 
      the ranks (owner-computes chain + broadcast, all-gathered rows) must give bit-identical `weight_packed`,
      `weight_scale` and `weight_g_idx` to the unsharded run of the same kernels on every rank.
   B. whole model through `quantize_model_gptq`: samples sharded + NCCL all-reduce(H) vs one rank doing everything.
-     H now differs in fp32 summation order: without act_order >= 99 % of the codes must agree; with actorder=group
+     H now differs in fp32 summation order: without act_order >= 99.5 % of layer 0's codes must agree (later layers
+     see inputs that already went through slightly different codes: objective only); with actorder=group
      (permutation = argsort of a nearly flat diagonal on random-init weights) the summed GPTQ loss must agree to 1 %.
 """
 import argparse
@@ -79,17 +80,20 @@ def main():
         out = None
         if rank == 0:
             r_1 = pipeline.quantize_model_gptq(shape, host_sd, ids, a_, dev, dist=single)
-            same = tot = 0
+            same, tot = {}, {}
             h_sh, h_1 = hashlib.sha256(), hashlib.sha256()
             for k in sorted(r_1.tensors):
                 if k.endswith("weight_packed"):
                     p1, p2 = r_1.tensors[k], r_sh.tensors[k]
+                    lay = int(k.split(".")[2])
                     for sft in range(0, 32, 4):
-                        same += int((((p1 >> sft) & 15) == ((p2 >> sft) & 15)).sum())
-                    tot += p1.numel() * 8
+                        same[lay] = same.get(lay, 0) + int((((p1 >> sft) & 15) == ((p2 >> sft) & 15)).sum())
+                    tot[lay] = tot.get(lay, 0) + p1.numel() * 8
                     h_1.update(p1.numpy().tobytes())
                     h_sh.update(p2.numpy().tobytes())
-            out = {"code_agreement": same / tot, "artifact_sha_sharded": h_sh.hexdigest()[:16],
+            out = {"code_agreement": sum(same.values()) / sum(tot.values()),
+                   "code_agreement_per_layer": [same[l] / tot[l] for l in sorted(tot)],
+                   "artifact_sha_sharded": h_sh.hexdigest()[:16],
                    "artifact_sha_single": h_1.hexdigest()[:16],
                    "gptq_loss_sharded_vs_single": [sum(r_sh.losses.values()), sum(r_1.losses.values())]}
         dist.barrier()
@@ -109,7 +113,9 @@ def main():
     if rank == 0:
         l_sh, l_1 = rb_act["gptq_loss_sharded_vs_single"]
         p_sh, p_1 = rb_plain["gptq_loss_sharded_vs_single"]
-        ok = (ok and rb_plain["code_agreement"] >= 0.99 and abs(p_sh - p_1) <= 0.01 * abs(p_1)
+        # layer 0 sees identical inputs on both sides (H differs by summation order only); from layer 1 on the inputs
+        # themselves differ (they went through layer 0's slightly different codes), so only the objective is asserted
+        ok = (ok and rb_plain["code_agreement_per_layer"][0] >= 0.995 and abs(p_sh - p_1) <= 0.01 * abs(p_1)
               and abs(l_sh - l_1) <= 0.01 * abs(l_1))
     dist.destroy_process_group()
     if not ok:

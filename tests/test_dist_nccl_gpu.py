@@ -25,5 +25,10 @@ def test_nccl_sharded_equals_unsharded():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_parity_nccl.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    if r.returncode != 0:       # keep the evidence where a gpurun call brings it back
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "dist_parity_nccl_failure.log"), "w") as f:
+            f.write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+    report = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0, (report[-1] if report else "") + r.stderr[-1500:]
     assert '"all_ranks": true' in r.stdout
