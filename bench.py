@@ -622,7 +622,7 @@ def main():
                 hess_events.extend(ev.values())
             # raw sums per rank; the NCCL all-reduce of each H, its 2/n scaling, the chain and the column loops run
             # per distinct input on that input's stream and communicator lane (what quantize_model_gptq does)
-            done = pipeline.accumulate_layer_sums(acts, n_local, accs, syrk_events=ev)
+            done = pipeline.accumulate_layer_sums(acts, n_local, accs, syrk_events=ev, dist=d)
             res = lq.quantize_layer(weights[l], None, accs=accs, n_total=a.samples, acc_events=done)
             for lin, r in res.items():
                 compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args)

@@ -104,6 +104,9 @@ int qt_hessian_finalize(float* H, int K, float factor, void* stream);
 int qt_hessian_diag_accumulate(const void* X, int dtype, int64_t T, int K, float* diag, float* scratch, void* stream);
 int qt_hessian_set_diagonal(float* H, int K, const float* diag, void* stream);
 int qt_hessian_set_splits(int splits);   /* tuning: force the token split count (0 = heuristic) */
+/* Leave n SMs to other streams for the following qt_hessian_accumulate calls (0 = take every SM): used while the
+ * NCCL all-reduce of the previous input's Hessian is in flight - its CTAs cannot be placed next to the SYRK's. */
+int qt_hessian_reserve_sms(int n);
 /* Packed upper block-triangle of a K x K fp32 matrix: what the multi-GPU path puts on NVLink instead of the full
  * square ("all-reduce the packed triangle").  Row block i (128 rows) is stored from column
  * floor(128 i / align) * align; align = 256 for the raw Hessian sums (the SYRK's tile width), 128 for the

@@ -36,6 +36,7 @@ _SIGS = {
     "qt_pack_int32": [_vp, _i32, _i32, _i32, _vp, _vp],
     "qt_unpack_int32": [_vp, _i32, _i32, _i32, _vp, _vp],
     "qt_hessian_set_splits": [_i32],
+    "qt_hessian_reserve_sms": [_i32],
     "qt_hessian_accumulate": [_vp, _i32, _i64, _i32, _vp, _vp],
     "qt_hessian_finalize": [_vp, _i32, _f32, _vp],
     "qt_hessian_diag_accumulate": [_vp, _i32, _i64, _i32, _vp, _vp, _vp],

@@ -402,13 +402,22 @@ __global__ void __launch_bounds__(256) panel_top_kernel(float* __restrict__ A, f
 }
 
 __global__ void __launch_bounds__(256) panel_top_commit_kernel(float* __restrict__ A, const float* __restrict__ X, int ld,
-                                                               int k, int nb, int nb2) {
+                                                               int k, int nb, int nb2, float* __restrict__ Lh,
+                                                               float* __restrict__ Ll) {
     const int r0 = k + nb;
     for (int q = blockIdx.x * 256 + threadIdx.x; q < nb2 * (NB / 4); q += gridDim.x * 256) {
         const int row = q >> 5, j4 = (q & 31) * 4;
         if (j4 < nb) {
             const long long g = (long long)(r0 + row) * ld + k + j4;
-            *reinterpret_cast<float4*>(A + g) = *reinterpret_cast<const float4*>(X + g);
+            const float4 v = *reinterpret_cast<const float4*>(X + g);
+            *reinterpret_cast<float4*>(A + g) = v;
+            if (Lh) {     // tf32 split of the solved rows (operands of the deferred tensor-core updates)
+                float4 h, l;
+                tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y);
+                tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+                *reinterpret_cast<float4*>(Lh + g) = h;
+                *reinterpret_cast<float4*>(Ll + g) = l;
+            }
         }
     }
 }
@@ -459,6 +468,30 @@ __global__ void __launch_bounds__(256) gather_flip_kernel(const float* __restric
         v += *damp;
     }
     Hf[(long long)i * K + j] = v;
+}
+
+// Same result, one CTA per output row: the source row H[p(i)][:] is read once, coalesced, into shared memory and the
+// permuted gather happens there (the per-element global gather moved a 32-byte sector per 4-byte element through
+// L2: 1.1 ms at K = 14336, on the multi-GPU critical path between the all-reduce of H and the chain).
+__global__ void __launch_bounds__(512) gather_flip_row_kernel(const float* __restrict__ H, const int* __restrict__ perm,
+                                                              const uint8_t* __restrict__ dead,
+                                                              const float* __restrict__ damp, float* __restrict__ Hf, int K) {
+    extern __shared__ float srow[];
+    const int i = blockIdx.x;
+    const int pi = perm ? perm[K - 1 - i] : (K - 1 - i);
+    const float4* src = reinterpret_cast<const float4*>(H + (long long)pi * K);
+    for (int c = threadIdx.x; c < (K >> 2); c += 512) reinterpret_cast<float4*>(srow)[c] = src[c];
+    __syncthreads();
+    float* dst = Hf + (long long)i * K;
+    for (int j = threadIdx.x; j <= i; j += 512) {
+        const int pj = perm ? perm[K - 1 - j] : (K - 1 - j);
+        float v = srow[pj];
+        if (j == i) {
+            if (dead[pi]) v = 1.f;
+            v += *damp;
+        }
+        dst[j] = v;
+    }
 }
 
 __global__ void __launch_bounds__(256) set_identity_kernel(float* __restrict__ U, int K) {
@@ -729,38 +762,32 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
                     if (cudaEventRecord(la.potrf_done, la.side) != cudaSuccess) return QT_ERR_CUDA;
                     potrf_ahead = true;
                 }
-                panel_top_commit_kernel<<<8, 256, 0, st>>>(A, X, ld, k, nb, nb2);
+                // the solved top rows go from X to A, together with their tf32 split
+                panel_top_commit_kernel<<<8, 256, 0, st>>>(A, X, ld, k, nb, nb2, Lh, Ll);
                 rc = check_launch("panel_top_commit");
                 if (rc) return rc;
             }
-            if (rem > nb2) {     // rest of the TRSM
+            const long long poff = (long long)(k + nb) * ld + k;
+            if (rem > nb2) {     // rest of the TRSM; its epilogue also writes the tf32 split of the solved rows
                 float* Pr = P + (long long)nb2 * ld;
                 t.A = Pr; t.C = Pr; t.M = rem - nb2;
+                t.split_hi = Lh + poff + (long long)nb2 * ld;
+                t.split_lo = Ll + poff + (long long)nb2 * ld;
+                t.ld_split = ld;
                 rc = sgemm(true, t, 1, st);
                 if (rc) return rc;
             }
-            const long long poff = (long long)(k + nb) * ld + k;
-            rc = split_block(false, P, ld, Lh + poff, Ll + poff, ld, rem, nb, 0, 1, 0, 0, st);
-            if (rc) return rc;
             if (n_in <= 0) continue;
-            // inner updates (FFMA): only the columns of this outer block
-            if (rem > nb2) {     // rows below the next diagonal block, its column:  -= P_rest P_top^T
+            // inner update (FFMA), only the columns of this outer block, ONE launch:
+            //   A[rows below the next diagonal block, (k+nb) .. oe) -= P_rest * P[(k+nb) .. oe, :]^T
+            // (column block 0 is the old "s1" against the top rows, the rest the old lower-tile "s2")
+            if (rem > nb2) {
                 float* Pr = P + (long long)nb2 * ld;
-                GemmArgs s1{};
-                s1.A = Pr; s1.B = P; s1.C = A + (long long)(k + nb + nb2) * ld + (k + nb);
-                s1.M = rem - nb2; s1.N = nb2; s1.Kd = nb; s1.lda = s1.ldb = s1.ldc = ld;
-                s1.alpha = -1.f; s1.beta = 1.f;
-                rc = sgemm(true, s1, 1, st);
-                if (rc) return rc;
-            }
-            const int n_in2 = n_in - nb2;
-            if (n_in2 > 0) {
-                float* P2 = P + (long long)nb2 * ld;
-                GemmArgs s2{};
-                s2.A = P2; s2.B = P2; s2.C = A + (long long)(k + nb + nb2) * ld + (k + nb + nb2);
-                s2.M = rem - nb2; s2.N = n_in2; s2.Kd = nb; s2.lda = s2.ldb = s2.ldc = ld;
-                s2.alpha = -1.f; s2.beta = 1.f; s2.lower_tiles_only = 1;
-                rc = sgemm(true, s2, 1, st);
+                GemmArgs s12{};
+                s12.A = Pr; s12.B = P; s12.C = A + (long long)(k + nb + nb2) * ld + (k + nb);
+                s12.M = rem - nb2; s12.N = n_in; s12.Kd = nb; s12.lda = s12.ldb = s12.ldc = ld;
+                s12.alpha = -1.f; s12.beta = 1.f; s12.lower_tiles_only = 1; s12.tri_row_offset = nb2;
+                rc = sgemm(true, s12, 1, st);
                 if (rc) return rc;
             }
         }
@@ -820,7 +847,11 @@ static int cholesky_lower_tc(float* A, float* X, float* Lh, float* Ll, float* df
             }
             p.M = remo - nextw; p.N = remo - nextw;
             p.a_row0 = p.b_row0 = p.c_row0 = p.c_col0 = oe + nextw;
+            // the far update runs underneath the next outer block's panel loop: leave SMs for its 1-10 CTA kernels
+            // (measured: potrf_inv waited ~220 us per outer block for a 148-CTA far update to drain)
+            p.reserve_sms = la.ok ? 16 : 0;
             rc = tgemm::launch(p, fs);
+            p.reserve_sms = 0;
             if (rc) return rc;
             diag_fix_post_kernel<<<(remo - nextw + 255) / 256, 256, 0, fs>>>(A, ld, oe + nextw, remo - nextw, dfix);
             rc = check_launch("diag_fix_post");
@@ -930,6 +961,17 @@ int qt_gptq_prepare_hessian(const float* H, const int* perm, int K, float percda
     diag_stats_kernel<<<1, 1024, 0, st>>>(H, K, percdamp, dead, damp_scratch);
     int rc = check_launch("diag_stats");
     if (rc) return rc;
+    const size_t row_bytes = (size_t)K * sizeof(float);
+    if (!(K & 3) && row_bytes <= 200 * 1024) {
+        static size_t attr_bytes = 0;
+        if (row_bytes > attr_bytes) {
+            if (cudaFuncSetAttribute(gather_flip_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes) !=
+                cudaSuccess) { set_last_error("gather_flip smem attr", cudaErrorInvalidValue); return QT_ERR_CUDA; }
+            attr_bytes = row_bytes;
+        }
+        gather_flip_row_kernel<<<K, 512, row_bytes, st>>>(H, perm, dead, damp_scratch, Hf, K);
+        return check_launch("gather_flip_row");
+    }
     dim3 grid((K + 255) / 256, K);
     gather_flip_kernel<<<grid, 256, 0, st>>>(H, perm, dead, damp_scratch, Hf, K);
     return check_launch("gather_flip");

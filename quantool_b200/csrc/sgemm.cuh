@@ -27,6 +27,11 @@ struct GemmArgs {
     int a_lower_tri;       // 1: A[m][k] == 0 for k > m  -> k range ends at the tile's last row
     int b_lower_tri;       // 1: B[k][n] == 0 for k < n  -> k range starts at the tile's first col
     int tri_row_offset;    // rows of this call start at this row of the triangular structure (row slices)
+    // Kd = 128 "NT" kernel only: also write the tf32 split of the result (what the tensor-core updates read as
+    // operands) - hi/lo at the same (row, column) offsets as C inside buffers with leading dimension ld_split
+    float* split_hi;
+    float* split_lo;
+    int ld_split;
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 16;
@@ -240,7 +245,14 @@ __global__ void __launch_bounds__(256, 2) sgemm_nt_k128_kernel(GemmArgs g) {
             const int n = n0 + tx + 16 * j;
             if (n >= g.N) continue;
             float* cp = g.C + (long long)m * g.ldc + n;
-            *cp = (g.beta != 0.f) ? g.alpha * acc[i][j] + g.beta * (*cp) : g.alpha * acc[i][j];
+            const float v = (g.beta != 0.f) ? g.alpha * acc[i][j] + g.beta * (*cp) : g.alpha * acc[i][j];
+            *cp = v;
+            if (g.split_hi) {
+                float h, l;
+                tf32_split(v, h, l);
+                g.split_hi[(long long)m * g.ld_split + n] = h;
+                g.split_lo[(long long)m * g.ld_split + n] = l;
+            }
         }
     }
 }

@@ -339,6 +339,7 @@ int launch(const Problem& p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const long long ntiles = (long long)a.batch * a.m_tiles * a.n_tiles;
+    if (p.reserve_sms > 0 && p.reserve_sms < nsm) nsm -= p.reserve_sms;
     tgemm_kernel<<<(unsigned)(ntiles < nsm ? ntiles : nsm), NTHREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mc, a);
     return check_launch("tgemm");
 }

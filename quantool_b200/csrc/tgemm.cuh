@@ -29,6 +29,8 @@ struct Problem {
     int a_tri = 0;                 // 1: A[m][k] = 0 for k > m (lower), 2: = 0 for k < m (upper) - k range is trimmed
     int b_tri = 0;                 // same for B[n][k]
     int max_chain = 128;           // longest k span accumulated in TMEM before the partial sum is flushed to C
+    int reserve_sms = 0;           // leave this many SMs to other streams (a persistent 148-CTA launch with ~200 KB of
+                                   // shared memory per CTA otherwise blocks every 1-10 CTA kernel until it drains)
     // single-product mode: A.hi * B.hi only (plain tf32 GEMM, a third of the tensor work; lo pointers unused)
     bool single = false;
     // bf16 operands (implies single): A.hi / B.hi point at __nv_bfloat16 arrays, ld / cols in elements; kind::f16,

@@ -602,19 +602,32 @@ def accumulate_layer_hessians(inputs: Dict[str, torch.Tensor], n_samples_local: 
     return out
 
 
+NCCL_SMS = 24      # SMs left to the NCCL kernels of an all-reduce that overlaps the following SYRKs (24 channels)
+
+
 def accumulate_layer_sums(inputs: Dict[str, torch.Tensor], n_samples_local: int, accs: Dict[str, HessianAccumulator],
-                          syrk_events=None):
+                          syrk_events=None, dist: Optional[Dist] = None):
     """Raw per-rank sums only (no cross-rank reduction): one SYRK per distinct input, largest K first, and a CUDA
     event after each so that `GPTQLayerQuantizer.quantize_layer(accs=...)` can start the all-reduce and the chain
-    of an input while the SYRKs of the others are still running.  Returns name -> event."""
+    of an input while the SYRKs of the others are still running.  With several ranks the SYRKs after the first
+    leave NCCL_SMS SMs free: the persistent SYRK grid otherwise fills every SM and the all-reduce of the largest
+    Hessian (the layer's critical path) only starts moving when the last SYRK has drained (measured at 8 GPUs:
+    4.7 ms for 420 MB).  Returns name -> event."""
     events = {}
-    for name in sorted(inputs, key=lambda n: -inputs[n].shape[-1]):
-        acc = accs[name]
-        acc.reset()
-        acc.add(inputs[name], n_samples_local, syrk_events=(syrk_events or {}).get(name))
-        ev = torch.cuda.Event()
-        ev.record()
-        events[name] = ev
+    multi = dist is not None and dist.on
+    try:
+        for i, name in enumerate(sorted(inputs, key=lambda n: -inputs[n].shape[-1])):
+            if multi and i == 1:
+                cabi.lib().qt_hessian_reserve_sms(NCCL_SMS)
+            acc = accs[name]
+            acc.reset()
+            acc.add(inputs[name], n_samples_local, syrk_events=(syrk_events or {}).get(name))
+            ev = torch.cuda.Event()
+            ev.record()
+            events[name] = ev
+    finally:
+        if multi:
+            cabi.lib().qt_hessian_reserve_sms(0)
     return events
 
 

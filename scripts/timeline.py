@@ -48,7 +48,7 @@ def main():
     accs = {n: HessianAccumulator(k, dev) for n, k in dims.items()}
 
     def layer():
-        done = pipeline.accumulate_layer_sums(acts, n_local, accs)
+        done = pipeline.accumulate_layer_sums(acts, n_local, accs, dist=d)
         res = lq.quantize_layer(w, None, accs=accs, n_total=samples, acc_events=done)
         for lin, r in res.items():
             compress_linear(r.weight, r.scale, r.zero_point, r.g_idx, args)
