@@ -203,7 +203,7 @@ def gguf_probe(device, hbm):
     # their roofline is the issue rate, ops/element counted from SASS (profiles/r02_kquant_ops.json)
     try:
         ops = json.load(open(os.path.join(ROOT, "profiles", "r02_kquant_ops.json")))
-        for t in ("Q4_K", "Q6_K"):
+        for t in ("Q4_K", "Q6_K", "IQ4_NL"):
             if t in ops:
                 o = ops[t]
                 ach = out[t]["Gelem_per_s"] * 1e9 * o["issue_slots_per_element"]
@@ -540,7 +540,11 @@ def main():
                 f"({shape.num_hidden_layers} layers), {a.samples}x{a.seq}-token synthetic calibration")
     config = {"workload": workload, "level": a.level, "actorder": a.actorder, "calibration": f"{a.samples}x{a.seq}",
               "layers": shape.num_hidden_layers, "parallelism": f"samples+rows sharded x{world}, H all-reduce",
-              "l2": "inputs larger than L2 (13.5 GB activations + 0.44 GB weights per layer per step)"}
+              "l2": "inputs larger than L2"}
+    _t_rank = -(-a.samples // world) * a.seq
+    config["l2"] = ("inputs larger than L2 (%.1f GB activations per rank + %.2f GB weights per layer per step; 126 MB L2)"
+                    % (sum(_t_rank * k * 2 for k in shape.input_dims().values()) / 1e9,
+                       sum(n_ * k_ * 2 for n_, k_ in shape.linear_shapes().values()) / 1e9))
 
     if a.impl == "reference":
         if rank != 0:

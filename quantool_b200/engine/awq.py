@@ -89,15 +89,25 @@ def search_mapping(shape, w: Dict[str, torch.Tensor], mp: Mapping, x_all: torch.
         cabi.hessian_finalize(H, 1.0)
         G = H.to(torch.bfloat16)
         del H
-        d16 = torch.empty(bw[0].shape, dtype=torch.bfloat16, device=dev)
-        d32 = torch.empty(bw[0].shape, dtype=torch.float32, device=dev)
+        # G is the same on every rank, and tr(D G D^T) is a sum over the rows of D: each rank takes a row slice of
+        # the weight (the losses are summed below) - otherwise all ranks would repeat the same 20 products
+        wl = bw[0]
+        if dist is not None and dist.on:
+            from .pipeline import row_split
+            sizes = row_split(wl.shape[0], dist.world, 16)
+            r0 = sum(sizes[: dist.rank])
+            wl = wl[r0: r0 + sizes[dist.rank]]
+        if wl.shape[0] > 0:
+            d16 = torch.empty(wl.shape, dtype=torch.bfloat16, device=dev)
+            d32 = torch.empty(wl.shape, dtype=torch.float32, device=dev)
         for gi in range(n_grid):
             s = candidate_scales(x_mean, w_mean, gi / n_grid, duo_scaling)
             cand.append(s)
-            cabi.awq_scale_qdq_delta(bw[0], s, gs, args.num_bits, args.symmetric, d16, d32)
-            cabi.awq_gram_loss(d16, d32, G, losses_dev[gi:gi + 1])
+            if wl.shape[0] > 0:
+                cabi.awq_scale_qdq_delta(wl, s, gs, args.num_bits, args.symmetric, d16, d32)
+                cabi.awq_gram_loss(d16, d32, G, losses_dev[gi:gi + 1])
         numel = x_all.shape[0] * bw[0].shape[0]
-        del G, d16, d32
+        del G
     else:
         ref_out = [_parent_forward(shape, mp.parent, w, lin, xin(c), c[3], c[4]) for c in chunks]
         numel = sum(o.numel() for o in ref_out)
@@ -115,8 +125,7 @@ def search_mapping(shape, w: Dict[str, torch.Tensor], mp: Mapping, x_all: torch.
                 cabi.sq_err_sum(ro, out, losses_dev[gi:gi + 1])
     tot = torch.tensor([float(numel)], dtype=torch.float64, device=dev)
     if dist is not None and dist.on:
-        if not gram:                      # the Gram matrix is already summed over the ranks
-            dist.all_reduce_sum(losses_dev)
+        dist.all_reduce_sum(losses_dev)   # forward form: token shards; Gram form: row slices of D against the summed G
         dist.all_reduce_sum(tot)
     losses = (losses_dev / tot).cpu().tolist()
     best, best_err = -1, float("inf")
