@@ -636,6 +636,31 @@ QT_D float dq_elem(const uint8_t* b, int e) {
     }
 }
 
+// four consecutive elements p .. p+3 (p % 4 == 0) of one block: the header / sub-block values are derived once.
+// Q4_K / Q5_K blocks are 16-byte multiples, so the four code bytes are one aligned 32-bit shared-memory load.
+template <int TYPE>
+QT_D void dq4(const uint8_t* b, int p, float (&o)[4]) {
+    if (TYPE == T_Q4_K || TYPE == T_Q5_K) {
+        const int j = p >> 5, l0 = p & 31;
+        const float d = ld_f16(b), mn = ld_f16(b + 2);
+        int sc, m;
+        scale_min_k4(j, b + 4, sc, m);
+        const float d1 = d * sc, m1 = mn * m;
+        const uint32_t qq = *reinterpret_cast<const uint32_t*>(b + (TYPE == T_Q4_K ? 16 : 48) + 32 * (j >> 1) + l0);
+        const uint32_t hh = TYPE == T_Q5_K ? *reinterpret_cast<const uint32_t*>(b + 16 + l0) : 0u;
+        const int sh = (j & 1) ? 4 : 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int x = (int)((qq >> (8 * i + sh)) & 0xFu);
+            if (TYPE == T_Q5_K) x += ((hh >> (8 * i + j)) & 1u) ? 16 : 0;
+            o[i] = d1 * x - m1;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = dq_elem<TYPE>(b, p + i);
+    }
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(256) dequant_staged_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
                                                              int64_t nblocks) {
@@ -661,10 +686,10 @@ __global__ void __launch_bounds__(256) dequant_staged_kernel(const uint8_t* __re
             if (e < nelem) {
                 const uint8_t* b = sb + (e / BE) * BB;
                 const int p = e % BE;
-                const float v0 = dq_elem<TYPE>(b, p), v1 = dq_elem<TYPE>(b, p + 1), v2 = dq_elem<TYPE>(b, p + 2),
-                            v3 = dq_elem<TYPE>(b, p + 3);
+                float v[4];
+                dq4<TYPE>(b, p, v);
                 uint4 u;
-                u.x = __float_as_uint(v0); u.y = __float_as_uint(v1); u.z = __float_as_uint(v2); u.w = __float_as_uint(v3);
+                u.x = __float_as_uint(v[0]); u.y = __float_as_uint(v[1]); u.z = __float_as_uint(v[2]); u.w = __float_as_uint(v[3]);
                 stg_stream(out + e, u);
             }
         }
