@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gguf", action="store_true")
+    ap.add_argument("--no-vllm", action="store_true", help="skip the vLLM ggml_dequantize comparison child process")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-side", action="store_true", help="skip the awq / smoothquant / tgemm blocks of the default line")
     ap.add_argument("--workload", default="gptq", choices=["gptq", "awq", "smoothquant", "gguf", "probes"],
@@ -215,7 +216,7 @@ def gguf_probe(device, hbm):
     return out
 
 
-def dequant_probe(device, hbm):
+def dequant_probe(device, hbm, vllm=True):
     """GGUF dequantize GB/s (row a16), with vLLM's CUDA `ggml_dequantize` (the bar to beat) timed beside
     it in a child process (so that vLLM's extension is not loaded into this one)."""
     from quantool_b200 import cabi
@@ -246,6 +247,8 @@ for name, (tid, be, bb) in T.items():
     res[name] = {"ms": round(ms, 4), "GBps": round((W.numel() + n * k * 2) / ms / 1e6, 1), "bytes": "packed in + fp16 out"}
 print("VLLM_JSON " + json.dumps(res))
 """
+    if not vllm:
+        return out
     try:
         env = dict(os.environ)
         idx = device.index or 0
@@ -749,7 +752,7 @@ def main():
             d.dist.destroy_process_group()
         return
     gg = None if a.no_gguf else guarded(gguf_probe, dev, hbm)
-    dq = None if a.no_gguf else guarded(dequant_probe, dev, hbm)
+    dq = None if a.no_gguf else guarded(dequant_probe, dev, hbm, not a.no_vllm)
     gs = None if a.no_gguf else guarded(gguf_smollm2, dev, world, rank)
     tg = None if a.no_side else guarded(tgemm_probe, dev, peaks)
     cb = None if a.no_cpu else cpu_reference_sample(shape, a.level, a.actorder, a.samples, a.seq)
