@@ -716,27 +716,41 @@ QT_HD float iq4nl_value(int i) {
 // best_index_int8(16, kvalues_iq4nl, x): nearest table value, ties to the upper one.  Branch-free form of the
 // reference's bisection: with 16 entries it ends after at most 4 halvings, and a halving of an interval of width 1
 // is a no-op (mav == ml, x >= tbl[ml] holds), so four unconditional rounds give the same (ml, mu).
-QT_HD int iq4nl_best_index(const float* tbl, float x) {
-    int ml = 0, mu = 15;
+// Returns the index and (through `q`) the table value at that index.  The first two bisection rounds compare
+// against immediates (the packer was bound by shared-memory look-ups: 7 per element and candidate, now 4).
+QT_HD int iq4nl_best_index_q(const float* tbl, float x, float& q) {
+    // round 1: mav = 7 (-10); round 2: mav = 3 (-65) or 11 (38)
+    const bool b1 = x < -10.f;
+    const bool b2 = x < (b1 ? -65.f : 38.f);
+    int ml = b1 ? (b2 ? 0 : 3) : (b2 ? 7 : 11);
+    int mu = b1 ? (b2 ? 3 : 7) : (b2 ? 11 : 15);
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 2; ++it) {
         const int mav = (ml + mu) >> 1;
         const bool below = x < tbl[mav];
         mu = below ? mav : mu;
         ml = below ? ml : mav;
     }
     const int lo = mu > 0 ? mu - 1 : 0;
-    int r = (x - tbl[lo] < tbl[mu] - x) ? lo : mu;
-    r = (x >= 113.f) ? 15 : r;
-    r = (x <= -127.f) ? 0 : r;
+    const float a = tbl[lo], b = tbl[mu];
+    const bool take_lo = (x - a < b - x);
+    int r = take_lo ? lo : mu;
+    q = take_lo ? a : b;
+    if (x >= 113.f) { r = 15; q = 113.f; }
+    if (x <= -127.f) { r = 0; q = -127.f; }
     return r;
+}
+QT_HD int iq4nl_best_index(const float* tbl, float x) {
+    float q;
+    return iq4nl_best_index_q(tbl, x, q);
 }
 
 QT_HD void iq4nl_sums(const float* tbl, const float (&x)[32], float id, float& sumqx, float& sumq2) {
     sumqx = 0.f; sumq2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const float q = tbl[iq4nl_best_index(tbl, id * x[j])];
+        float q;
+        iq4nl_best_index_q(tbl, id * x[j], q);
         const float w = x[j] * x[j];
         sumqx += w * q * x[j];
         sumq2 += w * q * q;
