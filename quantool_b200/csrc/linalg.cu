@@ -963,12 +963,9 @@ int qt_gptq_prepare_hessian(const float* H, const int* perm, int K, float percda
     if (rc) return rc;
     const size_t row_bytes = (size_t)K * sizeof(float);
     if (!(K & 3) && row_bytes <= 200 * 1024) {
-        static size_t attr_bytes = 0;
-        if (row_bytes > attr_bytes) {
-            if (cudaFuncSetAttribute(gather_flip_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes) !=
-                cudaSuccess) { set_last_error("gather_flip smem attr", cudaErrorInvalidValue); return QT_ERR_CUDA; }
-            attr_bytes = row_bytes;
-        }
+        // once per chain: set on every call (function attributes are per device)
+        if (cudaFuncSetAttribute(gather_flip_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes) !=
+            cudaSuccess) { set_last_error("gather_flip smem attr", cudaErrorInvalidValue); return QT_ERR_CUDA; }
         gather_flip_row_kernel<<<K, 512, row_bytes, st>>>(H, perm, dead, damp_scratch, Hf, K);
         return check_launch("gather_flip_row");
     }
