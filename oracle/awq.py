@@ -78,6 +78,22 @@ def compute_loss(fp16_outputs: List[torch.Tensor], int_w_outputs: List[torch.Ten
     return loss / num_elements
 
 
+def gram_loss_single_linear(x_batches: List[torch.Tensor], w: torch.Tensor, w_candidate: torch.Tensor) -> float:
+    """The loss `compute_loss` gives for a parent that is ONE Linear (F.linear(x, w)), written through the Gram matrix
+    G = X^T X:  sum ||x (Wc - W)^T||^2 / numel = tr(D G D^T) / numel with D = Wc - W.  This is the form the CUDA path
+    evaluates (qt_awq_gram_loss); here in fp64 so tests can pin both the identity and the size of what it leaves out
+    (upstream rounds each parent output to the model dtype before taking the difference; the Gram form does not)."""
+    K = w.shape[1]
+    G = torch.zeros((K, K), dtype=torch.float64)
+    numel = 0
+    for x in x_batches:
+        x2 = x.reshape(-1, K).double()
+        G += x2.t() @ x2
+        numel += x2.shape[0] * w.shape[0]
+    D = w_candidate.double() - w.double()
+    return float(((D @ G) * D).sum()) / numel
+
+
 def compute_best_scale(x_mean: torch.Tensor, w_mean: torch.Tensor, balance_weights: List[torch.Tensor],
                        parent_forward: Callable[[List[torch.Tensor]], List[torch.Tensor]], fp16_outputs,
                        symmetric: bool, bit_width: int, group_size: int, n_grid: int = N_GRID,

@@ -184,3 +184,35 @@ def test_gptq_oracle_self_consistency(level, actorder):
     assert og.layer_error(W, Wq, X.reshape(-1, K).float()) < og.layer_error(W, Wr, X.reshape(-1, K).float())
     assert (gi is not None) == (actorder == "group")
     assert loss > 0
+
+
+def test_awq_gram_form_loss_matches_forward_form():
+    """Single-Linear AWQ parent: tr(D G D^T) / numel (what the CUDA path evaluates) against the oracle's forward-form
+    loss on the same candidate weights.  In fp32 outputs the two agree to rounding; with the reference's bf16 outputs
+    the forward form carries the output-rounding noise of BOTH operands, which bounds the deviation (a few %), and
+    the grid point the search picks is the same."""
+    import torch
+    from oracle import awq as oa
+    g = torch.Generator().manual_seed(3)
+    N, K, T = 96, 256, 1024
+    w = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    xs = [torch.randn((2, T // 4, K), generator=g).to(torch.bfloat16) for _ in range(2)]
+    x_mean = torch.cat([x.reshape(-1, K) for x in xs]).abs().float().mean(0)
+    w_mean = oa.weight_mean([w], 128)
+    ref32 = [torch.nn.functional.linear(x.float(), w.float()) for x in xs]
+    ref16 = [torch.nn.functional.linear(x, w) for x in xs]
+    fwd32, fwd16, gram = [], [], []
+    for gi in range(0, 20, 3):
+        s = oa.candidate_scales(x_mean, w_mean, gi / 20).view(1, -1)
+        ws = w.clone()
+        ws.mul_(s)
+        wc = torch.empty_like(w)
+        wc.copy_(oa.pseudo_quantize_tensor(ws, True, 4, 128) / s)
+        fwd32.append(oa.compute_loss(ref32, [torch.nn.functional.linear(x.float(), wc.float()) for x in xs]))
+        fwd16.append(oa.compute_loss(ref16, [torch.nn.functional.linear(x, wc) for x in xs]))
+        gram.append(oa.gram_loss_single_linear(xs, w, wc))
+    for a, b in zip(fwd32, gram):
+        assert abs(a - b) <= 1e-4 * b, (a, b)
+    for a, b in zip(fwd16, gram):
+        assert abs(a - b) <= 0.05 * b, (a, b)
+    assert min(range(len(gram)), key=gram.__getitem__) == min(range(len(fwd16)), key=fwd16.__getitem__)
