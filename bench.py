@@ -758,7 +758,8 @@ def main():
     cb = None if a.no_cpu else cpu_reference_sample(shape, a.level, a.actorder, a.samples, a.seq)
     line = {"metric": "gptq_seconds_per_8b_model", "value": ms_step / 1e3, "unit": "s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": False,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 activations -> f32 accumulate / f32 solve",
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "dtype_detail": "bf16 activations on the tensor cores -> f32 accumulate; f32 (3xTF32) inverse-Hessian solve and column loop",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb, "parity": parity, "awq": awq, "smoothquant": smooth,
             "gguf_pack": gg, "gguf_smollm2": gs, "dequant": dq, "tgemm": tg}
