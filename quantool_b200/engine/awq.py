@@ -2,9 +2,12 @@
 
 Mirrors UPSTREAM llmcompressor AWQModifier, built by the reference at
 ref/src/quantool/methods/llm_compressor/awq/awq.py:81.  The per-candidate weight
-(scale -> quantize -> dequantize -> unscale) is ONE fused kernel pass (qt_awq_scale_qdq); the
-parent-module forwards are plain torch (cuBLAS / SDPA) and the reconstruction loss is reduced on
-the device (qt_sq_err_sum) - 20 losses come back to the host once per mapping.
+(scale -> quantize -> dequantize -> unscale) is ONE fused kernel pass (qt_awq_scale_qdq).  For a parent that
+is a single Linear (down_proj; o_proj where v -> o applies) the reconstruction loss is evaluated in Gram form,
+tr(D G D^T) with G = X^T X, by one tcgen05 GEMM with a reducing epilogue per grid point
+(qt_awq_scale_qdq_delta + qt_awq_gram_loss): no forward, no materialised output.  The self_attn / mlp parents run
+their forwards through torch (cuBLAS / SDPA) and the loss is reduced on the device (qt_sq_err_sum).  20 losses
+come back to the host once per mapping.
 """
 from dataclasses import dataclass
 from typing import Dict, List, Optional
