@@ -102,6 +102,28 @@ def _load_local_dataset(path: str, sample_size, seed: int, shuffle: bool):
     return rows
 
 
+def _apply_preprocess_fn(dataset, cargs, tokenizer):
+    """`preprocess_fn: "module.func"` is mapped over the rows, with `calibration_config` as keyword arguments and the
+    tokenizer as second positional argument when the function has a `tokenizer` parameter (ref cli.py:284-313).  As in
+    the reference a failing preprocess step is logged and the rows go on unchanged."""
+    import importlib
+    import inspect
+    try:
+        if not hasattr(dataset, "map"):
+            raise TypeError("rows of token ids cannot be preprocessed (use a .json / .jsonl dataset)")
+        module_name, fn_name = cargs.preprocess_fn.rsplit(".", 1)
+        fn = getattr(importlib.import_module(module_name), fn_name)
+        kw = dict(cargs.calibration_config or {})
+        if "tokenizer" in inspect.signature(fn).parameters:
+            if tokenizer is None:
+                raise ValueError(f"Preprocessing function '{cargs.preprocess_fn}' requires a tokenizer, but none was loaded")
+            return dataset.map(lambda ex: fn(ex, tokenizer, **kw), batched=False)
+        return dataset.map(lambda ex: fn(ex, **kw), batched=False)
+    except Exception as e:
+        logger.warning(f"Failed to run preprocess_fn '{cargs.preprocess_fn}': {e}")
+        return dataset
+
+
 def quantize_step(state):
     qargs, margs = state["quant_args"], state["model_args"]
     source = state.get("model_path", margs.model_id)
@@ -119,26 +141,31 @@ def quantize_step(state):
         dataset = None
         if requires:
             tok = state.get("tokenizer")
+            if tok is not None:
+                quantizer.last_tokenizer = tok             # the plugin tokenizes `text` rows and saves it with the model
             if cargs.dataset_path:
-                rows = _load_local_dataset(cargs.dataset_path, cargs.sample_size, cargs.dataset_seed, cargs.shuffle)
+                dataset = _load_local_dataset(cargs.dataset_path, cargs.sample_size, cargs.dataset_seed, cargs.shuffle)
             else:
                 from datasets import load_dataset
-                ds = load_dataset(cargs.dataset_id, cargs.dataset_config or None, split=cargs.split,
-                                  cache_dir=cargs.dataset_cache_dir)
+                dataset = load_dataset(cargs.dataset_id, cargs.dataset_config or None, split=cargs.split,
+                                       cache_dir=cargs.dataset_cache_dir)
                 if cargs.shuffle:
-                    ds = ds.shuffle(seed=cargs.dataset_seed)
+                    dataset = dataset.shuffle(seed=cargs.dataset_seed)
                 if cargs.sample_size:
-                    ds = ds.select(range(min(int(cargs.sample_size), len(ds))))
-                ds = quantizer.prepare_calibration_data(ds, tokenizer=tok)
-                rows = [dict(r) for r in ds]
-            if rows and isinstance(rows[0], dict):
-                if "input_ids" in rows[0]:
-                    rows = [r["input_ids"] for r in rows]
-                else:
-                    if tok is None:
-                        raise ValueError("text calibration rows need a tokenizer")
-                    rows = [tok(r.get("text") or "", truncation=True, max_length=2048)["input_ids"] for r in rows]
-            dataset = rows
+                    dataset = dataset.select(range(min(int(cargs.sample_size), len(dataset))))
+            if dataset and isinstance(dataset, list) and isinstance(dataset[0], dict):
+                import datasets
+                dataset = datasets.Dataset.from_list(dataset)
+            if cargs.preprocess_fn:
+                dataset = _apply_preprocess_fn(dataset, cargs, tok)
+            # chat-template rendering + `text` column (ref cli.py:315-323); token-id rows pass through unchanged
+            dataset = quantizer.prepare_calibration_data(dataset, tokenizer=tok)
+            cols = set(getattr(dataset, "column_names", []) or [])
+            if cols and not ({"text", "input_ids"} & cols):
+                raise ValueError(f"calibration rows carry neither `text` nor `input_ids` (columns: {sorted(cols)})")
+            if "text" in cols and "input_ids" not in cols and tok is None:
+                raise ValueError("text calibration rows need a tokenizer")
+            extra["shuffle_calibration_samples"] = False     # already shuffled above with dataset_seed
             if cargs.sample_size:
                 extra["num_calibration_samples"] = int(cargs.sample_size)
         kwargs = dict(qargs.quantization_config)

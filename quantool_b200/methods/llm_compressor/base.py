@@ -152,21 +152,48 @@ class LLMCompressorQuantizer(BaseQuantizer):
         return False
 
     def prepare_calibration_data(self, dataset, tokenizer=None):
-        """Ensure a `text` column exists (ref base.py:257-345); token-id tensors pass through."""
+        """Calibration rows -> something `quantize(dataset=...)` can tokenize (ref base.py:257-345): with a
+        tokenizer, conversational rows are rendered through its chat template (`chat.render_chat_row`); then every
+        split gets a `text` column, copied from the first of prompt / completion / chosen / rejected / label when it
+        has none.  Token-id tensors and lists of token-id rows pass through; a list of dict rows becomes a
+        `datasets.Dataset` first."""
+        from .chat import render_chat_row
         if isinstance(dataset, torch.Tensor):
             return dataset
-        cols = set(getattr(dataset, "column_names", []) or [])
+        if isinstance(dataset, (list, tuple)):
+            if not dataset or not isinstance(dataset[0], dict):
+                return dataset
+            import datasets
+            dataset = datasets.Dataset.from_list([dict(r) for r in dataset])
+        if tokenizer is not None:
+            try:
+                dataset = dataset.map(lambda ex: render_chat_row(ex, tokenizer), batched=False)
+                self.logger.info("Applied chat template processing to calibration dataset")
+            except Exception as e:
+                self.logger.warning(f"Failed to apply chat template processing: {e}")
+        try:
+            if isinstance(dataset, dict):                      # DatasetDict: every split
+                for split in list(dataset.keys()):
+                    dataset[split] = self._ensure_text_column(dataset[split])
+            else:
+                dataset = self._ensure_text_column(dataset)
+        except Exception as e:  # pragma: no cover
+            self.logger.warning(f"Error while ensuring text column for calibration dataset: {e}")
+        return dataset
+
+    def _ensure_text_column(self, ds):
+        cols = set(getattr(ds, "column_names", []) or [])
         if "text" in cols or "text_target" in cols or "input_ids" in cols:
-            return dataset
+            return ds
         for c in ("prompt", "completion", "chosen", "rejected", "label"):
             if c in cols:
                 try:
-                    dataset = dataset.map(lambda ex, _c=c: {"text": ex.get(_c)}, batched=False)
+                    ds = ds.map(lambda ex, _c=c: {"text": ex.get(_c)}, batched=False)
                     self.logger.info(f"Created 'text' column from fallback '{c}'")
                 except Exception as e:  # pragma: no cover
                     self.logger.warning(f"Failed to create 'text' fallback column from '{c}': {e}")
                 break
-        return dataset
+        return ds
 
     # ------------------------------------------------------------------
     # engine
