@@ -14,24 +14,20 @@ class ExportMixin:
         raise NotImplementedError("Subclasses must implement _save_model_files method")
 
     def _save_model_card(self, save_directory: Union[str, os.PathLike]):
+        """README.md exactly as the reference writes it (ref core/helpers/export_mixin.py:27-39 ->
+        modelcard_generator.py:6-20): huggingface_hub's default model-card template with the template card's fields
+        as YAML front matter - `name`, `tags: [quantization]`, `description`, `metrics` (the hyperparameters),
+        `intended_use`, `limitations`, `citations` - which is what the Hub indexes."""
         card = getattr(self, "template_card", None)
         if card is None:
             self.logger.warning("No template_card attribute found, skipping model card generation")
             return
-        lines = [f"# {card.title}", "", card.description, ""]
-        if card.hyperparameters:
-            lines += ["## Hyperparameters", ""]
-            lines += [f"- **{k}**: {v}" for k, v in card.hyperparameters.items()]
-            lines.append("")
-        if card.intended_use:
-            lines += ["## Intended use", "", card.intended_use, ""]
-        if card.limitations:
-            lines += ["## Limitations", "", card.limitations, ""]
-        if card.citations:
-            lines += ["## Citations", ""] + [f"- {c}" for c in card.citations] + [""]
+        from huggingface_hub import ModelCard, ModelCardData
+        data = ModelCardData(name=card.title, tags=["quantization"], description=card.description,
+                             metrics=card.hyperparameters, intended_use=card.intended_use,
+                             limitations=card.limitations, citations=card.citations)
         path = os.path.join(save_directory, "README.md")
-        with open(path, "w") as f:
-            f.write("\n".join(lines))
+        ModelCard.from_template(card_data=data, template_name=card.title).save(path)
         self.logger.info(f"Model card saved to {path}")
 
     def save_pretrained(self, save_directory: Union[str, os.PathLike]):

@@ -52,54 +52,76 @@ def setup_logging_step(state):
 
 
 def validate_args_step(state):
+    """Method availability and level shape (ref cli.py:163-189, same messages)."""
     qargs = state["quant_args"]
-    if qargs.method not in QuantizerRegistry.list():
-        raise ValueError(f"Unknown quantization method '{qargs.method}'. Available: {QuantizerRegistry.list()}")
+    available = QuantizerRegistry.list()
+    if qargs.method not in available:
+        raise ValueError(f"Quantization method '{qargs.method}' not available. Available methods: {available}")
     cls = QuantizerRegistry._plugins[qargs.method]
-    if isinstance(qargs.quant_level, list) and not cls.supports_multiple_levels:
-        raise ValueError(f"Method '{qargs.method}' does not support multiple quantization levels. "
-                         f"Please specify a single level.")
+    if getattr(qargs, "quant_level", None):
+        if isinstance(qargs.quant_level, list):
+            if not getattr(cls, "supports_multiple_levels", False):
+                raise ValueError(f"Quantization method '{qargs.method}' does not support multiple quantization levels. "
+                                 f"Please specify a single level or choose a method that supports multiple levels.")
+            logger.info(f"Using multiple quantization levels: {qargs.quant_level}")
+        else:
+            logger.info(f"Using quantization level: {qargs.quant_level}")
+    else:
+        logger.warning("No quantization level specified, using method defaults")
     return state
 
 
 def load_model_step(state):
+    """Resolve the model to a local directory (ref cli.py:102-136 downloads; this build is offline: a local
+    directory or the local HF cache) and load the tokenizer the calibration preprocessing may need."""
     margs = state["model_args"]
-    path = margs.model_id
-    if not os.path.isdir(path):
-        try:
-            from huggingface_hub import snapshot_download
-            path = snapshot_download(margs.model_id, cache_dir=margs.cache_dir, revision=margs.revision,
-                                     local_files_only=True)
-        except Exception as e:
-            raise RuntimeError(f"model '{margs.model_id}' is neither a local directory nor in the local HF cache "
-                               f"(this build does not download): {e}")
-    state["model_path"] = path
     try:
-        from transformers import AutoTokenizer
-        state["tokenizer"] = AutoTokenizer.from_pretrained(margs.tokenizer_name or path)
+        path = margs.model_id
+        if not os.path.isdir(path):
+            try:
+                from huggingface_hub import snapshot_download
+                path = snapshot_download(margs.model_id, cache_dir=margs.cache_dir, revision=margs.revision,
+                                         local_files_only=True)
+            except Exception as e:
+                raise RuntimeError(f"model '{margs.model_id}' is neither a local directory nor in the local HF cache "
+                                   f"(this build does not download): {e}")
+        state["model_path"] = path
+        try:
+            from transformers import AutoTokenizer
+            state["tokenizer"] = AutoTokenizer.from_pretrained(margs.tokenizer_name or path, trust_remote_code=True)
+        except Exception as e:
+            logger.warning(f"Could not load tokenizer: {e}")
+            state["tokenizer"] = None
     except Exception as e:
-        logger.warning(f"no tokenizer loaded: {e}")
-        state["tokenizer"] = None
+        raise RuntimeError(f"Model loading failed: {e}") from e
     return state
 
 
-def _load_local_dataset(path: str, sample_size, seed: int, shuffle: bool):
-    if path.endswith(".pt"):
-        ids = torch.load(path)
-        rows = [list(map(int, r)) for r in ids]
+def _load_calibration_dataset(cargs):
+    """`load_in_pipeline: true` (ref cli.py:251-282): the dataset is loaded here - a hub id through
+    `datasets.load_dataset(id, config, split=...)`, a local path as JSON / JSON-lines - then shuffled with
+    `dataset_seed` and cut to `sample_size`, with the same `datasets` calls as the reference so that the same rows
+    arrive in the same order.  Additive: a `.pt` file holding a [n, seq] tensor of token ids."""
+    if cargs.dataset_path and str(cargs.dataset_path).endswith(".pt"):
+        ids = torch.load(cargs.dataset_path)
+        rows = [r for r in torch.as_tensor(ids).long()]
+        if cargs.shuffle:
+            order = torch.randperm(len(rows), generator=torch.Generator().manual_seed(int(cargs.dataset_seed))).tolist()
+            rows = [rows[i] for i in order]
+        if cargs.sample_size:
+            rows = rows[: int(cargs.sample_size)]
+        return [r.tolist() for r in rows]
+    from datasets import load_dataset
+    if cargs.dataset_id:
+        ds = load_dataset(cargs.dataset_id, cargs.dataset_config or None, split=cargs.split,
+                          cache_dir=cargs.dataset_cache_dir)
     else:
-        rows = []
-        with open(path) as f:
-            data = json.load(f) if path.endswith(".json") else [json.loads(l) for l in f if l.strip()]
-        for r in data:
-            rows.append(r)
-    if shuffle:
-        g = torch.Generator().manual_seed(seed)
-        order = torch.randperm(len(rows), generator=g).tolist()
-        rows = [rows[i] for i in order]
-    if sample_size:
-        rows = rows[: int(sample_size)]
-    return rows
+        ds = load_dataset("json", data_files=cargs.dataset_path, split=cargs.split)
+    if cargs.shuffle:
+        ds = ds.shuffle(seed=cargs.dataset_seed)
+    if cargs.sample_size:
+        ds = ds.select(range(min(len(ds), int(cargs.sample_size))))
+    return ds
 
 
 def _apply_preprocess_fn(dataset, cargs, tokenizer):
@@ -125,73 +147,82 @@ def _apply_preprocess_fn(dataset, cargs, tokenizer):
 
 
 def quantize_step(state):
+    """ref cli.py:192-364.  Calibration data reaches the plugin in one of the reference's two ways: loaded and
+    prepared here (`load_in_pipeline: true` -> `dataset=<rows>`), or as a descriptor the plugin resolves itself
+    (`dataset_path=<path>`, or `dataset=<hub id>` + `num_calibration_samples=sample_size`)."""
     qargs, margs = state["quant_args"], state["model_args"]
     source = state.get("model_path", margs.model_id)
     try:
         quantizer = QuantizerRegistry.create(qargs.method, model_id=margs.model_id, **qargs.quantization_config)
         cargs = state.get("calibration_args")
-        requires = bool(quantizer.require_calibration())
-        has_desc = bool(cargs and (cargs.dataset_id or cargs.dataset_path))
+        try:
+            requires = bool(quantizer.require_calibration())
+        except Exception:
+            requires = False
+        has_desc = bool(cargs and (getattr(cargs, "dataset_id", None) or getattr(cargs, "dataset_path", None)))
         if requires and not has_desc:
             raise ValueError(f"Quantization method '{qargs.method}' requires calibration data, but none was provided. "
                              f"Specify 'dataset_id' or 'dataset_path' in calibration_args.")
         if not requires and has_desc:
-            logger.warning(f"Quantization method '{qargs.method}' does not require calibration data; it is ignored.")
+            logger.warning(f"Quantization method '{qargs.method}' does not require calibration data, but "
+                           f"calibration_args were provided. They may be ignored by the method.")
         extra = {}
         dataset = None
-        if requires:
+        if has_desc and getattr(cargs, "load_in_pipeline", False):
             tok = state.get("tokenizer")
-            if tok is not None:
-                quantizer.last_tokenizer = tok             # the plugin tokenizes `text` rows and saves it with the model
-            if cargs.dataset_path:
-                dataset = _load_local_dataset(cargs.dataset_path, cargs.sample_size, cargs.dataset_seed, cargs.shuffle)
-            else:
-                from datasets import load_dataset
-                dataset = load_dataset(cargs.dataset_id, cargs.dataset_config or None, split=cargs.split,
-                                       cache_dir=cargs.dataset_cache_dir)
-                if cargs.shuffle:
-                    dataset = dataset.shuffle(seed=cargs.dataset_seed)
-                if cargs.sample_size:
-                    dataset = dataset.select(range(min(int(cargs.sample_size), len(dataset))))
-            if dataset and isinstance(dataset, list) and isinstance(dataset[0], dict):
-                import datasets
-                dataset = datasets.Dataset.from_list(dataset)
+            dataset = _load_calibration_dataset(cargs)
             if cargs.preprocess_fn:
                 dataset = _apply_preprocess_fn(dataset, cargs, tok)
-            # chat-template rendering + `text` column (ref cli.py:315-323); token-id rows pass through unchanged
-            dataset = quantizer.prepare_calibration_data(dataset, tokenizer=tok)
-            cols = set(getattr(dataset, "column_names", []) or [])
-            if cols and not ({"text", "input_ids"} & cols):
-                raise ValueError(f"calibration rows carry neither `text` nor `input_ids` (columns: {sorted(cols)})")
-            if "text" in cols and "input_ids" not in cols and tok is None:
-                raise ValueError("text calibration rows need a tokenizer")
-            extra["shuffle_calibration_samples"] = False     # already shuffled above with dataset_seed
-            if cargs.sample_size:
-                extra["num_calibration_samples"] = int(cargs.sample_size)
-        kwargs = dict(qargs.quantization_config)
+            try:
+                # chat-template rendering + `text` column (ref cli.py:315-328); token-id rows pass through unchanged
+                dataset = (quantizer.prepare_calibration_data(dataset, tokenizer=tok) if tok is not None
+                           else quantizer.prepare_calibration_data(dataset))
+            except Exception as e:
+                logger.warning(f"Quantizer-specific calibration preparation failed: {e}")
+        elif has_desc:
+            if getattr(cargs, "dataset_id", None):
+                # the reference also sets this key and then passes `dataset=None` explicitly, which makes its own
+                # call fail ("got multiple values for keyword argument 'dataset'"); the evident intent is kept
+                dataset = cargs.dataset_id
+                if getattr(cargs, "sample_size", None):
+                    extra["num_calibration_samples"] = cargs.sample_size
+            else:
+                extra["dataset_path"] = cargs.dataset_path
+        kwargs = dict(qargs.quantization_config or {})
         kwargs.update(extra)
-        if dataset is not None:
-            kwargs["dataset"] = dataset
-        state["quantized_artifact"] = quantizer.quantize(model=source, level=qargs.quant_level, **kwargs)
+        state["quantized_output"] = quantizer.quantize(model=source, level=qargs.quant_level, dataset=dataset, **kwargs)
         state["quantizer"] = quantizer
     except Exception as e:
-        raise RuntimeError(f"Quantization failed: {e}") from e
+        logger.error(f"Quantization failed: {e}")
+        raise RuntimeError(f"Failed to quantize model using {qargs.method}: {e}") from e
     return state
 
 
 def model_card_step(state):
-    state["quantizer"].save_model_card(state["export_args"].output_path)
+    """README from the quantizer's template card; a failure is logged, not fatal (ref cli.py:435-444)."""
+    try:
+        state["quantizer"].save_model_card(save_directory=state["export_args"].output_path)
+    except Exception as e:
+        logger.warning(f"Failed to check README generation capability: {e}")
     return state
 
 
 def save_step(state):
+    """ref cli.py:369-432: push when `push_to_hub` and `repo_id` are both set, else save locally."""
     eargs = state["export_args"]
     q = state["quantizer"]
-    if eargs.push_to_hub:
-        q.push_to_hub(repo_id=eargs.repo_id, private=eargs.private,
-                      commit_message=f"Upload {state['quant_args'].method} quantized model")
-    else:
-        q.save_pretrained(eargs.output_path)
+    try:
+        if getattr(eargs, "push_to_hub", False) and getattr(eargs, "repo_id", None):
+            q.push_to_hub(repo_id=eargs.repo_id, private=getattr(eargs, "private", None),
+                          commit_message=f"Upload quantized model using {state['quant_args'].method}")
+        else:
+            output_path = eargs.output_path
+            if not output_path:
+                output_path = f"./output/{state['quant_args'].method}_{state['model_args'].model_id.replace('/', '_')}"
+            q.save_pretrained(save_directory=output_path)
+    except Exception as e:
+        logger.error(f"Failed to save model: {e}")
+        raise RuntimeError(f"Model saving failed: {e}") from e
     return state
 
 

@@ -58,7 +58,15 @@ class GGUF(BaseQuantizer):
     CONVERT_OUTTYPES = {"f32", "f16", "bf16", "q8_0", "tq1_0", "tq2_0", "auto"}
 
     def __init__(self, *args, llama_cpp_path: Optional[Union[str, Path]] = None, **kwargs) -> None:
-        super().__init__(*args, **kwargs)
+        # The CLI hands the whole `quantization_config` to the constructor AND to quantize() (ref cli.py:201-203,
+        # 345-350).  In the reference any key other than `llama_cpp_path` falls through to object.__init__ and raises
+        # TypeError (tests/golden/cli_traces.json, case gguf_levels_and_ignored_calibration); here such keys - e.g.
+        # `output_dir`, which quantize() consumes - are left to quantize().
+        if "model_id" in kwargs:
+            args = (kwargs.pop("model_id"),) + tuple(args)
+        super().__init__(*args)
+        if kwargs:
+            self.logger.info(f"constructor ignores quantization_config keys {sorted(kwargs)} (quantize() receives them)")
         self.llama_cpp_path = Path(llama_cpp_path) if llama_cpp_path else None   # accepted, unused
         self.use_module_import = True
         self._check_dependencies()

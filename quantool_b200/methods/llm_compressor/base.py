@@ -226,6 +226,8 @@ class LLMCompressorQuantizer(BaseQuantizer):
         shuffle = oneshot_kwargs.get("shuffle_calibration_samples", True)
         if ds is None and oneshot_kwargs.get("dataset_path"):
             ds = self._load_dataset_path(oneshot_kwargs["dataset_path"], oneshot_kwargs)
+        if isinstance(ds, str):
+            ds = self._load_dataset_id(ds, oneshot_kwargs)
         if ds is None:
             raise ValueError("no calibration data: pass `dataset` (token-id tensor, list of token lists, or a "
                              "datasets.Dataset with `input_ids` or `text`) or a local `dataset_path`")
@@ -258,6 +260,19 @@ class LLMCompressorQuantizer(BaseQuantizer):
         if len({int(r.numel()) for r in rows}) == 1:
             return torch.stack(rows).contiguous()
         return rows
+
+    def _load_dataset_id(self, name: str, kw: Dict[str, Any]):
+        """`dataset=<hub id>` (what the reference's CLI passes without `load_in_pipeline`, ref cli.py:334-338, and
+        llm-compressor resolves through `datasets`): served from the local `datasets` cache when it is there."""
+        import datasets
+        split = kw.get("splits") or "train"
+        split = split if isinstance(split, str) else next(iter(split.values() if isinstance(split, dict) else split))
+        try:
+            ds = datasets.load_dataset(name, kw.get("dataset_config_name") or None, split=split)
+        except Exception as e:
+            raise ValueError(f"calibration dataset {name!r} could not be loaded (hub datasets need network access or "
+                             f"a populated local cache; pass `dataset_path` or a loaded dataset instead): {e}") from e
+        return self.prepare_calibration_data(ds)
 
     def _load_dataset_path(self, path: str, kw: Dict[str, Any]):
         """Local calibration files (`dataset_path`; the reference hands this key to oneshot, ref base.py:118-124):

@@ -8,6 +8,7 @@ Recorded per case: the keyword arguments that reach `llmcompressor.oneshot` (dat
 `input_ids` columns, in order) or the llama.cpp command lines, the state keys the step sets, and exceptions
 (type and message).  tests/test_cli_golden.py replays the same configurations on quantool_b200's CLI.
 Run:  python tests/golden/make_cli_golden.py"""
+import hashlib
 import json
 import os
 import sys
@@ -163,7 +164,7 @@ def main():
                                ExportArguments, CommonArguments, LoggingArguments))
     names = ("model_args", "quant_args", "calibration_args", "evaluation_args", "export_args", "common_args", "logging_args")
     tok = chat_tokenizer(work)
-    gold = {"template": TEMPLATE, "datasets": DATASETS, "fns": FNS, "quantize": [], "validate": []}
+    gold = {"template": TEMPLATE, "datasets": DATASETS, "fns": FNS, "quantize": [], "validate": [], "readme": {}}
 
     def state_for(cfg, out):
         full = subst({**BASE, **cfg}, {"<DATA>": data, "<OUT>": out, "<LLAMA_CPP>": lcp})
@@ -204,6 +205,9 @@ def main():
             st = rcli.model_card_step(st)
             st = rcli.save_step(st)
             rec["saved"] = sorted(os.listdir(st["export_args"].output_path))
+            readme = open(os.path.join(st["export_args"].output_path, "README.md")).read()
+            rec["readme_sha256"] = hashlib.sha256(readme.encode()).hexdigest()
+            gold["readme"].setdefault(st["quant_args"].method, readme)
         except Exception as e:
             rec["save_raises"], rec["save_message"] = type(e).__name__, mpg.jsonable(str(e), tags)
         gold["quantize"].append(rec)

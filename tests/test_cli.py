@@ -62,7 +62,7 @@ def test_validate_and_calibration_errors(tmp_path):
     p = _cfg(tmp_path, model="m", method="nope", level="null", qcfg="  {}", dataset="null", out="o")
     st = dict(zip(("model_args", "quant_args", "calibration_args", "eval", "export_args", "common_args", "logging_args"),
                   cli.parse([p])))
-    with pytest.raises(ValueError, match="Unknown quantization method"):
+    with pytest.raises(ValueError, match="Quantization method 'nope' not available. Available methods:"):
         cli.validate_args_step(st)
     st["quant_args"].method = "awq"
     st["quant_args"].quant_level = ["W4A16", "W8A16"]
@@ -90,11 +90,16 @@ def test_quantize_step_routes_config_twice_like_the_reference(tmp_path):
         return "outdir"
     with patch.object(GPTQ, "quantize", fake):
         st = cli.quantize_step(st)
-    assert st["quantized_artifact"] == "outdir" and seen["model"] == "local/dir" and seen["level"] == "W4A16"
-    assert seen["method_kwargs"] == {"actorder": "group"} and seen["max_seq_length"] == 8
-    assert seen["num_calibration_samples"] == 6 and len(seen["dataset"]) == 6
+        assert st["quantized_output"] == "outdir" and seen["model"] == "local/dir" and seen["level"] == "W4A16"
+        assert seen["method_kwargs"] == {"actorder": "group"} and seen["max_seq_length"] == 8
+        # without `load_in_pipeline` the plugin gets the descriptor and resolves it itself (ref cli.py:330-340)
+        assert seen["dataset"] is None and seen["dataset_path"] == str(ds) and "num_calibration_samples" not in seen
+        # with it, the rows are loaded, shuffled (dataset_seed) and cut to sample_size here
+        st["calibration_args"].load_in_pipeline = True
+        seen.clear()
+        cli.quantize_step(st)
+    assert "dataset_path" not in seen and len(seen["dataset"]) == 6
     assert len(seen["dataset"][0]["input_ids"]) == 12            # dict rows travel as a datasets.Dataset
-    assert seen["shuffle_calibration_samples"] is False          # the CLI shuffled already (dataset_seed)
 
 
 @pytest.mark.gpu
@@ -216,16 +221,18 @@ def test_cli_chat_rows_and_preprocess_fn(tmp_path):
     names = ("model_args", "quant_args", "calibration_args", "eval", "export_args", "common_args", "logging_args")
     st = dict(zip(names, cli.parse([p])))
     st["model_path"], st["tokenizer"] = "local/dir", _chat_tokenizer(tmp_path)
+    st["calibration_args"].load_in_pipeline = True
+    st["calibration_args"].shuffle = False
     seen = {}
     from quantool_b200.methods.llm_compressor.awq import AWQ
 
     def fake(self, model, level=None, **kw):
         seen.clear()
-        seen.update(kw, tok=self.last_tokenizer)
+        seen.update(kw)
         return "outdir"
     with patch.object(AWQ, "quantize", fake):
         cli.quantize_step(st)
-        assert seen["dataset"]["text"] == ["<|user|>hi<|end|><|assistant|>yo<|end|>"] * 6 and seen["tok"] is st["tokenizer"]
+        assert seen["dataset"]["text"] == ["<|user|>hi<|end|><|assistant|>yo<|end|>"] * 6
         # preprocess_fn = "module.func", calibration_config as keyword arguments, tokenizer injected when asked for
         plain = tmp_path / "plain.jsonl"
         plain.write_text("\n".join(json.dumps({"text": f"row {i}"}) for i in range(8)))
@@ -242,12 +249,14 @@ def test_cli_chat_rows_and_preprocess_fn(tmp_path):
         st["calibration_args"].preprocess_fn = "test_cli.does_not_exist"
         cli.quantize_step(st)
         assert seen["dataset"]["text"][0] == "row 0"
-        # rows with neither text nor token ids are an error, not an empty calibration set
+        # rows with neither text nor token ids
         junk = tmp_path / "junk.jsonl"
         junk.write_text(json.dumps({"foo": 1}))
         st["calibration_args"].dataset_path, st["calibration_args"].preprocess_fn = str(junk), None
-        with pytest.raises(RuntimeError, match="neither `text` nor `input_ids`"):
-            cli.quantize_step(st)
+        cli.quantize_step(st)
+        assert seen["dataset"].column_names == ["foo"]      # passed on as it is; the plugin rejects it (below)
+    with pytest.raises(ValueError, match="unsupported calibration dataset"):
+        AWQ(model_id="m")._token_ids({"dataset": seen["dataset"]}, None)
 
 
 def test_chat_rows_equal_the_reference_golden(tmp_path):
