@@ -3,8 +3,11 @@
 ref/src/quantool/methods/llm_compressor/base.py:162): LlamaRMSNorm (fp32 statistics, weight multiply in
 the model dtype), apply_rotary_pos_emb (`q*cos + rotate_half(q)*sin`), eager attention through SDPA,
 LlamaMLP (`down(silu(gate(x)) * up(x))`).  The product path (quantool_b200/engine/llama.py) runs the same
-expression with fused CUDA kernels; tests compare the two.  Parity unpinned (transformers itself is not
-imported here; it is installed at a different version than the reference pins).
+expression with fused CUDA kernels; tests compare the two.  PINNED against the installed transformers
+(5.5; the reference pins 4.56.2): tests/test_oracle_cpu.py::test_forward_restatement_equals_transformers_llama -
+in fp32 the hidden states after every layer and the four captured Linear inputs are bit-exact with a
+LlamaForCausalLM built from the same config and weights (plain and llama3-scaled rope); in bf16 they differ only
+behind the library attention kernel, by rounding of its accumulation.
 """
 from typing import Dict, Optional
 
