@@ -344,3 +344,62 @@ def test_forward_restatement_equals_transformers_llama(dtype, rope_scaling):
         if l < L - 1:
             close(h, out.hidden_states[l + 1], ("hidden", l))
     close(lf.rms_norm(h, sd["model.norm.weight"], shape.rms_norm_eps), out.hidden_states[-1], "final norm")
+
+
+@pytest.mark.parametrize("qtype,limit", [("Q4_0", 0.002), ("Q4_1", 0.002), ("Q5_0", 0.002), ("Q5_1", 0.002), ("Q8_0", 0.002),
+                                         ("Q4_K", 0.002), ("Q5_K", 0.002), ("Q6_K", 0.002), ("IQ4_NL", 0.002),
+                                         ("Q3_K", 0.0040), ("Q2_K", 0.0075)])
+def test_ggml_round_trip_error_within_llama_cpp_acceptance_limits(qtype, limit):
+    """llama.cpp's own acceptance test for its block quantizers (tests/test-quantize-fns.cpp, upstream source absent
+    here, restated): 32*128 values `0.1 + 2*cos(i)` are quantized and dequantized and sqrt(sum of squared errors) / n
+    must stay below MAX_QUANTIZATION_TOTAL_ERROR = 0.002 (3-bit types 0.0040, 2-bit types 0.0075).  The CUDA packers
+    are bit-exact with this oracle, so the limits carry over to them."""
+    from oracle import ggml_quants as oq
+    n = 32 * 128
+    x = (np.float32(0.1) + np.float32(2.0) * np.cos(np.arange(n, dtype=np.float32))).astype(np.float32).reshape(1, n)
+    y = oq.dequantize(oq.quantize(x, qtype), qtype, n)
+    err = float(np.sqrt(((x - y).astype(np.float64) ** 2).sum()) / n)
+    assert 0.0 < err < limit, err
+
+
+def test_smoothing_and_awq_scales_preserve_the_block_function():
+    """Size-independent property of rows a8 / a9: folding per-channel scales into the preceding norm (weight / s) and
+    the consuming Linears (W * s[None, :]) leaves `Linear(norm(x))` unchanged - checked in fp64 on the oracle's
+    `apply_smoothing` / `apply_scales` with the scales its own formulas produce, for the norm -> {q, k, v} and the
+    Linear -> Linear (`up_proj -> down_proj`, scales applied to the LAST rows of the producer) mappings."""
+    from oracle import awq as oa
+    from oracle import llama_forward as lf
+    from oracle import smoothquant as osq
+    g = torch.Generator().manual_seed(0)
+    K, T = 64, 200
+    x = torch.randn((T, K), generator=g, dtype=torch.float64) * 3
+    norm_w = torch.rand((K,), generator=g, dtype=torch.float64) + 0.5
+    ws = [torch.randn((n, K), generator=g, dtype=torch.float64) * 0.05 for n in (64, 32, 32)]
+    ref = [torch.nn.functional.linear(lf.rms_norm(x, norm_w, 1e-5), w) for w in ws]
+    xn = lf.rms_norm(x, norm_w, 1e-5)
+    mn, mx = osq.update_channel_minmax(xn, None, None)
+    s = osq.smoothing_scales(mn, mx, ws, 0.5).double()
+    assert s.shape == (K,) and bool((s > 0).all()) and s.max() / s.min() > 1.5      # a real, non-trivial rescaling
+    nw, w2 = norm_w.clone(), [w.clone() for w in ws]
+    osq.apply_smoothing(nw, w2, s)
+    for r, w in zip(ref, w2):
+        assert torch.allclose(torch.nn.functional.linear(lf.rms_norm(x, nw, 1e-5), w), r, rtol=1e-10, atol=1e-12)
+    # AWQ: scales from its own grid formula, norm -> Linears
+    x_mean = xn.abs().mean(0).float()
+    w_mean = oa.weight_mean([w.float() for w in ws], 32)
+    s = oa.candidate_scales(x_mean, w_mean, 0.5).double()
+    nw, w2 = norm_w.clone(), [w.clone() for w in ws]
+    oa.apply_scales(nw, w2, s)
+    for r, w in zip(ref, w2):
+        assert torch.allclose(torch.nn.functional.linear(lf.rms_norm(x, nw, 1e-5), w), r, rtol=1e-10, atol=1e-12)
+    # AWQ: Linear -> Linear (up_proj -> down_proj): the producer's output rows are divided
+    I = 96
+    up = torch.randn((I, K), generator=g, dtype=torch.float64) * 0.05
+    down = torch.randn((K, I), generator=g, dtype=torch.float64) * 0.05
+    gate_act = torch.rand((T, I), generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.linear(gate_act * torch.nn.functional.linear(x, up), down)
+    s = (torch.rand((I,), generator=g, dtype=torch.float64) + 0.5)
+    up2, down2 = up.clone(), down.clone()
+    oa.apply_scales(up2, [down2], s)
+    assert torch.allclose(torch.nn.functional.linear(gate_act * torch.nn.functional.linear(x, up2), down2), ref,
+                          rtol=1e-10, atol=1e-12)
