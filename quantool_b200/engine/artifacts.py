@@ -55,7 +55,12 @@ class QuantizedModel:
         self.source_dir = source_dir
         self.writer = writer        # multi-process runs: rank 0 holds the tensors and is the only one that writes
 
-    def save_pretrained(self, dest: str, save_compressed: bool = True, **_):
+    def save_pretrained(self, dest: str, save_compressed: bool = True, max_shard_size="5GB", **_):
+        """config.json + weights laid out as `PreTrainedModel.save_pretrained` does for the reference
+        (transformers 4.56.2 as pinned at ref/pyproject.toml:26-30: `max_shard_size="5GB"`): one `model.safetensors`
+        when everything fits into a shard, else `model-0000i-of-0000n.safetensors` + `model.safetensors.index.json`,
+        split by huggingface_hub's `split_torch_state_dict_into_shards` (the function transformers itself calls)."""
+        from huggingface_hub import split_torch_state_dict_into_shards
         from safetensors.torch import save_file
         if not self.writer:
             return
@@ -64,8 +69,14 @@ class QuantizedModel:
         cfg["quantization_config"] = self.qconfig
         with open(os.path.join(dest, "config.json"), "w") as f:
             json.dump(cfg, f, indent=2)
-        save_file({k: v.contiguous() for k, v in self.tensors.items()}, os.path.join(dest, "model.safetensors"),
-                  metadata={"format": "pt"})
+        tensors = {k: v.contiguous() for k, v in self.tensors.items()}
+        split = split_torch_state_dict_into_shards(tensors, filename_pattern="model{suffix}.safetensors",
+                                                   max_shard_size=max_shard_size)
+        for fn, keys in split.filename_to_tensors.items():
+            save_file({k: tensors[k] for k in keys}, os.path.join(dest, fn), metadata={"format": "pt"})
+        if split.is_sharded:
+            with open(os.path.join(dest, "model.safetensors.index.json"), "w") as f:
+                json.dump({"metadata": split.metadata, "weight_map": split.tensor_to_filename}, f, indent=2, sort_keys=True)
         if self.source_dir and os.path.isdir(self.source_dir):
             for fn in os.listdir(self.source_dir):
                 if fn.startswith("tokenizer") or fn in ("special_tokens_map.json", "generation_config.json", "vocab.json",

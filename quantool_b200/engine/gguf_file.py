@@ -93,16 +93,26 @@ def _permute_qk(w: torch.Tensor, n_head: int) -> torch.Tensor:
 
 
 def load_hf_model(model_path: str):
-    """(hf config dict, {name: host tensor}) from a local HF directory with safetensors shards."""
+    """(hf config dict, {name: host tensor}) from a local HF directory: `model.safetensors`, the shards listed in
+    `model.safetensors.index.json` (or every `*.safetensors` file when there is no index), else `pytorch_model*.bin`."""
     from safetensors.torch import load_file
     with open(os.path.join(model_path, "config.json")) as f:
         cfg = json.load(f)
     sd = {}
-    files = sorted(f for f in os.listdir(model_path) if f.endswith(".safetensors"))
-    if not files:
-        raise FileNotFoundError(f"no .safetensors files under {model_path}")
+    index = os.path.join(model_path, "model.safetensors.index.json")
+    if os.path.exists(index):
+        with open(index) as f:
+            files = sorted(set(json.load(f)["weight_map"].values()))
+    else:
+        files = sorted(f for f in os.listdir(model_path) if f.endswith(".safetensors"))
     for fn in files:
         sd.update(load_file(os.path.join(model_path, fn)))
+    if not files:
+        bins = sorted(f for f in os.listdir(model_path) if f.startswith("pytorch_model") and f.endswith(".bin"))
+        if not bins:
+            raise FileNotFoundError(f"no .safetensors or pytorch_model*.bin files under {model_path}")
+        for fn in bins:
+            sd.update(torch.load(os.path.join(model_path, fn), map_location="cpu", weights_only=True))
     return cfg, sd
 
 

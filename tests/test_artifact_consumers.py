@@ -104,6 +104,32 @@ def test_compressed_tensors_artifact_loads_in_transformers(tmp_path, level, acto
     check_loads_in_transformers(out, fake, 1e-2, shape.vocab_size)
 
 
+def test_sharded_artifact_loads_in_transformers(tmp_path):
+    """Above the shard limit (5 GB by default, the reference's transformers 4.56.2 default; 200 kB here) the writer
+    emits `model-0000i-of-0000n.safetensors` + `model.safetensors.index.json` like `save_pretrained` does, and the
+    HF loader reassembles the packed tensors from the shards."""
+    from quantool_b200.engine import artifacts, llama, schemes
+    shape = tiny_shape()
+    sd = llama.random_state_dict(shape, seed=3)
+    tensors, fake = oracle_artifact(shape, sd, "W4A16", "group")
+    fmt = artifacts.artifact_format(schemes.resolve("W4A16", "group").num_bits, "W4A16")
+    qm = artifacts.QuantizedModel(shape.to_hf_config(), tensors, artifacts.quantization_config("W4A16", "group", fmt))
+    out = str(tmp_path / "out")
+    qm.save_pretrained(out, max_shard_size=200_000)
+    files = sorted(os.listdir(out))
+    shards = [f for f in files if f.startswith("model-") and f.endswith(".safetensors")]
+    assert len(shards) >= 2 and "model.safetensors" not in files and "model.safetensors.index.json" in files
+    assert shards[0] == f"model-00001-of-{len(shards):05d}.safetensors"
+    index = json.load(open(os.path.join(out, "model.safetensors.index.json")))
+    assert set(index["weight_map"]) == set(tensors) and set(index["weight_map"].values()) == set(shards)
+    assert index["metadata"]["total_size"] == sum(t.numel() * t.element_size() for t in tensors.values())
+    check_loads_in_transformers(out, fake, 1e-2, shape.vocab_size)
+    # and the loader of this repo reads a sharded directory back
+    from quantool_b200.engine import gguf_file
+    _, back = gguf_file.load_hf_model(out)
+    assert set(back) == set(tensors) and all(torch.equal(back[k], tensors[k]) for k in tensors)
+
+
 def unpermute_qk(w, n_head):
     """Inverse of gguf_file._permute_qk (what a GGUF consumer applies to attn_q / attn_k)."""
     out_dim = w.shape[0]
