@@ -403,3 +403,13 @@ def test_smoothing_and_awq_scales_preserve_the_block_function():
     oa.apply_scales(up2, [down2], s)
     assert torch.allclose(torch.nn.functional.linear(gate_act * torch.nn.functional.linear(x, up2), down2), ref,
                           rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no gcc")
+def test_lean_block_kernel_division_is_correctly_rounded(tmp_path):
+    """tests/div_by_check.c: the reciprocal-based division of `gptq_block128_kernel` returns the bits of `w / s` for
+    every reciprocal seed the hardware instruction may produce (5 M random pairs x 3 seeds, IEEE fmaf on the host)."""
+    exe = str(tmp_path / "div_by_check")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "div_by_check.c"), "-lm"])
+    r = subprocess.run([exe, "5000000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout + r.stderr
