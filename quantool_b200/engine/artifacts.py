@@ -17,15 +17,28 @@ import torch
 
 
 def quantization_config(level: str, actorder: Optional[str], fmt: str, ignore=("lm_head",)) -> dict:
+    """The `quantization_config` block as the installed compressed-tensors writes it
+    (`ModelCompressor.update_config`, CT/compressors/model_compressors/model_compressor.py:177-213): the pydantic dump
+    of the config - the group carries its own `format` - plus `version`, `quant_method` and the (empty)
+    `sparsity_config` / `transform_config` entries of this CT version.
+    tests/test_artifact_consumers.py compares it with that writer's own output."""
     from compressed_tensors import __version__ as ct_version
     from compressed_tensors.quantization import QuantizationConfig, preset_name_to_scheme
     scheme = preset_name_to_scheme(level, ["Linear"])
     if actorder is not None and scheme.weights is not None:
         scheme.weights.actorder = "static" if actorder == "weight" else actorder
+    if "format" in type(scheme).model_fields:
+        scheme.format = fmt
     qc = QuantizationConfig(config_groups={"group_0": scheme}, quant_method="compressed-tensors", format=fmt,
                             quantization_status="compressed", ignore=list(ignore))
     d = qc.model_dump(mode="json")
     d["version"] = ct_version
+    try:
+        from compressed_tensors.base import SPARSITY_CONFIG_NAME, TRANSFORM_CONFIG_NAME
+        d.setdefault(SPARSITY_CONFIG_NAME, {})
+        d.setdefault(TRANSFORM_CONFIG_NAME, {})
+    except ImportError:       # older compressed-tensors: no such entries
+        pass
     return d
 
 
@@ -68,7 +81,7 @@ class QuantizedModel:
         cfg = dict(self.hf_config)
         cfg["quantization_config"] = self.qconfig
         with open(os.path.join(dest, "config.json"), "w") as f:
-            json.dump(cfg, f, indent=2)
+            json.dump(cfg, f, indent=2, sort_keys=True)            # transformers and CT both write sorted keys
         tensors = {k: v.contiguous() for k, v in self.tensors.items()}
         split = split_torch_state_dict_into_shards(tensors, filename_pattern="model{suffix}.safetensors",
                                                    max_shard_size=max_shard_size)

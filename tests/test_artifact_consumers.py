@@ -104,6 +104,38 @@ def test_compressed_tensors_artifact_loads_in_transformers(tmp_path, level, acto
     check_loads_in_transformers(out, fake, 1e-2, shape.vocab_size)
 
 
+@pytest.mark.parametrize("level,actorder", [("W4A16", "group"), ("W4A16", "weight"), ("W4A16_ASYM", None), ("W8A8", None),
+                                            ("W8A16", None), ("W4A8", None)])
+def test_quantization_config_block_equals_compressed_tensors_own_writer(tmp_path, level, actorder):
+    """The `quantization_config` block against the installed compressed-tensors' own writer: a tiny HF Llama gets the
+    preset scheme applied, is compressed by `ModelCompressor.compress_model` and described by
+    `ModelCompressor.update_config` - what `save_pretrained(save_compressed=True)` runs for the reference
+    (ref/src/quantool/methods/llm_compressor/base.py:188) - and the resulting block must be ours, key for key."""
+    from compressed_tensors.compressors import ModelCompressor
+    from compressed_tensors.quantization import (QuantizationConfig, QuantizationStatus, apply_quantization_config,
+                                                 preset_name_to_scheme)
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from quantool_b200.engine import artifacts, llama, schemes
+    shape = llama.LlamaShape(128, 256, 1, 2, 1, 64, rope_theta=10000.0, tie_word_embeddings=True)
+    cfg = LlamaConfig(**{k: v for k, v in shape.to_hf_config().items() if k not in ("model_type", "architectures")})
+    model = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    scheme = preset_name_to_scheme(level, ["Linear"])
+    if actorder:
+        scheme.weights.actorder = "static" if actorder == "weight" else actorder
+    apply_quantization_config(model, QuantizationConfig(config_groups={"group_0": scheme}, ignore=["lm_head"]))
+    for mod in model.modules():
+        if hasattr(mod, "quantization_status"):
+            mod.quantization_status = QuantizationStatus.FROZEN
+    compressor = ModelCompressor.from_pretrained_model(model)
+    model.config.save_pretrained(str(tmp_path))
+    compressor.compress_model(model)
+    compressor.update_config(str(tmp_path))
+    want = json.load(open(tmp_path / "config.json"))["quantization_config"]
+    a = schemes.resolve(level, actorder)
+    fmt = artifacts.artifact_format(a.num_bits, level)
+    assert artifacts.quantization_config(level, actorder, fmt) == want
+
+
 def test_sharded_artifact_loads_in_transformers(tmp_path):
     """Above the shard limit (5 GB by default, the reference's transformers 4.56.2 default; 200 kB here) the writer
     emits `model-0000i-of-0000n.safetensors` + `model.safetensors.index.json` like `save_pretrained` does, and the
