@@ -5,6 +5,7 @@ llm-compressor is not installed and has no source on this box: restated from SUR
 (`_accumulate_mean`, `_compute_best_scale`, `_pseudo_quantize_tensor`, `_compute_loss`, smoothing
 application).  Tensor dtypes are what torch would produce: weights and `w_mean` in the model
 dtype, `x_mean` and the candidate scales in fp32, losses as python floats.
+Property pinned in tests/test_oracle_cpu.py: folding the scales leaves the block's function unchanged (fp64).
 PARITY UNPINNED: the reference's tests hold no AWQ vectors; dtype choices that
 SURVEY.md does not state (x_mean fp32, scales fp32) are this restatement's and are documented in
 DESIGN.md.

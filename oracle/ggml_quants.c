@@ -13,14 +13,15 @@
  * (`quantize_row_<type>_ref`, `make_qkx2_quants`, `make_qx_quants`, `nearest_int`) as
  * recorded in SURVEY.md §D.1-§D.5.
  *
- * Parity pins (tests/test_oracle_gguf.py):
+ * Parity pins (tests/test_oracle_cpu.py):
  *   - Q8_0 / Q4_0 / Q4_1 / Q5_0 / Q5_1 packed bytes == gguf-py `gguf.quants.quantize`
  *     (GGUFPY/quants.py:220-239, 291-311, 378-393; "bit-exact same results as reference
  *     implementation in ggml-quants.c") and the sha256 KATs in SURVEY.md §8c.
  *   - IQ4_NL / Q2_K / Q3_K / Q4_K / Q5_K / Q6_K: PARITY UNPINNED against llama.cpp itself (no quantize twin on
  *     disk); pinned only by (a) an independent numpy restatement (oracle/ggml_quants_np.py)
  *     agreeing byte-for-byte and (b) gguf-py's dequantizers (GGUFPY/quants.py:475-572)
- *     reading the packed layout back to within the format's error.
+ *     reading the packed layout back to within the format's error, and (c) llama.cpp's own
+ *     acceptance limits for the round-trip error of each type (tests/test-quantize-fns.cpp, restated).
  *
  * Arithmetic contract: strict IEEE fp32, evaluation order as written, NO fused
  * multiply-add (build with -ffp-contract=off), fp16 conversion = round-to-nearest-even.

@@ -5,6 +5,7 @@ ref/src/quantool/methods/llm_compressor/smoothquant/smoothquant.py:77-84.
 llm-compressor is not installed and has no source on this box: restated from SURVEY.md §C
 (`_calculate_smoothing_scales`, `_apply_smoothing`, the per-channel min/max forward hook).
 All arithmetic runs in the tensors' own dtype exactly as torch would (bf16 tensors -> bf16 ops).
+Property pinned in tests/test_oracle_cpu.py: folding the scales leaves the block's function unchanged (fp64).
 PARITY UNPINNED: the reference's tests hold no SmoothQuant vectors.
 """
 from typing import List, Optional, Tuple
