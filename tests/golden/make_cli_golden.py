@@ -65,6 +65,10 @@ CASES = [
     {"id": "gguf_levels_and_ignored_calibration", "cfg": {"method": "gguf", "quant_level": ["Q4_K_M", "Q8_0"], "dataset_path": "<DATA>/text.jsonl",
                                                           "quantization_config": {"llama_cpp_path": "<LLAMA_CPP>", "output_dir": "<OUT>/gg"}}},
     {"id": "gguf_no_level", "cfg": {"method": "gguf", "quant_level": None, "quantization_config": {"llama_cpp_path": "<LLAMA_CPP>"}}},
+    {"id": "push_to_hub", "cfg": {"dataset_path": "<DATA>/text.jsonl", "push_to_hub": True, "repo_id": "org/My-Model-W4A16", "private": True}},
+    {"id": "push_to_hub_without_repo_id_saves_locally", "cfg": {"dataset_path": "<DATA>/text.jsonl", "push_to_hub": True, "repo_id": None}},
+    {"id": "gguf_push_to_hub", "cfg": {"method": "gguf", "quant_level": "Q4_0", "quantization_config": {"llama_cpp_path": "<LLAMA_CPP>"},
+                                       "push_to_hub": True, "repo_id": "org/My-Model-GGUF", "private": False}},
 ]
 VALIDATE_CASES = [
     {"id": "unknown_method", "cfg": {"method": "nope"}},
@@ -160,6 +164,20 @@ def main():
         target = cmd[cmd.index("--outfile") + 1] if "--outfile" in cmd else cmd[2]
         open(target, "w").write("gguf")
     ref_gguf.run_command = run_command
+    import quantool.core.helpers.export_mixin as ref_export
+    hub = []
+
+    def create_repo(**kw):
+        hub.append({"call": "create_repo", "kwargs": kw})
+        return "https://huggingface.co/" + kw["repo_id"]
+
+    def upload_folder(**kw):
+        kw = dict(kw)
+        kw["folder_files"] = sorted(os.listdir(kw.pop("folder_path")))
+        hub.append({"call": "upload_folder", "kwargs": kw})
+        return "commit-url"
+    ref_export.create_repo, ref_export.upload_folder = create_repo, upload_folder
+    os.environ.pop("HF_TOKEN", None)
     parser = HfArgumentParser((ModelArguments, QuantizationArguments, CalibrationArguments, EvaluationArguments,
                                ExportArguments, CommonArguments, LoggingArguments))
     names = ("model_args", "quant_args", "calibration_args", "evaluation_args", "export_args", "common_args", "logging_args")
@@ -186,7 +204,7 @@ def main():
         st = state_for(case["cfg"], out)
         st["model_path"] = "/models/My-Model"
         st["tokenizer"] = tok if case.get("tokenizer") else None
-        del calls[:], cmds[:]
+        del calls[:], cmds[:], hub[:]
         rec = {"id": case["id"], "cfg": case["cfg"], "tokenizer": bool(case.get("tokenizer"))}
         try:
             st = rcli.quantize_step(st)
@@ -205,6 +223,7 @@ def main():
             st = rcli.model_card_step(st)
             st = rcli.save_step(st)
             rec["saved"] = sorted(os.listdir(st["export_args"].output_path))
+            rec["hub_calls"] = mpg.jsonable(hub, tags)
             readme = open(os.path.join(st["export_args"].output_path, "README.md")).read()
             rec["readme_sha256"] = hashlib.sha256(readme.encode()).hexdigest()
             gold["readme"].setdefault(st["quant_args"].method, readme)

@@ -133,7 +133,21 @@ def test_quantize_and_save_steps_replay_the_reference(case, workdir):
         open(out_file, "w").write("gguf")
         return out_file
 
+    import huggingface_hub
+    hub = []
+
+    def create_repo(**kw):
+        hub.append({"call": "create_repo", "kwargs": kw})
+        return "https://huggingface.co/" + kw["repo_id"]
+
+    def upload_folder(**kw):
+        kw = dict(kw)
+        kw["folder_files"] = sorted(os.listdir(kw.pop("folder_path")))
+        hub.append({"call": "upload_folder", "kwargs": kw})
+        return "commit-url"
+    os.environ.pop("HF_TOKEN", None)
     with patch.object(LLMCompressorQuantizer, "_oneshot", engine), \
+            patch.object(huggingface_hub, "create_repo", create_repo), patch.object(huggingface_hub, "upload_folder", upload_folder), \
             patch.object(gguf_file, "convert_hf_to_f16_gguf", convert), patch.object(gguf_file, "quantize_gguf", quantize):
         if case["id"] in REFERENCE_DEFECTS:
             assert REFERENCE_DEFECTS[case["id"]] in case["message"]          # what the reference does: crash
@@ -167,6 +181,7 @@ def test_quantize_and_save_steps_replay_the_reference(case, workdir):
         st = cli.model_card_step(st)
         st = cli.save_step(st)
         assert sorted(os.listdir(st["export_args"].output_path)) == case["saved"]
+        assert hub == case["hub_calls"]          # push_to_hub: same create_repo / upload_folder calls, same uploaded files
         # the model card: byte for byte the README the reference wrote (huggingface_hub template + front matter)
         readme = open(os.path.join(st["export_args"].output_path, "README.md")).read()
         assert readme == GOLD["readme"][st["quant_args"].method]
