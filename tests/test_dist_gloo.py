@@ -109,3 +109,27 @@ def test_row_split_and_placement():
     place = assign_devices([100, 90, 10, 10, 5], 2)
     loads = [sum(s for s, d in zip([100, 90, 10, 10, 5], place) if d == k) for k in range(2)]
     assert abs(loads[0] - loads[1]) <= 10
+
+
+def test_triangular_area_bounds_and_layer_key_check():
+    """Host helpers of the multi-GPU path: the row / column ranges the 2 x 2 distributed chain hands to the ranks are
+    128-aligned, cover [0, n) and carry equal triangular work; a checkpoint with tensors the driver would drop raises."""
+    import pytest
+    import torch
+    from quantool_b200.engine.pipeline import GPTQLayerQuantizer, _check_layer_keys
+    for n, parts in ((14336, 8), (7168, 4), (4096, 2), (14336, 3)):
+        for grow in (True, False):
+            b = GPTQLayerQuantizer._area_bounds(n, parts, grow)
+            assert b[0] == 0 and b[-1] == n and len(b) == parts + 1 and all(x <= y for x, y in zip(b, b[1:]))
+            assert all(x % 128 == 0 for x in b[:-1])
+            # work of a range: rows weighted by their index (grow) or by what is left to their right (shrink)
+            w = [(hi * hi - lo * lo) if grow else ((n - lo) ** 2 - (n - hi) ** 2) for lo, hi in zip(b, b[1:])]
+            assert max(w) <= 1.35 * (sum(w) / parts), (n, parts, grow, w)
+    ok = {f"model.layers.0.{k}": torch.zeros(1) for k in ("self_attn.q_proj.weight", "input_layernorm.weight",
+                                                          "self_attn.rotary_emb.inv_freq")}
+    ok["model.norm.weight"] = torch.zeros(1)
+    _check_layer_keys(ok)
+    with pytest.raises(ValueError, match="unsupported decoder-layer tensors"):
+        _check_layer_keys({**ok, "model.layers.0.self_attn.q_proj.bias": torch.zeros(1)})
+    with pytest.raises(ValueError, match="unsupported decoder-layer tensors"):
+        _check_layer_keys({**ok, "model.layers.1.self_attn.q_norm.weight": torch.zeros(1)})
