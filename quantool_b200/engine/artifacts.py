@@ -90,11 +90,37 @@ class QuantizedModel:
         if split.is_sharded:
             with open(os.path.join(dest, "model.safetensors.index.json"), "w") as f:
                 json.dump({"metadata": split.metadata, "weight_map": split.tensor_to_filename}, f, indent=2, sort_keys=True)
+        if getattr(self, "recipe", None):
+            with open(os.path.join(dest, "recipe.yaml"), "w") as f:
+                f.write(recipe_yaml(self.recipe))
         if self.source_dir and os.path.isdir(self.source_dir):
             for fn in os.listdir(self.source_dir):
                 if fn.startswith("tokenizer") or fn in ("special_tokens_map.json", "generation_config.json", "vocab.json",
                                                         "merges.txt"):
                     shutil.copy(os.path.join(self.source_dir, fn), dest)
+
+
+_MODIFIER_NAMES = {"gptq": "GPTQModifier", "awq": "AWQModifier", "smoothquant": "SmoothQuantModifier"}
+_MODIFIER_FIELDS = {"gptq": ("targets", "ignore", "scheme", "block_size", "dampening_frac", "actorder"),
+                    "awq": ("targets", "ignore", "scheme", "duo_scaling"),
+                    "smoothquant": ("smoothing_strength",)}
+
+
+def recipe_yaml(modifiers) -> str:
+    """`recipe.yaml`, the record of the applied recipe llm-compressor's `oneshot` leaves next to the weights
+    (`default_stage: default_modifiers: <ModifierClass>: {fields}`; layout restated from published llm-compressor
+    output directories - informational, no consumer parses it, unpinned)."""
+    import yaml
+    mods = {}
+    for m in modifiers:
+        fields = {}
+        for k in _MODIFIER_FIELDS[m.kind]:
+            v = getattr(m, k)
+            if v is None:
+                continue
+            fields[k] = [v] if k == "targets" and isinstance(v, str) else (list(v) if isinstance(v, (list, tuple)) else v)
+        mods[_MODIFIER_NAMES[m.kind]] = fields
+    return yaml.safe_dump({"default_stage": {"default_modifiers": mods}}, sort_keys=False)
 
 
 def autogptq_view(weight_packed: torch.Tensor, weight_scale: torch.Tensor, weight_zero_point: Optional[torch.Tensor],

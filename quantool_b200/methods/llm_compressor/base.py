@@ -331,6 +331,7 @@ class LLMCompressorQuantizer(BaseQuantizer):
         d = pipeline.Dist()
         qm = artifacts.QuantizedModel(cfg, res.tensors, qcfg, source_dir=src, writer=(d.rank == 0))
         qm.stats = res
+        qm.recipe = list(mods)              # written as recipe.yaml next to the weights, as oneshot does
         if save_compressed:
             qm.save_pretrained(output_dir, save_compressed=True)      # rank 0 writes; the other ranks hold no tensors
         if d.on:

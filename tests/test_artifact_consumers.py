@@ -162,6 +162,20 @@ def test_sharded_artifact_loads_in_transformers(tmp_path):
     assert set(back) == set(tensors) and all(torch.equal(back[k], tensors[k]) for k in tensors)
 
 
+def test_recipe_yaml_is_written_next_to_the_weights(tmp_path):
+    import yaml
+    from quantool_b200.engine import artifacts
+    from quantool_b200.methods.llm_compressor.base import Modifier
+    qm = artifacts.QuantizedModel({"model_type": "llama"}, {"w": torch.zeros(4)}, {"quant_method": "compressed-tensors"})
+    qm.recipe = [Modifier(kind="smoothquant", smoothing_strength=0.8), Modifier(kind="gptq", scheme="W8A8", dampening_frac=0.05)]
+    qm.save_pretrained(str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == ["config.json", "model.safetensors", "recipe.yaml"]
+    mods = yaml.safe_load(open(tmp_path / "recipe.yaml"))["default_stage"]["default_modifiers"]
+    assert list(mods) == ["SmoothQuantModifier", "GPTQModifier"] and mods["SmoothQuantModifier"] == {"smoothing_strength": 0.8}
+    assert mods["GPTQModifier"] == {"targets": ["Linear"], "ignore": ["lm_head"], "scheme": "W8A8", "block_size": 128,
+                                    "dampening_frac": 0.05}
+
+
 def unpermute_qk(w, n_head):
     """Inverse of gguf_file._permute_qk (what a GGUF consumer applies to attn_q / attn_k)."""
     out_dim = w.shape[0]
