@@ -224,10 +224,13 @@ class LLMCompressorQuantizer(BaseQuantizer):
         max_len = oneshot_kwargs.get("max_seq_length")     # explicit: truncates everything; default: tokenizer only
         tok_len = max_len or 384                           # llm-compressor DatasetArguments default for tokenization
         shuffle = oneshot_kwargs.get("shuffle_calibration_samples", True)
+        text_col = oneshot_kwargs.get("text_column") or "text"      # oneshot's `text_column`, `tokenizer` are honoured
         if ds is None and oneshot_kwargs.get("dataset_path"):
             ds = self._load_dataset_path(oneshot_kwargs["dataset_path"], oneshot_kwargs)
         if isinstance(ds, str):
             ds = self._load_dataset_id(ds, oneshot_kwargs)
+        if oneshot_kwargs.get("preprocessing_func") is not None and hasattr(ds, "map"):
+            ds = ds.map(oneshot_kwargs["preprocessing_func"])       # oneshot's per-row hook, applied before tokenization
         if ds is None:
             raise ValueError("no calibration data: pass `dataset` (token-id tensor, list of token lists, or a "
                              "datasets.Dataset with `input_ids` or `text`) or a local `dataset_path`")
@@ -237,11 +240,13 @@ class LLMCompressorQuantizer(BaseQuantizer):
             cols = set(getattr(ds, "column_names", []) or [])
             if "input_ids" in cols:
                 rows = [list(r) for r in ds["input_ids"]]
-            elif "text" in cols:
-                from transformers import AutoTokenizer
-                tok = self.last_tokenizer or AutoTokenizer.from_pretrained(source_dir or self.model_id)
+            elif text_col in cols:
+                tok = oneshot_kwargs.get("tokenizer") or self.last_tokenizer
+                if tok is None or isinstance(tok, str):
+                    from transformers import AutoTokenizer
+                    tok = AutoTokenizer.from_pretrained(tok or source_dir or self.model_id)
                 self.last_tokenizer = tok
-                rows = [tok(t, truncation=True, max_length=tok_len)["input_ids"] for t in ds["text"]]
+                rows = [tok(t, truncation=True, max_length=tok_len)["input_ids"] for t in ds[text_col]]
             elif isinstance(ds, (list, tuple)):
                 rows = [list(r) for r in ds]
             else:
@@ -365,6 +370,13 @@ class LLMCompressorQuantizer(BaseQuantizer):
                 raise ValueError(f"{key}={kw[key]!r} is not supported")
         if kw.get("calibration_dataloader") is not None:
             raise ValueError("`calibration_dataloader` is not supported: pass `dataset` or `dataset_path`")
+        for key in ("data_collator", "recipe_args", "stage", "processor"):
+            if kw.get(key) is not None:
+                raise ValueError(f"`{key}` is not supported by the sm_100a engine")
+        if kw.get("streaming"):
+            raise ValueError("`streaming` datasets are not supported: calibration rows are materialised")
+        if kw.get("precision") not in (None, "auto"):
+            raise ValueError(f"precision={kw['precision']!r} is not supported: the checkpoint's own dtype is used ('auto')")
         if kw.get("pad_to_max_length") or kw.get("concatenate_data"):
             raise ValueError("pad_to_max_length / concatenate_data are not supported: samples are calibrated at their "
                              "own length")

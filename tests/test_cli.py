@@ -276,3 +276,27 @@ def test_chat_rows_equal_the_reference_golden(tmp_path):
     tok.chat_template = None
     assert has_chat_template(tok) == gold["has_chat_template"]["without_template"]
     assert render_chat_row(dict(gold["no_template_row"]["row"]), tok) == gold["no_template_row"]["rendered"]
+
+
+def test_text_column_and_tokenizer_keys_are_honoured(tmp_path):
+    """`text_column` and `tokenizer` are `oneshot` parameters the reference forwards (ref base.py:118-124)."""
+    import datasets
+    from quantool_b200.methods.llm_compressor.gptq import GPTQ
+    tok = _chat_tokenizer(tmp_path)
+    ds = datasets.Dataset.from_list([{"body": "the thin thing"}, {"body": "in the inn"}])
+    q = GPTQ(model_id="org/m")
+    rows = q._token_ids({"dataset": ds, "text_column": "body", "tokenizer": tok, "shuffle_calibration_samples": False}, None)
+    assert [r.tolist() for r in rows] == [tok("the thin thing")["input_ids"], tok("in the inn")["input_ids"]]
+    assert q.last_tokenizer is tok
+    with pytest.raises(ValueError, match="unsupported calibration dataset"):
+        GPTQ(model_id="org/m")._token_ids({"dataset": ds, "tokenizer": tok}, None)      # no `text` column
+
+
+def test_preprocessing_func_runs_before_tokenization(tmp_path):
+    import datasets
+    from quantool_b200.methods.llm_compressor.gptq import GPTQ
+    tok = _chat_tokenizer(tmp_path)
+    ds = datasets.Dataset.from_list([{"q": "the", "a": "inn"}])
+    rows = GPTQ(model_id="m")._token_ids({"dataset": ds, "tokenizer": tok, "shuffle_calibration_samples": False,
+                                          "preprocessing_func": lambda ex: {"text": ex["q"] + " " + ex["a"]}}, None)
+    assert rows.tolist() == [tok("the inn")["input_ids"]]

@@ -244,6 +244,18 @@ def test_unsupported_recipe_keys_raise():
             chk([Modifier(kind="gptq", scheme="W4A16")], kw)
 
 
+def test_oneshot_keys_that_cannot_be_honoured_raise():
+    import pytest
+    from quantool_b200.methods.llm_compressor.base import LLMCompressorQuantizer, Modifier
+    chk = LLMCompressorQuantizer._check_supported
+    m = [Modifier(kind="gptq", scheme="W4A16")]
+    chk(m, {"precision": "auto", "streaming": False, "batch_size": 4, "text_column": "body"})
+    for bad in ({"data_collator": object()}, {"streaming": True}, {"precision": "float16"}, {"stage": "s"},
+                {"recipe_args": {"a": 1}}, {"processor": object()}, {"pad_to_max_length": True}):
+        with pytest.raises(ValueError):
+            chk(m, bad)
+
+
 def test_ignore_patterns():
     import pytest
     from quantool_b200.engine.pipeline import _ignored_linears
