@@ -51,6 +51,49 @@ class Modifier:
     duo_scaling: bool = True
 
 
+_MODIFIER_KINDS = {"GPTQModifier": "gptq", "AWQModifier": "awq", "SmoothQuantModifier": "smoothquant"}
+
+
+def parse_recipe(recipe) -> List[Modifier]:
+    """An explicit `recipe=` (ref base.py:81,132-135 hands it to `oneshot` untouched) as a list of `Modifier`s.
+    Accepted: `Modifier` objects (one or a list), and llm-compressor's YAML recipe layout - a path, a YAML string or
+    the parsed dict `{<stage>: {<group>_modifiers: {GPTQModifier | AWQModifier | SmoothQuantModifier: {fields}}}}`,
+    which is also what this engine writes as `recipe.yaml`.  Unknown modifiers or fields raise: nothing is dropped."""
+    if isinstance(recipe, Modifier):
+        return [recipe]
+    if isinstance(recipe, (list, tuple)) and all(isinstance(m, Modifier) for m in recipe):
+        return list(recipe)
+    if isinstance(recipe, (str, os.PathLike)):
+        import yaml
+        text = os.fspath(recipe)
+        if os.path.exists(text):
+            with open(text) as f:
+                text = f.read()
+        recipe = yaml.safe_load(text)
+    if not isinstance(recipe, dict):
+        raise TypeError("recipe must be quantool_b200 Modifier objects or an llm-compressor style YAML recipe "
+                        "(llm-compressor modifier instances cannot be interpreted without llm-compressor)")
+    known = {f.name for f in Modifier.__dataclass_fields__.values()} - {"kind"}
+    mods: List[Modifier] = []
+    for stage, groups in recipe.items():
+        if not isinstance(groups, dict):
+            raise ValueError(f"recipe stage {stage!r} holds no modifier groups")
+        for group, entries in groups.items():
+            for cls, fields in (entries or {}).items():
+                if cls not in _MODIFIER_KINDS:
+                    raise ValueError(f"recipe modifier {cls!r} is not implemented ({sorted(_MODIFIER_KINDS)} are)")
+                fields = dict(fields or {})
+                extra = sorted(set(fields) - known)
+                if extra:
+                    raise ValueError(f"{cls}: unsupported recipe fields {extra}")
+                if isinstance(fields.get("targets"), list) and len(fields["targets"]) == 1:
+                    fields["targets"] = fields["targets"][0]
+                mods.append(Modifier(kind=_MODIFIER_KINDS[cls], **fields))
+    if not mods:
+        raise ValueError("the recipe holds no modifiers")
+    return mods
+
+
 class LLMCompressorQuantizer(BaseQuantizer):
     """Shared logic for the calibration-based quantizers."""
 
@@ -306,11 +349,7 @@ class LLMCompressorQuantizer(BaseQuantizer):
         from ...engine import artifacts, llama, pipeline, schemes
         if not torch.cuda.is_available():
             raise RuntimeError("the sm_100a quantization engine needs a CUDA device (there is no CPU fallback)")
-        mods = recipe if isinstance(recipe, (list, tuple)) else [recipe]
-        for m in mods:
-            if not isinstance(m, Modifier):
-                raise TypeError("recipe entries must be quantool_b200 Modifier objects (llm-compressor modifier "
-                                "instances / YAML recipe paths are not interpretable without llm-compressor)")
+        mods = parse_recipe(recipe)
         self._check_supported(mods, kw)
         cfg, sd, src = self._load_model(model)
         shape = llama.LlamaShape.from_hf_config(cfg)

@@ -320,3 +320,35 @@ def test_llama_config_validation_and_llama3_rope():
     assert torch.allclose(cos, want.cos(), atol=1e-6) and torch.allclose(sin, want.sin(), atol=1e-6)
     plain, _ = llama.rope_tables(llama.SHAPES["llama-3.2-1b"], 64, "cpu", torch.float32)
     assert not torch.allclose(cos, plain, atol=1e-3)      # the scaling matters below 2048 positions too
+
+
+def test_yaml_recipes_round_trip_and_unknown_fields_raise(tmp_path):
+    """`recipe=` accepts llm-compressor's YAML layout (and the `recipe.yaml` this engine writes); nothing in it is
+    silently dropped."""
+    import pytest
+    from quantool_b200.engine import artifacts
+    from quantool_b200.methods.llm_compressor.base import Modifier, parse_recipe
+    mods = [Modifier(kind="smoothquant", smoothing_strength=0.8),
+            Modifier(kind="gptq", scheme="W8A8", dampening_frac=0.05, actorder="group", ignore=["lm_head", "re:.*down_proj"])]
+    text = artifacts.recipe_yaml(mods)
+    assert parse_recipe(text) == mods
+    p = tmp_path / "recipe.yaml"
+    p.write_text(text)
+    assert parse_recipe(str(p)) == mods and parse_recipe(mods) == mods and parse_recipe(mods[1]) == [mods[1]]
+    upstream_style = """
+quant_stage:
+  quant_modifiers:
+    GPTQModifier:
+      targets: [Linear]
+      ignore: [lm_head]
+      scheme: W4A16
+      dampening_frac: 0.1
+"""
+    (m,) = parse_recipe(upstream_style)
+    assert m.kind == "gptq" and m.scheme == "W4A16" and m.dampening_frac == 0.1 and m.targets == "Linear"
+    with pytest.raises(ValueError, match="unsupported recipe fields"):
+        parse_recipe("s:\n  g_modifiers:\n    GPTQModifier:\n      scheme: W4A16\n      offload_hessians: true\n")
+    with pytest.raises(ValueError, match="not implemented"):
+        parse_recipe("s:\n  g_modifiers:\n    SparseGPTModifier:\n      sparsity: 0.5\n")
+    with pytest.raises(TypeError):
+        parse_recipe(object())
