@@ -307,3 +307,59 @@ print("VIEWS_OK")
     if "No module named 'vllm'" in r.stderr:
         pytest.skip("vLLM not installed")
     assert "VIEWS_OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+@pytest.mark.parametrize("method,level,mk", [("gptq", "W4A16", {"actorder": "group"}), ("smoothquant", "W8A8", {}),
+                                             ("awq", "W4A16_ASYM", {})])
+def test_plugin_host_path_end_to_end_with_a_stub_engine(tmp_path, monkeypatch, method, level, mk):
+    """Everything `Plugin.quantize()` does on the HOST - key routing, recipe, checkpoint and calibration loading, the
+    call into the engine, quantization_config, artifact directory (weights, config, recipe.yaml, tokenizer files),
+    model card, `save_pretrained` - with only `engine.pipeline.quantize_model_*` replaced: here (no GPU) a stub that
+    returns artifact tensors computed by the CPU oracle.  The directory it leaves must load in transformers.  The
+    GPU twin of this test (tests/test_zz_consumers_gpu.py) runs the same flow on the CUDA engine."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU stand-in for the GPU twin")
+    import yaml
+    from safetensors.torch import save_file
+    import quantool_b200.methods  # noqa: F401
+    from quantool_b200 import QuantizerRegistry
+    from quantool_b200.engine import llama, pipeline
+    from _tiny import write_tiny_tokenizer
+    shape = tiny_shape()
+    sd = llama.random_state_dict(shape, seed=3)
+    mdir = tmp_path / "tiny-llama"
+    mdir.mkdir()
+    save_file(sd, str(mdir / "model.safetensors"), metadata={"format": "pt"})
+    json.dump(shape.to_hf_config(), open(mdir / "config.json", "w"))
+    write_tiny_tokenizer(str(mdir))
+    calls = []
+
+    def engine(kind):
+        def run(shape_, host_sd, token_ids, args, dev, fmt="pack-quantized", **kw):
+            calls.append((kind, fmt, kw, token_ids))
+            assert set(host_sd) == set(sd) and args.num_bits == (8 if level == "W8A8" else 4)
+            tensors, _ = oracle_artifact(shape_, host_sd, level, mk.get("actorder"))
+            return pipeline.ModelQuantResult(tensors=tensors)
+        return run
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(pipeline, "quantize_model_gptq", engine("gptq"))
+    monkeypatch.setattr(pipeline, "quantize_model_awq", engine("awq"))
+    ids = torch.randint(0, shape.vocab_size, (12, 128), generator=torch.Generator().manual_seed(1234))
+    q = QuantizerRegistry.create(method, model_id="org/tiny-llama")
+    out = q.quantize(model=str(mdir), level=level, dataset=ids, num_calibration_samples=8, max_seq_length=96,
+                     output_dir=str(tmp_path / "out"), method_kwargs=mk)
+    monkeypatch.undo()                       # the consumers below see the real (CUDA-less) torch again
+    (kind, fmt, kw, token_ids), = calls
+    assert kind == ("awq" if method == "awq" else "gptq") and tuple(token_ids.shape) == (8, 96)
+    assert fmt == ("int-quantized" if level == "W8A8" else "pack-quantized")
+    if method == "smoothquant":
+        assert kw["smooth_strength"] == 0.5
+    files = sorted(os.listdir(out))
+    assert {"config.json", "model.safetensors", "recipe.yaml", "tokenizer.json", "tokenizer_config.json"} <= set(files)
+    mods = yaml.safe_load(open(os.path.join(out, "recipe.yaml")))["default_stage"]["default_modifiers"]
+    assert list(mods) == {"gptq": ["GPTQModifier"], "awq": ["AWQModifier"], "smoothquant": ["SmoothQuantModifier", "GPTQModifier"]}[method]
+    check_loads_in_transformers(out, {}, 1.0, shape.vocab_size)
+    q.save_model_card(str(tmp_path / "saved"))
+    q.save_pretrained(str(tmp_path / "saved"))
+    assert {"README.md", "config.json", "model.safetensors", "recipe.yaml"} <= set(os.listdir(tmp_path / "saved"))
