@@ -413,3 +413,20 @@ def test_lean_block_kernel_division_is_correctly_rounded(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "div_by_check.c"), "-lm"])
     r = subprocess.run([exe, "5000000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout + r.stderr
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no gcc")
+def test_c_oracle_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    """The checker itself is checked: oracle/ggml_quants.c built with -fsanitize=address,undefined and driven over
+    every block type (tests/oracle_sanitize.c) reports nothing - the bytes the GPU is compared with do not depend on
+    out-of-bounds reads or undefined arithmetic."""
+    exe = str(tmp_path / "oracle_sanitize")
+    r = subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        "-fno-omit-frame-pointer", "-ffp-contract=off", "-pthread", "-Wno-unused-function", "-o", exe,
+                        os.path.join(ROOT, "tests", "oracle_sanitize.c"), os.path.join(ROOT, "oracle", "ggml_quants.c"), "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "sanitizer" in (r.stderr or "").lower():
+        pytest.skip("sanitizer runtime not available")
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip() == "ok" and "runtime error" not in r.stderr, (r.stdout + r.stderr)[-3000:]
