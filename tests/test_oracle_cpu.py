@@ -430,3 +430,25 @@ def test_c_oracle_is_clean_under_address_and_ub_sanitizers(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == "ok" and "runtime error" not in r.stderr, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
+def test_cuda_kquant_device_math_is_clean_under_sanitizers(tmp_path):
+    """PRODUCT code under ASan + UBSan: the __host__ __device__ phase functions of csrc/gguf_kquant.cuh (what the
+    K-quant / IQ4_NL kernels execute per thread), run on the host through tests/host_emul.cu - no out-of-bounds
+    access to the staged arrays, no undefined shifts / conversions, on ordinary, tiny and sparse inputs."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "host_emul_sanitize")
+    cmd = [nvcc, "-O1", "-g", "-std=c++17", "-Wno-deprecated-gpu-targets"]
+    for flag in ("-fsanitize=address", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-ffp-contract=off"):
+        cmd += ["-Xcompiler", flag]
+    cmd += ["-I", os.path.join(ROOT, "quantool_b200", "csrc"), "-I", os.path.join(ROOT, "include"), "-o", exe,
+            os.path.join(ROOT, "tests", "host_emul_sanitize.cu"), os.path.join(ROOT, "tests", "host_emul.cu"),
+            "-Xlinker", "-lasan", "-Xlinker", "-lubsan"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and ("lasan" in r.stderr or "lubsan" in r.stderr):
+        pytest.skip("sanitizer runtime not available")
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:protect_shadow_gap=0")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == "ok" and "runtime error" not in r.stderr, (r.stdout + r.stderr)[-3000:]
