@@ -452,3 +452,39 @@ def test_cuda_kquant_device_math_is_clean_under_sanitizers(tmp_path):
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:protect_shadow_gap=0")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and r.stdout.strip() == "ok" and "runtime error" not in r.stderr, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
+def test_cuda_kquant_device_math_on_host_across_input_classes():
+    """The same host run of the kernels' phase functions against the C oracle over 17 input classes x 6 block types:
+    heavy tails, one-sided, sparse, constant, two-valued, exact ties, ramps, 1e-20 .. 1e12 magnitudes and denormals.
+    (Beyond ~1e19 the fp16 block scale overflows on both sides and the bytes are garbage; an f16 GGUF cannot hold
+    such values, so that range is outside the path's domain.)"""
+    test_cuda_kquant_device_math_on_host_equals_oracle("Q4_K")          # builds tests/_build/libhost_emul.so if stale
+    from oracle import ggml_quants as oq
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libhost_emul.so"))
+    rng = np.random.default_rng(12345)
+    n, k = 24, 2048
+    sgn = rng.choice([-1.0, 1.0], (n, k))
+    classes = {
+        "normal": rng.standard_normal((n, k)), "weights": rng.standard_normal((n, k)) * 0.02,
+        "uniform": rng.uniform(-1, 1, (n, k)), "laplace": rng.laplace(0, 1, (n, k)),
+        "cauchy": np.clip(rng.standard_cauchy((n, k)), -1e4, 1e4), "lognormal": rng.lognormal(0, 2, (n, k)) * sgn,
+        "positive": np.abs(rng.standard_normal((n, k))), "negative": -np.abs(rng.standard_normal((n, k))),
+        "tiny": rng.standard_normal((n, k)) * 1e-20, "denormal": rng.standard_normal((n, k)) * 1e-40,
+        "large": rng.standard_normal((n, k)) * 1e12,
+        "sparse": rng.standard_normal((n, k)) * (rng.uniform(0, 1, (n, k)) < 0.05),
+        "grid": rng.integers(-8, 8, (n, k)) * 0.125, "constant": np.full((n, k), 0.3),
+        "two_values": rng.choice([0.25, -0.75], (n, k)),
+        "outliers": rng.standard_normal((n, k)) + 100 * (rng.uniform(0, 1, (n, k)) < 0.01),
+        "ties": np.round(rng.standard_normal((n, k)) * 4) / 4,
+    }
+    for name, x in classes.items():
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        for qtype in ("IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"):
+            ref = oq.quantize(x, qtype)
+            out = np.zeros_like(ref)
+            units = x.size // (32 if qtype == "IQ4_NL" else 256)
+            getattr(L, "emul_" + qtype.lower().replace("_k", "_K"))(ctypes.c_void_p(x.ctypes.data),
+                                                                  ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(units))
+            assert np.array_equal(out, ref), (name, qtype)
