@@ -454,19 +454,10 @@ def test_cuda_kquant_device_math_is_clean_under_sanitizers(tmp_path):
     assert r.returncode == 0 and r.stdout.strip() == "ok" and "runtime error" not in r.stderr, (r.stdout + r.stderr)[-3000:]
 
 
-@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
-def test_cuda_kquant_device_math_on_host_across_input_classes():
-    """The same host run of the kernels' phase functions against the C oracle over 17 input classes x 6 block types:
-    heavy tails, one-sided, sparse, constant, two-valued, exact ties, ramps, 1e-20 .. 1e12 magnitudes and denormals.
-    (Beyond ~1e19 the fp16 block scale overflows on both sides and the bytes are garbage; an f16 GGUF cannot hold
-    such values, so that range is outside the path's domain.)"""
-    test_cuda_kquant_device_math_on_host_equals_oracle("Q4_K")          # builds tests/_build/libhost_emul.so if stale
-    from oracle import ggml_quants as oq
-    L = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libhost_emul.so"))
+def _input_classes(n, k):
     rng = np.random.default_rng(12345)
-    n, k = 24, 2048
     sgn = rng.choice([-1.0, 1.0], (n, k))
-    classes = {
+    return {
         "normal": rng.standard_normal((n, k)), "weights": rng.standard_normal((n, k)) * 0.02,
         "uniform": rng.uniform(-1, 1, (n, k)), "laplace": rng.laplace(0, 1, (n, k)),
         "cauchy": np.clip(rng.standard_cauchy((n, k)), -1e4, 1e4), "lognormal": rng.lognormal(0, 2, (n, k)) * sgn,
@@ -479,6 +470,30 @@ def test_cuda_kquant_device_math_on_host_across_input_classes():
         "outliers": rng.standard_normal((n, k)) + 100 * (rng.uniform(0, 1, (n, k)) < 0.01),
         "ties": np.round(rng.standard_normal((n, k)) * 4) / 4,
     }
+
+
+def test_k_quant_restatements_agree_across_input_classes():
+    """The C oracle and the independent numpy restatement give the same bytes on all 17 input classes (heavy tails,
+    one-sided, sparse, constant, ties, 1e-40 .. 1e12): the restated llama.cpp algorithm is not ambiguous there."""
+    from oracle import ggml_quants as oq, ggml_quants_np as onp
+    for name, x in _input_classes(3, 1024).items():
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        for qtype in ("IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"):
+            with np.errstate(all="ignore"):
+                twin = onp.QUANTIZE[qtype](x)
+            assert np.array_equal(oq.quantize(x, qtype), twin), (name, qtype)
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
+def test_cuda_kquant_device_math_on_host_across_input_classes():
+    """The same host run of the kernels' phase functions against the C oracle over 17 input classes x 6 block types:
+    heavy tails, one-sided, sparse, constant, two-valued, exact ties, ramps, 1e-20 .. 1e12 magnitudes and denormals.
+    (Beyond ~1e19 the fp16 block scale overflows on both sides and the bytes are garbage; an f16 GGUF cannot hold
+    such values, so that range is outside the path's domain.)"""
+    test_cuda_kquant_device_math_on_host_equals_oracle("Q4_K")          # builds tests/_build/libhost_emul.so if stale
+    from oracle import ggml_quants as oq
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libhost_emul.so"))
+    classes = _input_classes(24, 2048)
     for name, x in classes.items():
         x = np.ascontiguousarray(x, dtype=np.float32)
         for qtype in ("IQ4_NL", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K"):
