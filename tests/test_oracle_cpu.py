@@ -503,3 +503,25 @@ def test_cuda_kquant_device_math_on_host_across_input_classes():
             getattr(L, "emul_" + qtype.lower().replace("_k", "_K"))(ctypes.c_void_p(x.ctypes.data),
                                                                   ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(units))
             assert np.array_equal(out, ref), (name, qtype)
+
+
+def test_simple_types_equal_gguf_py_across_input_classes():
+    """Q8_0 / Q4_0 / Q4_1 / Q5_0 / Q5_1: C oracle == gguf-py byte for byte on all 17 input classes.
+    One corner is excluded on purpose: NEGATIVE ZEROS.  ggml's scalar loops (`if (amax < fabsf(v))`, `if (v < min)`,
+    both strict, starting from +0 / FLT_MAX) give an all-zero block the scale -0.0 and a zero minimum the sign of
+    the first zero met, whereas gguf-py's vectorised `argmax` / `min` take the sign of whichever zero numpy picks;
+    the two differ only in the sign bit of a zero `d` / `m` field (no dequantized value changes).  The oracle keeps
+    ggml's loop semantics - asserted below."""
+    from gguf import GGMLQuantizationType as T
+    from gguf import quants as gq
+    from oracle import ggml_quants as oq
+    for name, x in _input_classes(6, 1024).items():
+        x = np.ascontiguousarray(x, dtype=np.float32) + np.float32(0.0)          # -0.0 -> +0.0
+        for qtype in ("Q8_0", "Q4_0", "Q4_1", "Q5_0", "Q5_1"):
+            with np.errstate(all="ignore"):
+                ref = gq.quantize(x, getattr(T, qtype))
+            assert np.array_equal(oq.quantize(x, qtype), ref), (name, qtype)
+    z = np.zeros((1, 32), dtype=np.float32)
+    z[0, 0] = -0.0
+    assert oq.quantize(z, "Q4_0")[0, :2].tolist() == [0x00, 0x80]     # d = (+0) / -8 = -0.0, whatever the zeros' signs
+    assert oq.quantize(-z, "Q4_0")[0, :2].tolist() == [0x00, 0x80]
