@@ -525,3 +525,17 @@ def test_simple_types_equal_gguf_py_across_input_classes():
     z[0, 0] = -0.0
     assert oq.quantize(z, "Q4_0")[0, :2].tolist() == [0x00, 0x80]     # d = (+0) / -8 = -0.0, whatever the zeros' signs
     assert oq.quantize(-z, "Q4_0")[0, :2].tolist() == [0x00, 0x80]
+
+
+@pytest.mark.parametrize("qtype", ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL"])
+def test_dequant_equals_gguf_py_on_arbitrary_bytes(qtype):
+    """Row a16 beyond what a quantizer emits: on random byte patterns (every 6-bit scale combination, denormal / inf /
+    NaN fp16 scales) the oracle's dequantize is bit-identical to gguf-py's, NaN payloads included."""
+    from gguf import GGMLQuantizationType as T
+    from gguf import quants as gq
+    from oracle import ggml_quants as oq
+    be, bb, nblk = oq.block_elems(qtype), oq.block_bytes(qtype), 64
+    y = np.random.default_rng(7).integers(0, 256, (5, nblk * bb), dtype=np.uint8)
+    with np.errstate(all="ignore"):
+        ref = gq.dequantize(y, getattr(T, qtype)).astype(np.float32)
+    assert np.array_equal(oq.dequantize(y, qtype, nblk * be).view(np.uint32), ref.view(np.uint32))
