@@ -577,3 +577,40 @@ def test_gptq_oracle_equals_obq_recursion_per_channel_int8_partial_blocks(N, K, 
     assert (saved == og.compress_int8(Qm, s, None, a)).float().mean().item() >= 0.999
     flips = (saved.long() != codes).float().mean().item()
     assert 0.002 < flips < 0.05, flips                      # the save-time re-derivation is not the identity for int8
+
+
+def test_gptq_oracle_equals_obq_recursion_static_actorder():
+    """actorder="weight" (compressed-tensors "static"): group parameters come from the ORIGINAL column groups and are
+    never re-fitted, the columns are only visited in order of decreasing diag(H); no g_idx is stored."""
+    from compressed_tensors.quantization import ActivationOrdering
+    from oracle import gptq as og
+    g = torch.Generator().manual_seed(0)
+    N, K, T = 48, 384, 3072
+    W = (torch.randn((N, K), generator=g) * 0.02).to(torch.bfloat16)
+    X = torch.randn((4, T // 4, K), generator=g).to(torch.bfloat16)
+    X[..., 7] *= 10
+    X[..., 100] *= 3
+    H, n = og.make_empty_hessian(K), 0
+    for b in range(4):
+        H, n = og.accumulate_hessian(X[b:b + 1], H, n)
+    a = og.scheme_weight_args("W4A16")
+    a.actorder = ActivationOrdering.WEIGHT
+    _, Wq, s, _, gi, _, perm = og.quantize_weight(W, H, a, return_hinv=True)
+    assert gi is None and perm is not None
+    codes_o, _, _ = og.compress_packed(Wq, s, None, None, a)
+    Wd, Hd = W.double().clone(), H.double().clone()
+    blk = Wd.view(N, K // 128, 128)
+    scale_g = torch.maximum(blk.amin(2).clamp(max=0).abs(), blk.amax(2).clamp(min=0).abs()) / 7.5
+    Wd, Hd, group_of = Wd[:, perm], Hd[perm][:, perm], (torch.arange(K) // 128)[perm]
+    Hd += 0.01 * torch.mean(torch.diag(Hd)) * torch.eye(K, dtype=torch.float64)
+    Hinv = torch.linalg.inv(Hd)
+    codes = torch.zeros((N, K), dtype=torch.int64)
+    for i in range(K):
+        sc = scale_g[:, group_of[i]]
+        w = Wd[:, i].clone()
+        c = torch.clamp(torch.round(w / sc), -8, 7)
+        codes[:, i] = c.long()
+        d = Hinv[i, i]
+        Wd[:, i:] -= ((w - c * sc) / d)[:, None] * Hinv[i, i:][None, :]
+        Hinv = Hinv - torch.outer(Hinv[:, i], Hinv[i, :]) / d
+    assert (codes_o.long() == codes[:, torch.argsort(perm)]).float().mean().item() >= 0.999
