@@ -291,6 +291,7 @@ def test_autogptq_autoawq_views_equal_vllm_packers(tmp_path):
     code = r"""
 import sys, torch
 from vllm.model_executor.layers.quantization.utils import quant_utils as q
+print("VLLM_IMPORTED")
 d = torch.load(sys.argv[1])
 u, zu = d["u"], d["zu"]                       # [K, N] and [G, N] unsigned 4-bit values
 K, N = u.shape
@@ -304,8 +305,8 @@ print("VIEWS_OK")
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     r = subprocess.run([sys.executable, "-c", code, str(tmp_path / "views.pt")], capture_output=True, text=True,
                        timeout=600, env=env, cwd=str(tmp_path))
-    if "No module named 'vllm'" in r.stderr:
-        pytest.skip("vLLM not installed")
+    if "VLLM_IMPORTED" not in r.stdout:
+        pytest.skip("vLLM is not importable here: " + (r.stderr or "").strip().splitlines()[-1][:200] if r.stderr else "vLLM missing")
     assert "VIEWS_OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
 
 
