@@ -364,3 +364,12 @@ def test_plugin_host_path_end_to_end_with_a_stub_engine(tmp_path, monkeypatch, m
     q.save_model_card(str(tmp_path / "saved"))
     q.save_pretrained(str(tmp_path / "saved"))
     assert {"README.md", "config.json", "model.safetensors", "recipe.yaml"} <= set(os.listdir(tmp_path / "saved"))
+
+
+def test_only_the_writer_rank_touches_the_output_directory(tmp_path):
+    """Multi-process runs: every rank builds a QuantizedModel, rank 0 alone holds the tensors and writes."""
+    from quantool_b200.engine import artifacts
+    qm = artifacts.QuantizedModel({"model_type": "llama"}, {}, {"quant_method": "compressed-tensors"}, writer=False)
+    qm.recipe = []
+    qm.save_pretrained(str(tmp_path / "out"))
+    assert not os.path.exists(tmp_path / "out")
