@@ -69,21 +69,15 @@ SHIM_SCRIPT = '''
 import json, os, sys, types
 sys.path.insert(0, {root!r})
 import datasets, transformers                      # before the accelerate stub: both probe for the real package
-sys.path.insert(0, "/root/reference/src")
+sys.path.insert(0, {refsrc!r})
 for name in ("accelerate", "accelerate.commands", "accelerate.commands.config"):
     sys.modules[name] = types.ModuleType(name)
 acc = types.ModuleType("accelerate.commands.config.config_args")
 acc.cache_dir = "/tmp"                              # the reference's only use of accelerate: a stray import (cli.py:4)
 sys.modules["accelerate.commands.config.config_args"] = acc
 
-import quantool.methods                             # the REFERENCE package: registers what it can (gguf needs llama.cpp)
+import quantool.methods        # the REFERENCE package (scratch copy + the shim package quantool/methods/zz_b200)
 from quantool.core.registry import QuantizerRegistry
-# ---- INTEGRATION.md section 1, verbatim ----
-import quantool_b200.methods
-from quantool_b200 import QuantizerRegistry as B200
-for name in ("gptq", "awq", "smoothquant", "gguf"):
-    QuantizerRegistry._plugins[name] = B200._plugins[name]
-# --------------------------------------------
 import quantool.entrypoints.cli as rcli             # the REFERENCE CLI steps, unmodified
 from quantool.args import (CalibrationArguments, CommonArguments, EvaluationArguments, ExportArguments,
                            LoggingArguments, ModelArguments, QuantizationArguments)
@@ -147,14 +141,26 @@ print("SHIM_JSON " + json.dumps(out))
 
 @pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="the reference checkout is not on this machine")
 def test_integration_shim_lets_the_reference_cli_drive_our_plugins(tmp_path):
-    """INTEGRATION.md section 1 executed for real: the REFERENCE package is imported, its registry entries are
-    replaced by quantool_b200's classes with the documented loop, and the reference's unmodified CLI steps
+    """INTEGRATION.md section 1 executed for real: a scratch copy of the REFERENCE package gets the documented shim
+    sub-package, the reference's own loader imports it, and the reference's unmodified CLI steps
     (validate_args -> quantize -> generate_readme -> save_model) then run a GPTQ and a GGUF configuration.  Only the
     engine entry points are recorders here (no GPU in this container)."""
     import json
+    # a scratch copy of the reference package (outside this repository) with the shim added the way INTEGRATION.md
+    # tells a maintainer to: one new sub-package of quantool/methods, imported last by the reference's own loader
+    refsrc = tmp_path / "refsrc"
+    shutil.copytree("/root/reference/src/quantool", refsrc / "quantool")
+    shim = refsrc / "quantool" / "methods" / "zz_b200"
+    shim.mkdir()
+    (shim / "__init__.py").write_text(
+        "from quantool.core.registry import QuantizerRegistry\n"
+        "import quantool_b200.methods\n"
+        "from quantool_b200 import QuantizerRegistry as B200\n\n"
+        "for name in (\"gptq\", \"awq\", \"smoothquant\", \"gguf\"):\n"
+        "    QuantizerRegistry._plugins[name] = B200._plugins[name]\n")
     env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
-    r = subprocess.run([sys.executable, "-c", SHIM_SCRIPT.format(root=ROOT, work=str(tmp_path))], capture_output=True,
-                       text=True, cwd=str(tmp_path), env=env, timeout=600)
+    r = subprocess.run([sys.executable, "-c", SHIM_SCRIPT.format(root=ROOT, work=str(tmp_path), refsrc=str(refsrc))],
+                       capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=600)
     got = [l for l in r.stdout.splitlines() if l.startswith("SHIM_JSON ")]
     assert got, (r.stdout + r.stderr)[-3000:]
     o = json.loads(got[-1][len("SHIM_JSON "):])
