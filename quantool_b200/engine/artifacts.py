@@ -119,6 +119,8 @@ def recipe_yaml(modifiers) -> str:
             if v is None:
                 continue
             fields[k] = [v] if k == "targets" and isinstance(v, str) else (list(v) if isinstance(v, (list, tuple)) else v)
+        if m.kind == "awq" and m.n_grid != 20:
+            fields["n_grid"] = m.n_grid                 # additive key; upstream's grid is the constant 20
         mods[_MODIFIER_NAMES[m.kind]] = fields
     return yaml.safe_dump({"default_stage": {"default_modifiers": mods}}, sort_keys=False)
 
