@@ -3,12 +3,13 @@
 Same step sequence as the reference's CLI (ref/src/quantool/entrypoints/cli.py:22-98, 102-444;
 SURVEY.md §3.1): setup_logging -> validate_args -> load_model -> quantize -> generate_readme ->
 save_model, driven by a dict threaded through the steps.  The reference's YAML configs
-(`ref/test_{gptq,awq,gguf}_config.yaml`) parse unchanged.  Differences, all forced by this being
-an offline, single-node engine: the model must resolve to a local directory (or the HF cache) and
-calibration data comes from `dataset_path` (a `.pt` tensor of token ids, a `.json`/`.jsonl` file of
-`{"input_ids": [...]}` / `{"text": ...}` rows) or from `datasets.load_dataset` when it is reachable.
+(`ref/test_{gptq,awq,gguf}_config.yaml`) parse unchanged, and the steps are replayed against traces of
+the reference's own steps (tests/test_cli_golden.py): both calibration modes (`load_in_pipeline: true` - load,
+shuffle, sample, `preprocess_fn`, chat templates here - or a `dataset_path` / `dataset_id` descriptor the
+plugin resolves), messages, state keys, model card, save / push rules.  Differences, all forced by this being
+an offline engine: the model must resolve to a local directory (or the local HF cache), hub datasets must be in
+the local `datasets` cache; additive: a `.pt` file of token ids as `dataset_path`.
 """
-import json
 import logging
 import os
 import sys
